@@ -1,0 +1,309 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (dev container only).
+
+TEST INFRASTRUCTURE.  Usage:  python oracle/make_golden.py [--out tests/golden]
+
+/root/reference does not exist on the GPU box, so its outputs are committed here as small
+fixtures together with this script.  Everything is single-threaded float32 torch-CPU with
+fixed seeds; inputs are stored next to outputs so no RNG has to be reproduced elsewhere.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle.ref_import import import_reference, REFERENCE_ROOT  # noqa: E402
+
+MSE = "tensor_mseminmax_symmetric"
+
+
+def run_mse_with_internals(ref, x, bits, num_attempts):
+    """Call the reference projection, then recover (index, scale, codes) by re-evaluating the
+    reference's own expressions for the chosen candidate (source/quantization.py:125-144)."""
+    xq = ref.quantize_tensor(x, bits, MSE, num_attempts=num_attempts)
+    q = 2 ** (bits - 1)
+    denom = 2 * q - 1
+    mx = torch.max(torch.abs(x.min()), torch.abs(x.max()))
+    grid = torch.linspace(0.2 * mx.item(), 1.2 * mx.item(), num_attempts)
+    found = None
+    for i in range(num_attempts):
+        scale = 2 * grid[i] / denom
+        cand = torch.clamp(torch.round(x / scale), -q, q - 1) * scale
+        if torch.equal(cand, xq) or (torch.isnan(xq).all() and torch.isnan(cand).all()):
+            found = i
+            break
+    assert found is not None
+    scale = 2 * grid[found] / denom
+    codes = torch.clamp(torch.round(x / scale), -q, q - 1)
+    return xq, found, float(scale), codes.to(torch.int8)
+
+
+def projection_cases(ref):
+    g = torch.Generator().manual_seed(1234)
+    cases = []
+
+    def add(name, x, bits, n=200):
+        cases.append((name, x.contiguous().float(), bits, n))
+
+    for bits in (2, 3, 4, 6, 8):
+        add(f"gauss64x134_b{bits}", torch.randn(64, 134, generator=g), bits)
+    add("gauss9x134_b4", torch.randn(9, 134, generator=g), 4)
+    add("gauss128x278_b4", torch.randn(128, 278, generator=g) * 0.05, 4)
+    add("gauss256x566_b4", torch.randn(256, 566, generator=g) * 3.0, 4)
+    add("gauss64x134_b4_n1000", torch.randn(64, 134, generator=g), 4, 1000)
+    add("gauss64x134_b4_n7", torch.randn(64, 134, generator=g), 4, 7)
+    add("uniform_b4", torch.rand(40, 77, generator=g) - 0.5, 4)
+    add("positive_only_b4", torch.rand(33, 65, generator=g) + 0.1, 4)
+    add("negative_only_b3", -torch.rand(33, 65, generator=g) - 0.1, 3)
+    x = torch.randn(64, 134, generator=g)
+    x[7, 11] = 25.0
+    add("one_outlier_b4", x, 4)
+    add("constant_0p3_b4", torch.full((16, 16), 0.3), 4)
+    add("ties_b4", torch.tensor([[0.5, 1.5, 2.5, -0.5, -7.5, 7.0, 3.5, -2.5]]), 4)
+    add("single_element_b4", torch.tensor([[1.7]]), 4)
+    add("ragged_1x513_b4", torch.randn(1, 513, generator=g), 4)
+    add("ragged_257x3_b6", torch.randn(257, 3, generator=g), 6)
+    add("tiny_values_b4", torch.randn(32, 32, generator=g) * 1e-20, 4)
+    add("huge_values_b4", torch.randn(32, 32, generator=g) * 1e18, 4)
+    add("all_zero_b4", torch.zeros(8, 8), 4)
+    # grid-valued input (re-projection is not idempotent)
+    y = ref.quantize_tensor(torch.randn(64, 134, generator=g), 4, MSE)
+    add("regrid_b4", y, 4)
+    out = {}
+    meta = []
+    for name, x, bits, n in cases:
+        xq, idx, scale, codes = run_mse_with_internals(ref, x, bits, n)
+        out[f"{name}/x"] = x.numpy()
+        out[f"{name}/xq"] = xq.numpy()
+        out[f"{name}/codes"] = codes.numpy()
+        out[f"{name}/idx_scale"] = np.array([idx, scale], dtype=np.float64)
+        meta.append(dict(name=name, bits=bits, num_attempts=n, shape=list(x.shape)))
+    # the other tensor_* schemes (source/quantization.py:48-66, 91-106)
+    for scheme in ("tensor_minmax", "tensor_symmetric", "tensor_affine"):
+        for bits in (1, 2, 4, 8) if scheme == "tensor_minmax" else (2, 4, 8):
+            x = torch.randn(48, 100, generator=g) * 0.7 + 0.1
+            y = ref.quantize_tensor(x, bits, scheme)
+            name = f"{scheme}_b{bits}"
+            out[f"{name}/x"] = x.numpy()
+            out[f"{name}/xq"] = y.float().numpy()
+            meta.append(dict(name=name, bits=bits, scheme=scheme, shape=list(x.shape)))
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
+def contraction_cases(ref):
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    meta = []
+    for name, (I, J, K, R) in dict(c3_small=(12, 10, 9, 17), c3_l1=(64, 64, 9, 134), c3_odd=(33, 20, 49, 40)).items():
+        W = torch.randn(I, J, K, generator=g) * 0.06
+        A, B, C = (torch.randn(d, R, generator=g) for d in (I, J, K))
+        out[f"{name}/W"], out[f"{name}/A"], out[f"{name}/B"], out[f"{name}/C"] = (t.numpy() for t in (W, A, B, C))
+        out[f"{name}/G0"] = (B.T @ B * (C.T @ C)).numpy()
+        out[f"{name}/G1"] = (A.T @ A * (C.T @ C)).numpy()
+        out[f"{name}/G2"] = (A.T @ A * (B.T @ B)).numpy()
+        out[f"{name}/F0"] = torch.einsum("abc,cr,br->ar", W, C, B).numpy()
+        out[f"{name}/F1"] = torch.einsum("abc,cr,ar->br", W, C, A).numpy()
+        out[f"{name}/F2"] = torch.einsum("abc,br,ar->cr", W, B, A).numpy()
+        out[f"{name}/err"] = np.array([ref.squared_relative_diff(W, torch.einsum("ir,jr,kr->ijk", A, B, C))])
+        meta.append(dict(name=name, ndim=3, dims=[I, J, K], rank=R))
+    for name, (I, J, R) in dict(c2_small=(40, 24, 15), c2_rect=(96, 200, 48)).items():
+        W = torch.randn(I, J, generator=g) * 0.02
+        A, B = torch.randn(I, R, generator=g), torch.randn(J, R, generator=g)
+        out[f"{name}/W"], out[f"{name}/A"], out[f"{name}/B"] = W.numpy(), A.numpy(), B.numpy()
+        out[f"{name}/G0"] = (B.T @ B).numpy()
+        out[f"{name}/G1"] = (A.T @ A).numpy()
+        out[f"{name}/F0"] = (W @ B).numpy()
+        out[f"{name}/F1"] = (W.T @ A).numpy()
+        out[f"{name}/err"] = np.array([ref.squared_relative_diff(W, A @ B.T)])
+        meta.append(dict(name=name, ndim=2, dims=[I, J], rank=R))
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
+def config1_weight():
+    """BASELINE config 1 input: resnet18(weights=None) under seed 42,
+    layer1.0.conv1 reshaped to (64, 64, 9)."""
+    import torchvision
+    torch.manual_seed(42)
+    m = torchvision.models.resnet18(weights=None)
+    return m.layer1[0].conv1.weight.detach().reshape(64, 64, 9).contiguous()
+
+
+def admm_iteration_cases(ref):
+    """One reference `admm_iteration` call per case, replayed one inner iteration at a time
+    (`max_iter=2` runs exactly one iteration, source/admm.py:55) so every iterate is recorded."""
+    out = {}
+    meta = []
+    W = config1_weight()
+    R = 134
+    specs = [
+        dict(name="l1_mode0_b4", mode=0, bits=4, iters=120, qscheme=MSE),
+        dict(name="l1_mode2_b4", mode=2, bits=4, iters=60, qscheme=MSE),
+        dict(name="l1_mode1_b3", mode=1, bits=3, iters=40, qscheme=MSE),
+        dict(name="l1_mode0_b8_minmax", mode=0, bits=8, iters=30, qscheme="tensor_minmax"),
+    ]
+    for sp in specs:
+        fac = ref.init_factors(W, R, init="random", device=None, seed=42)
+        A, B, C = fac
+        m = sp["mode"]
+        if m == 0:
+            G = B.T @ B * (C.T @ C); F = torch.einsum("abc,cr,br->ar", W, C, B)
+        elif m == 1:
+            G = A.T @ A * (C.T @ C); F = torch.einsum("abc,cr,ar->br", W, C, A)
+        else:
+            G = A.T @ A * (B.T @ B); F = torch.einsum("abc,br,ar->cr", W, B, A)
+        H = fac[m].clone()
+        U = torch.zeros_like(H)
+        name = sp["name"]
+        out[f"{name}/H0"], out[f"{name}/F"], out[f"{name}/G"] = H.numpy().copy(), F.numpy(), G.numpy()
+        Hs, Us = [], []
+        for it in range(sp["iters"]):
+            H, U = ref.admm_iteration(H, U, F, G, max_iter=2, eps=1e-8, bits=sp["bits"], qscheme=sp["qscheme"])
+            Hs.append(H.numpy().copy())
+            Us.append(U.numpy().copy())
+        keep = sorted(set(list(range(0, 12)) + list(range(12, sp["iters"], 9)) + [sp["iters"] - 1]))
+        out[f"{name}/keep"] = np.array(keep)
+        out[f"{name}/H"] = np.stack([Hs[k] for k in keep])
+        out[f"{name}/U"] = np.stack([Us[k] for k in keep])
+        # every iterate's H as grid values is large; store all of them as float16-safe codes instead:
+        # the grid value / min positive spacing is recovered in the tests from H itself.
+        out[f"{name}/H_all_sum"] = np.array([float(np.abs(h).astype(np.float64).sum()) for h in Hs])
+        # and one genuine multi-iteration call to pin the loop/in-place semantics
+        fac2 = ref.init_factors(W, R, init="random", device=None, seed=42)
+        H2 = fac2[m].clone(); U2 = torch.zeros_like(H2)
+        Hn, Un = ref.admm_iteration(H2, U2, F, G, max_iter=sp["iters"] + 1, eps=1e-8, bits=sp["bits"],
+                                    qscheme=sp["qscheme"])
+        assert Un is U2
+        assert np.array_equal(Hn.numpy(), Hs[-1]) and np.array_equal(Un.numpy(), Us[-1])
+        meta.append(dict(name=name, bits=sp["bits"], qscheme=sp["qscheme"], iters=sp["iters"], mode=m, rank=R))
+    # 2-D case, larger ridge system than rows
+    g = torch.Generator().manual_seed(5)
+    Wm = torch.randn(96, 40, generator=g) * 0.02
+    Rm = 30
+    A, B = torch.randn(96, Rm, generator=g), torch.randn(40, Rm, generator=g)
+    G = B.T @ B; F = Wm @ B
+    H = A.clone(); U = torch.zeros_like(H)
+    out["mat_mode0_b4/H0"], out["mat_mode0_b4/F"], out["mat_mode0_b4/G"] = H.numpy().copy(), F.numpy(), G.numpy()
+    Hs, Us = [], []
+    for it in range(25):
+        H, U = ref.admm_iteration(H, U, F, G, max_iter=2, eps=1e-8, bits=4, qscheme=MSE)
+        Hs.append(H.numpy().copy()); Us.append(U.numpy().copy())
+    out["mat_mode0_b4/keep"] = np.arange(25)
+    out["mat_mode0_b4/H"] = np.stack(Hs); out["mat_mode0_b4/U"] = np.stack(Us)
+    out["mat_mode0_b4/H_all_sum"] = np.array([float(np.abs(h).astype(np.float64).sum()) for h in Hs])
+    meta.append(dict(name="mat_mode0_b4", bits=4, qscheme=MSE, iters=25, mode=0, rank=Rm))
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
+def outer_loop_cases(ref):
+    """scripts/factorize.py:207-310 replayed verbatim with the reference's functions."""
+    out = {}
+    meta = []
+    W = config1_weight()
+    out["config1/W"] = W.numpy()
+
+    def run3(W, R, bits, qscheme, sweeps, max_iter_admm, seed):
+        A, B, C = ref.init_factors(W, R, init="random", device=None, seed=seed)
+        init = [A.numpy().copy(), B.numpy().copy(), C.numpy().copy()]
+        U_A, U_B, U_C = torch.zeros_like(A), torch.zeros_like(B), torch.zeros_like(C)
+        loss, lossq = [], []
+        for _ in range(sweeps):
+            G = B.T @ B * (C.T @ C)
+            F = torch.einsum("abc,cr,br->ar", W, C, B)
+            A, U_A = ref.admm_iteration(A, U_A, F, G, max_iter=max_iter_admm, eps=1e-8, bits=bits, qscheme=qscheme)
+            Aq = ref.quantize_tensor(A, qscheme=qscheme, bits=bits)
+            G = A.T @ A * (C.T @ C)
+            F = torch.einsum("abc,cr,ar->br", W, C, A)
+            B, U_B = ref.admm_iteration(B, U_B, F, G, max_iter=max_iter_admm, eps=1e-8, bits=bits, qscheme=qscheme)
+            Bq = ref.quantize_tensor(B, qscheme=qscheme, bits=bits)
+            G = A.T @ A * (B.T @ B)
+            F = torch.einsum("abc,br,ar->cr", W, B, A)
+            C, U_C = ref.admm_iteration(C, U_C, F, G, max_iter=max_iter_admm, eps=1e-8, bits=bits, qscheme=qscheme)
+            Cq = ref.quantize_tensor(C, qscheme=qscheme, bits=bits)
+            loss.append(ref.squared_relative_diff(W, torch.einsum("ir,jr,kr->ijk", A, B, C)))
+            lossq.append(ref.squared_relative_diff(W, torch.einsum("ir,jr,kr->ijk", Aq, Bq, Cq)))
+        return init, [A, B, C], [U_A, U_B, U_C], loss, lossq
+
+    t0 = time.time()
+    for name, kw in dict(config1_full=dict(sweeps=2, max_iter_admm=1000),
+                         config1_short=dict(sweeps=6, max_iter_admm=60)).items():
+        init, fac, duals, loss, lossq = run3(W, 134, 4, MSE, seed=42, **kw)
+        for m in range(3):
+            out[f"{name}/init{m}"] = init[m]
+            out[f"{name}/fac{m}"] = fac[m].numpy()
+            out[f"{name}/dual{m}"] = duals[m].numpy()
+        out[f"{name}/loss"] = np.array(loss)
+        out[f"{name}/lossq"] = np.array(lossq)
+        meta.append(dict(name=name, W="config1", rank=134, bits=4, qscheme=MSE, seed=42, **kw))
+        print(name, loss, f"{time.time() - t0:.0f}s", flush=True)
+    # matrix branch (scripts/factorize.py:269-310)
+    g = torch.Generator().manual_seed(9)
+    Wm = torch.randn(128, 48, generator=g) * 0.02
+    out["mat/W"] = Wm.numpy()
+    R = 17
+    A, B = ref.init_factors(Wm, R, init="random", device=None, seed=3)
+    out["mat/init0"], out["mat/init1"] = A.numpy().copy(), B.numpy().copy()
+    U_A, U_B = torch.zeros_like(A), torch.zeros_like(B)
+    loss, lossq = [], []
+    for _ in range(5):
+        G = B.T @ B; F = Wm @ B
+        A, U_A = ref.admm_iteration(A, U_A, F, G, max_iter=80, eps=1e-8, bits=4, qscheme=MSE)
+        Aq = ref.quantize_tensor(A, qscheme=MSE, bits=4)
+        G = A.T @ A; F = Wm.T @ A
+        B, U_B = ref.admm_iteration(B, U_B, F, G, max_iter=80, eps=1e-8, bits=4, qscheme=MSE)
+        Bq = ref.quantize_tensor(B, qscheme=MSE, bits=4)
+        loss.append(ref.squared_relative_diff(Wm, A @ B.T))
+        lossq.append(ref.squared_relative_diff(Wm, Aq @ Bq.T))
+    out["mat/fac0"], out["mat/fac1"] = A.numpy(), B.numpy()
+    out["mat/loss"], out["mat/lossq"] = np.array(loss), np.array(lossq)
+    meta.append(dict(name="mat", rank=R, bits=4, qscheme=MSE, seed=3, sweeps=5, max_iter_admm=80))
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
+def rank_table():
+    """source/rank_map.py is pure data; it pins the rank rule (scripts/factorize.py:157-158)."""
+    spec = importlib.util.spec_from_file_location("ref_rank_map", os.path.join(REFERENCE_ROOT, "source", "rank_map.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    table = {}
+    for rate in (1.5, 2, 3, 4):
+        table[str(rate)] = {k: v for k, v in mod.get_rank_map("resnet18", rate).items() if k.startswith("layer") or k == "conv1"}
+    return table
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    torch.set_num_threads(1)
+    os.makedirs(args.out, exist_ok=True)
+    ref = import_reference()
+    jobs = dict(projection=projection_cases, contractions=contraction_cases,
+                admm_iteration=admm_iteration_cases, outer_loop=outer_loop_cases)
+    for name, fn in jobs.items():
+        if args.only and name not in args.only.split(","):
+            continue
+        t0 = time.time()
+        data = fn(ref)
+        np.savez_compressed(os.path.join(args.out, name + ".npz"), **data)
+        print(f"{name}: {len(data)} arrays, {time.time() - t0:.1f}s", flush=True)
+    if not args.only or "rank" in args.only:
+        with open(os.path.join(args.out, "rank_table.json"), "w") as f:
+            json.dump(dict(source="source/rank_map.py get_rank_map('resnet18', rate)", table=rank_table()), f, indent=1, sort_keys=True)
+    with open(os.path.join(args.out, "PROVENANCE.json"), "w") as f:
+        json.dump(dict(generator="oracle/make_golden.py", reference=REFERENCE_ROOT, torch=torch.__version__,
+                       numpy=np.__version__, threads=1, cpu_capability=torch.backends.cpu.get_cpu_capability()), f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
