@@ -1,0 +1,450 @@
+// admm_loop.cu - the persistent ADMM inner loop (admmq_admm_iteration) and the ridge-system
+// inverse (admmq_spd_inverse).  Replaces admm_iteration() of source/admm.py:51-67.
+//
+// One cooperative launch (one CTA per SM) runs ALL max_iter-1 inner iterations; per iteration
+//   P1  H_ls = RHS . Minv            float32 FFMA tile product, RHS = F + rho (H + U)   (:56-57)
+//       epilogue: abs-max key of V = H_ls - U                                          (:59, q.py:129)
+//   --- device-wide barrier
+//   P2  per-candidate squared-error sums of the clip search over V (search.cuh)         (q.py:136-139)
+//   --- device-wide barrier
+//   P3  argmin -> scale; H = Q(V); U += H - H_ls; residual sums; next RHS              (:59-63, q.py:141-144)
+//   --- device-wide barrier, then the exit test r < eps && s < eps                       (:64-65)
+// State (H, U, F, H_ls, RHS, Minv) stays L2 resident for the whole call: per iteration the
+// algorithmic traffic is 16 B per element of H plus one pass over Minv, all served from L2.
+#include <algorithm>
+#include "search.cuh"
+#include "spd_inverse.cuh"
+
+namespace admmq {
+
+constexpr int kKeySlots = 3;
+
+struct LoopHeader {  // start of the workspace; zeroed by cudaMemsetAsync before every call
+  unsigned int barrier_inv;
+  unsigned int barrier_loop;
+  int status;  // ADMMQ_E_NOT_PD from the inverse
+  float rho;
+  unsigned int keys[kKeySlots][4];  // rotating {max key, ~min key, -, -} of V
+};
+
+struct LoopParams {
+  float* H;
+  float* U;
+  const float* F;
+  int I, R, Rp;
+  int max_iter;
+  float eps;
+  int bits, scheme, Nc;
+  int8_t* codes;
+  admmq_loop_report* report;
+  LoopHeader* hdr;
+  unsigned long long* cand;  // [kKeySlots][kMaxCandidates]
+  double* slots;             // [gridDim.x][4]
+  float* Hls;                // I x Rp
+  float* RHS;                // I x Rp (pad columns stay zero)
+  const float* Minv;         // R x Rp
+};
+
+template <int BM, int BN>
+struct __align__(16) GemmSmem {
+  float a[16][BM + 4];
+  float b[16][BN + 4];
+};
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// P1: every CTA takes tiles round-robin; 256 threads as (BM/TM) x (BN/TN).
+template <int BM, int BN, int TM, int TN>
+__device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned int* keys) {
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == kThreads, "thread tiling must cover the CTA");
+  const int t = threadIdx.x, tx = t % TX, ty = t / TX;
+  const int I = p.I, R = p.R, Rp = p.Rp;
+  const int tilesN = (R + BN - 1) / BN, tilesM = (I + BM - 1) / BM;
+  const int arow = t >> 2, akq = (t & 3) * 4;                 // A loader: BM rows x 4 float4
+  const int brow = t / (BN / 4), bc4 = (t % (BN / 4)) * 4;    // B loader: 16 rows x BN/4 float4
+  unsigned int kmax = 0u, kinv = 0u;
+  for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
+    const int i0 = (tile / tilesN) * BM, n0 = (tile % tilesN) * BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+      for (int n = 0; n < TN; ++n) acc[m][n] = 0.0f;
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+    auto fetch = [&](int k0) {
+      ra = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb = ra;
+      if (t < BM * 4 && i0 + arow < I && k0 + akq < Rp) ra = ldcg4(p.RHS + (size_t)(i0 + arow) * Rp + k0 + akq);
+      if (t < 4 * BN && k0 + brow < R && n0 + bc4 < Rp) rb = __ldg(reinterpret_cast<const float4*>(p.Minv + (size_t)(k0 + brow) * Rp + n0 + bc4));
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < R; k0 += 16) {
+      __syncthreads();
+      if (t < BM * 4) {
+        gs.a[akq + 0][arow] = ra.x;
+        gs.a[akq + 1][arow] = ra.y;
+        gs.a[akq + 2][arow] = ra.z;
+        gs.a[akq + 3][arow] = ra.w;
+      }
+      if (t < 4 * BN) *reinterpret_cast<float4*>(&gs.b[brow][bc4]) = rb;
+      __syncthreads();
+      if (k0 + 16 < R) fetch(k0 + 16);
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float av[TM], bv[TN];
+#pragma unroll
+        for (int m = 0; m < TM; ++m) av[m] = gs.a[kk][ty * TM + m];
+#pragma unroll
+        for (int n = 0; n < TN; ++n) bv[n] = gs.b[kk][tx * TN + n];
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+          for (int n = 0; n < TN; ++n) acc[m][n] = fmaf(av[m], bv[n], acc[m][n]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+      for (int n = 0; n < TN; ++n) {
+        const int i = i0 + ty * TM + m, c = n0 + tx * TN + n;
+        if (i < I && c < R) {
+          p.Hls[(size_t)i * Rp + c] = acc[m][n];
+          const float v = sub_rn(acc[m][n], __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
+          const unsigned int k = float_key(v);
+          kmax = max(kmax, k);
+          kinv = max(kinv, ~k);
+        }
+      }
+  }
+  kmax = warp_max_u32(kmax);
+  kinv = warp_max_u32(kinv);
+  if ((t & 31) == 0 && (kmax | kinv) != 0u) {
+    atomicMax(&keys[0], kmax);
+    atomicMax(&keys[1], kinv);
+  }
+}
+
+__global__ void __launch_bounds__(kInvThreads, 1) k_spd_inverse(InvParams p) {
+  __shared__ InvSmem sm;
+  GridBarrier bar;
+  bar.init(p.barrier);
+  spd_inverse_body(p, sm, bar);
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
+  __shared__ SearchSmem sm;
+  __shared__ GemmSmem<BM, BN> gs;
+  __shared__ double sred[4][kThreads];
+  const int t = threadIdx.x;
+  LoopHeader* hdr = p.hdr;
+  admmq_loop_report rep;
+  rep.iterations = 0;
+  rep.status = 0;
+  rep.rho = hdr->rho;
+  rep.scale = 0.0f;
+  rep.r = 0.0f;
+  rep.s = 0.0f;
+  rep.best_index = -1;
+  rep.absmax = 0.0f;
+  if (hdr->status != 0) {  // G + rho I was not positive definite: nothing is touched
+    rep.status = hdr->status;
+    if (blockIdx.x == 0 && t == 0) *p.report = rep;
+    return;
+  }
+  GridBarrier bar;
+  bar.init(&hdr->barrier_loop);
+  const float rho = rep.rho;
+  const int R = p.R, Rp = p.Rp;
+  const long long N = (long long)p.I * R;
+  const long long cs = chunk_size(N, gridDim.x);
+  const long long e0 = min(N, (long long)blockIdx.x * cs), e1 = min(N, e0 + cs);
+  const Levels L = make_levels(p.bits);
+  const float qnan = __int_as_float(0x7fc00000);
+
+  // RHS = F + rho * (H + U) for the first iteration (:56)
+  for (long long e = e0 + t; e < e1; e += kThreads) {
+    const int ei = (int)e, i = ei / R, n = ei - i * R;
+    p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(p.H[e], p.U[e])));
+  }
+  bar.sync();
+
+  for (int j = 1; j < p.max_iter; ++j) {  // range(1, max_iter), :55
+    const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
+    // ---------------- P1
+    gemm_phase<BM, BN, TM, TN>(p, gs, hdr->keys[slot]);
+    if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
+      if (t < 4) hdr->keys[next_slot][t] = 0u;
+      for (int c = t; c < p.Nc; c += kThreads) p.cand[(size_t)next_slot * kMaxCandidates + c] = 0ull;
+    }
+    bar.sync();
+    // ---------------- P2
+    const float tmax = key_float(__ldcg(&hdr->keys[slot][0]));
+    const float tmin = key_float(~__ldcg(&hdr->keys[slot][1]));
+    float absmax = fmaxf(fabsf(tmin), fabsf(tmax));
+    if (tmin != tmin || tmax != tmax) absmax = qnan;
+    rep.absmax = absmax;
+    rep.iterations = j;
+    QParams qp;
+    qp.scheme = p.scheme;
+    qp.bits = p.bits;
+    qp.aux = 0.0f;
+    qp.n = 0.0f;
+    qp.scale = 0.0f;
+    bool degenerate = false;
+    if (p.scheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) {
+      degenerate = !(absmax > 0.0f) || isinf(absmax);
+      if (!degenerate) {
+        unsigned long long* cand = p.cand + (size_t)slot * kMaxCandidates;
+        const float* Hls = p.Hls;
+        const float* U = p.U;
+        cta_candidate_sums(
+            [Hls, U, R, Rp](long long e) {
+              const int ei = (int)e, i = ei / R, n = ei - i * R;  // I*R < 2^31 is checked on the host
+              return sub_rn(__ldcg(Hls + (size_t)i * Rp + n), __ldcg(U + e));
+            },
+            e0, e1, absmax, p.Nc, L, (double)N, cand, sm);
+        bar.sync();
+        // ---------------- P3
+        rep.best_index = cta_best_candidate(cand, p.Nc, absmax, (double)N, sm);
+        qp.scale = scale_of(clip_candidate(make_clip_grid(absmax, p.Nc), rep.best_index), L);
+      }
+    } else {
+      degenerate = (absmax != absmax) || isinf(absmax);
+      qp = params_from_minmax(p.scheme, p.bits, tmin, tmax, L);
+    }
+    rep.scale = qp.scale;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (long long e = e0 + t; e < e1; e += kThreads) {
+      const int ei = (int)e, i = ei / R, n = ei - i * R;
+      const float hls = __ldcg(p.Hls + (size_t)i * Rp + n);
+      const float u = __ldcg(p.U + e);
+      const float v = sub_rn(hls, u);
+      float code = 0.0f;
+      const float hq = degenerate ? qnan : quantize_value(v, qp, L, code);   // H = Q(H_ls - U)   (:59)
+      const float d1 = sub_rn(hq, hls);
+      const float un = add_rn(u, d1);                                        // U += H - H_ls     (:60)
+      const float d2 = sub_rn(hq, __ldcg(p.H + e));
+      s0 += (double)mul_rn(d1, d1);  // sum (H - H_ls)^2     (:62)
+      s1 += (double)mul_rn(hq, hq);  // sum H^2
+      s2 += (double)mul_rn(d2, d2);  // sum (H - H_prev)^2   (:63)
+      s3 += (double)mul_rn(un, un);  // sum U^2
+      p.H[e] = hq;
+      p.U[e] = un;
+      p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(hq, un)));
+      if (p.codes != nullptr) p.codes[e] = (int8_t)code;
+    }
+    if (degenerate) {  // uniform: the reference would carry NaN through every remaining iteration
+      rep.status |= ADMMQ_ST_NONFINITE;
+      rep.r = qnan;
+      rep.s = qnan;
+      break;
+    }
+    sred[0][t] = s0;
+    sred[1][t] = s1;
+    sred[2][t] = s2;
+    sred[3][t] = s3;
+    __syncthreads();
+    for (int s = kThreads / 2; s > 0; s >>= 1) {
+      if (t < s) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sred[q][t] += sred[q][t + s];
+      }
+      __syncthreads();
+    }
+    if (t < 4) p.slots[(size_t)blockIdx.x * 4 + t] = sred[t][0];
+    bar.sync();
+    // ---------------- exit test (:62-65), evaluated identically by every CTA
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int c = t; c < (int)gridDim.x; c += kThreads) {
+      a0 += __ldcg(p.slots + (size_t)c * 4 + 0);
+      a1 += __ldcg(p.slots + (size_t)c * 4 + 1);
+      a2 += __ldcg(p.slots + (size_t)c * 4 + 2);
+      a3 += __ldcg(p.slots + (size_t)c * 4 + 3);
+    }
+    __syncthreads();
+    sred[0][t] = a0;
+    sred[1][t] = a1;
+    sred[2][t] = a2;
+    sred[3][t] = a3;
+    __syncthreads();
+    for (int s = kThreads / 2; s > 0; s >>= 1) {
+      if (t < s) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sred[q][t] += sred[q][t + s];
+      }
+      __syncthreads();
+    }
+    rep.r = div_rn((float)sred[0][0], (float)sred[1][0]);
+    rep.s = div_rn((float)sred[2][0], (float)sred[3][0]);
+    __syncthreads();
+    if (rep.r < p.eps && rep.s < p.eps) {
+      rep.status |= ADMMQ_ST_CONVERGED;
+      break;
+    }
+  }
+  if (blockIdx.x == 0 && t == 0) *p.report = rep;
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct LoopLayout {
+  size_t header, cand, slots, hls, rhs, minv, lw, xw, total;
+  int Rp, nb, Rb;
+};
+
+static LoopLayout loop_layout(int I, int R, int grid) {
+  LoopLayout l;
+  l.Rp = (R + 3) / 4 * 4;
+  l.nb = (R + kNB - 1) / kNB;
+  l.Rb = l.nb * kNB;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) {
+    const size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  l.header = take(sizeof(LoopHeader));
+  l.cand = take((size_t)kKeySlots * kMaxCandidates * sizeof(unsigned long long));
+  l.slots = take((size_t)grid * 4 * sizeof(double));
+  l.rhs = take((size_t)I * l.Rp * sizeof(float));
+  l.hls = take((size_t)I * l.Rp * sizeof(float));
+  l.minv = take((size_t)R * l.Rp * sizeof(float));
+  l.lw = take((size_t)l.Rb * l.Rb * sizeof(double));
+  l.xw = take((size_t)l.Rb * l.Rb * sizeof(double));
+  l.total = off;
+  return l;
+}
+
+static int coop_grid(const DeviceProps& dp) { return dp.sm_count; }
+
+static int launch_spd_inverse(const float* G, int R, float* Minv, int ldm, float* rho_out, int* status,
+                              unsigned int* barrier, double* Lw, double* Xw, int grid, cudaStream_t stream) {
+  InvParams ip;
+  ip.G = G;
+  ip.R = R;
+  ip.nb = (R + kNB - 1) / kNB;
+  ip.Rb = ip.nb * kNB;
+  ip.ldm = ldm;
+  ip.Lw = Lw;
+  ip.Xw = Xw;
+  ip.Minv = Minv;
+  ip.rho_out = rho_out;
+  ip.status = status;
+  ip.barrier = barrier;
+  void* args[] = {&ip};
+  ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_spd_inverse, dim3(grid), dim3(kInvThreads), args, 0, stream));
+  return ADMMQ_OK;
+}
+
+// tile shape for P1: minimise waves * tile cost (relative FFMA efficiencies measured on B200)
+static int pick_tile(int I, int R, int grid) {
+  const int bm[3] = {64, 32, 16}, bn[3] = {64, 32, 32};
+  const double eff[3] = {1.0, 0.55, 0.40};
+  int best = 0;
+  double best_cost = 1e300;
+  for (int c = 0; c < 3; ++c) {
+    const long long tiles = (long long)((I + bm[c] - 1) / bm[c]) * ((R + bn[c] - 1) / bn[c]);
+    const long long waves = (tiles + grid - 1) / grid;
+    const double cost = (double)waves * bm[c] * bn[c] / eff[c];
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+}  // namespace admmq
+
+using namespace admmq;
+
+extern "C" int admmq_padded_ld(int R) { return (R + 3) / 4 * 4; }
+
+extern "C" size_t admmq_spd_inverse_workspace_bytes(int R) {
+  if (R <= 0) return 0;
+  const size_t Rb = (size_t)((R + kNB - 1) / kNB) * kNB;
+  return 256 + 2 * align_up(Rb * Rb * sizeof(double), 256);
+}
+
+extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (G == nullptr || Minv == nullptr || rho_out == nullptr || status == nullptr || R <= 0)
+    return fail(ADMMQ_E_BADARG, "admmq_spd_inverse: bad argument");
+  if (workspace == nullptr || workspace_bytes < admmq_spd_inverse_workspace_bytes(R) || ((uintptr_t)workspace & 255) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_spd_inverse: workspace too small or not 256-byte aligned");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
+  const size_t Rb = (size_t)((R + kNB - 1) / kNB) * kNB;
+  char* ws = (char*)workspace;
+  ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, 256, stream));
+  ADMMQ_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), stream));
+  double* Lw = (double*)(ws + 256);
+  double* Xw = (double*)(ws + 256 + align_up(Rb * Rb * sizeof(double), 256));
+  return launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp), stream);
+}
+
+extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts) {
+  (void)num_attempts;
+  if (I <= 0 || R <= 0) return 0;
+  return loop_layout(I, R, 1024).total;  // sized for any grid up to 1024 CTAs
+}
+
+extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R, int max_iter,
+                                    float eps, int bits, int qscheme, int num_attempts, int8_t* codes,
+                                    admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (H == nullptr || U == nullptr || F == nullptr || G == nullptr || report == nullptr || I <= 0 || R <= 0)
+    return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: null pointer or empty shape");
+  if (bits < 1 || bits > 8) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: bits must be in 1..8, got %d", bits);
+  if (qscheme < 0 || qscheme > 3) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: unknown qscheme %d", qscheme);
+  if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC && (num_attempts < 1 || num_attempts > kMaxCandidates))
+    return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: num_attempts must be in 1..%d", kMaxCandidates);
+  if ((long long)I * R >= (1ll << 31)) return fail(ADMMQ_E_UNSUPPORTED, "admmq_admm_iteration: I*R must be < 2^31");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
+  const int grid = coop_grid(dp);
+  const LoopLayout l = loop_layout(I, R, grid);
+  if (workspace == nullptr || workspace_bytes < l.total || ((uintptr_t)workspace & 255) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_admm_iteration: workspace needs %zu bytes, 256-byte aligned", l.total);
+  char* ws = (char*)workspace;
+  // header + candidate accumulators + RHS (its pad columns must be zero)
+  ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, l.slots, stream));
+  ADMMQ_CUDA_OK(cudaMemsetAsync(ws + l.rhs, 0, (size_t)I * l.Rp * sizeof(float), stream));
+  LoopHeader* hdr = (LoopHeader*)(ws + l.header);
+  if (int e = launch_spd_inverse(G, R, (float*)(ws + l.minv), l.Rp, &hdr->rho, &hdr->status, &hdr->barrier_inv,
+                                 (double*)(ws + l.lw), (double*)(ws + l.xw), grid, stream))
+    return e;
+  LoopParams p;
+  p.H = H;
+  p.U = U;
+  p.F = F;
+  p.I = I;
+  p.R = R;
+  p.Rp = l.Rp;
+  p.max_iter = max_iter;
+  p.eps = eps;
+  p.bits = bits;
+  p.scheme = qscheme;
+  p.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
+  p.codes = codes;
+  p.report = report;
+  p.hdr = hdr;
+  p.cand = (unsigned long long*)(ws + l.cand);
+  p.slots = (double*)(ws + l.slots);
+  p.Hls = (float*)(ws + l.hls);
+  p.RHS = (float*)(ws + l.rhs);
+  p.Minv = (const float*)(ws + l.minv);
+  void* args[] = {&p};
+  const void* fn = nullptr;
+  switch (pick_tile(I, R, grid)) {
+    case 0: fn = (const void*)k_admm_loop<64, 64, 4, 4>; break;
+    case 1: fn = (const void*)k_admm_loop<32, 32, 2, 2>; break;
+    default: fn = (const void*)k_admm_loop<16, 32, 1, 2>; break;
+  }
+  ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
+  return ADMMQ_OK;
+}

@@ -1,0 +1,198 @@
+// numerics.cuh - the float32 recipe of the projection, shared by every kernel that
+// quantizes (and compiled for the host by tests/hostcheck to pin it against the oracle).
+//
+// Follows source/quantization.py:69-144 of the reference operation by operation:
+// IEEE float32 multiply / divide / subtract with round-to-nearest-even and no FMA
+// contraction, `torch.round` = rint (half to even), `torch.linspace` = FMA form
+// (SURVEY App. A.3).  Nothing here may be compiled with --use_fast_math.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define ADMMQ_HD __host__ __device__ __forceinline__
+#else
+#define ADMMQ_HD inline
+#endif
+
+namespace admmq {
+
+// --- explicitly rounded float32 primitives (no contraction on either side) ------------
+ADMMQ_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b;
+  return r;
+#endif
+}
+ADMMQ_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b;
+  return r;
+#endif
+}
+ADMMQ_HD float sub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b;
+  return r;
+#endif
+}
+ADMMQ_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  volatile float r = a / b;
+  return r;
+#endif
+}
+ADMMQ_HD float fma_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+ADMMQ_HD float rint_rn(float a) {
+#if defined(__CUDA_ARCH__)
+  return rintf(a);
+#else
+  return nearbyintf(a);
+#endif
+}
+
+// --- quantizer description -------------------------------------------------------------
+struct Levels {
+  float lo;     // -q            (source/quantization.py:88: q = 2**(bits-1))
+  float hi;     //  q-1
+  float denom;  //  2q-1         (:89 scale_denom)
+  float fast_lo, fast_hi, fast_thr;  // fast-path clamp window and "too close to .5" threshold
+};
+
+ADMMQ_HD Levels make_levels(int bits) {
+  Levels L;
+  const float q = (float)(1 << (bits - 1));
+  L.lo = -q;
+  L.hi = q - 1.0f;
+  L.denom = 2.0f * q - 1.0f;
+  L.fast_lo = -q - 0.25f;
+  L.fast_hi = q - 0.75f;
+  // |x*rcp(s) - x/s| <= |t| * 2^-23 (two roundings) and |fl(x/s) - x/s| <= |t| * 2^-24;
+  // q * 2^-21 leaves a >2.5x margin for |t| <= q + 0.25.
+  L.fast_thr = 0.5f - q * 4.76837158203125e-07f;
+  return L;
+}
+
+// --- candidate grid of quantize_tensor_mse (source/quantization.py:129-131) ----------
+struct ClipGrid {
+  float start, end, step;
+  int n;
+};
+
+ADMMQ_HD ClipGrid make_clip_grid(float absmax, int n) {
+  ClipGrid g;
+  g.n = n;
+  g.start = (float)(0.2 * (double)absmax);
+  g.end = (float)(1.2 * (double)absmax);
+  g.step = n > 1 ? div_rn(sub_rn(g.end, g.start), (float)(n - 1)) : 0.0f;
+  return g;
+}
+
+ADMMQ_HD float clip_candidate(const ClipGrid& g, int i) {
+  if (g.n == 1) return g.start;
+  return (i < g.n / 2) ? fma_rn(g.step, (float)i, g.start) : fma_rn(-g.step, (float)(g.n - 1 - i), g.end);
+}
+
+// scale = 2 * tmax / scale_denom  (source/quantization.py:125)
+ADMMQ_HD float scale_of(float clip, const Levels& L) { return div_rn(mul_rn(2.0f, clip), L.denom); }
+
+// clamp(round(x / scale), -q, q-1)  (source/quantization.py:127) - the exact form
+ADMMQ_HD float code_exact(float x, float scale, const Levels& L) {
+  float k = rint_rn(div_rn(x, scale));
+  k = fminf(fmaxf(k, L.lo), L.hi);
+  return k;
+}
+
+// (x - code*scale)^2 with every intermediate rounded to float32 (:127, :138)
+ADMMQ_HD float sqerr_exact(float x, float scale, const Levels& L) {
+  const float d = sub_rn(x, mul_rn(code_exact(x, scale, L), scale));
+  return mul_rn(d, d);
+}
+
+// Fast path used inside the 200-candidate search: the code is obtained from x * (1/scale)
+// (no division); `frac` returns |t - k| so that the caller can detect the rare inputs whose
+// quotient lies too close to a rounding boundary for the shortcut to be provably equal to
+// code_exact() and redo them with sqerr_exact().  MAGIC rounding = round-half-even for |t| < 2^22.
+ADMMQ_HD float sqerr_fast(float x, float scale, float rcp_scale, const Levels& L, float& frac) {
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23
+  float t = mul_rn(x, rcp_scale);
+  t = fminf(fmaxf(t, L.fast_lo), L.fast_hi);
+  const float k = sub_rn(add_rn(t, MAGIC), MAGIC);
+  frac = fabsf(sub_rn(t, k));
+  const float d = sub_rn(x, mul_rn(k, scale));
+  return mul_rn(d, d);
+}
+
+// --- fixed-point accumulation of the per-candidate squared-error sums --------------------
+// Every element contributes d^2 <= 16 * absmax^2, so sum <= 16 * N * absmax^2 which is mapped to
+// 2^62.  Integer addition is associative: the total does not depend on how many CTAs or in which
+// order the partial sums arrive, and it resolves ~3e-15 of a typical total.
+ADMMQ_HD double fixed_point_unit_inv(double n_elems, float absmax) {
+  const double bound = n_elems * (double)absmax * (double)absmax;  // * 16 folded into 2^58
+  return 288230376151711744.0 /* 2^58 */ / bound;
+}
+ADMMQ_HD double fixed_point_unit(double n_elems, float absmax) {
+  const double bound = n_elems * (double)absmax * (double)absmax;
+  return bound / 288230376151711744.0;
+}
+
+// mean as the reference forms it (:138 `.mean`): float32 total divided by float32 count, where
+// the total is the correctly rounded sum of the float32 squares.
+ADMMQ_HD float mse_from_fixed(long long fixed_sum, double unit, float n_elems_f) {
+  const float total = (float)((double)fixed_sum * unit);
+  return div_rn(total, n_elems_f);
+}
+
+// --- the other tensor_* schemes ---------------------------------------------------------
+struct QParams {
+  int scheme;   // ADMMQ_Q_*
+  float scale;  // mse/symmetric/affine: grid scale; minmax: (max - min)
+  float aux;    // affine: zero point; minmax: min
+  float n;      // minmax: 2^bits - 1
+  int bits;
+};
+
+// min_max_quantize, source/quantization.py:48-66
+ADMMQ_HD float minmax_value(float x, const QParams& p, float& level) {
+  if (p.bits == 1) {
+    const float sgn = (x > 0.0f ? 1.0f : 0.0f) - (x < 0.0f ? 1.0f : 0.0f);  // torch.sign = (0<x)-(x<0)
+    level = sgn;
+    return sub_rn(sgn, 1.0f);
+  }
+  const float unit = div_rn(sub_rn(x, p.aux), p.scale);
+  const float k = floorf(add_rn(mul_rn(unit, p.n), 0.5f));
+  level = k;
+  return add_rn(div_rn(mul_rn(k, p.scale), p.n), p.aux);
+}
+
+// tensor_affine, source/quantization.py:97-106
+ADMMQ_HD float affine_value(float x, const QParams& p, const Levels& L, float& code) {
+  float k = add_rn(rint_rn(div_rn(x, p.scale)), p.aux);
+  k = fminf(fmaxf(k, L.lo), L.hi);
+  code = k;
+  return mul_rn(sub_rn(k, p.aux), p.scale);
+}
+
+// zero point of tensor_affine (:102-103): clamp(int(-q - int(tmin/scale)), -q, q-1), `.int()` truncates
+ADMMQ_HD float affine_zero_point(float tmin, float scale, const Levels& L) {
+  const float t = truncf(div_rn(tmin, scale));
+  float zp = truncf(sub_rn(L.lo, t));
+  zp = fminf(fmaxf(zp, L.lo), L.hi);
+  return zp;
+}
+
+}  // namespace admmq

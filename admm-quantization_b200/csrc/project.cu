@@ -1,0 +1,144 @@
+// project.cu - standalone projection onto the b-bit grid (admmq_project).
+// Replaces quantize_tensor / quantize_tensor_mse / min_max_quantize of
+// source/quantization.py:48-144 for the tensor_* schemes.
+//
+// Three launches on the caller's stream:
+//   k_minmax_keys   min and max of x as order-preserving integer keys (atomicMax)
+//   k_mse_sums      per-candidate squared-error sums (only for tensor_mseminmax_symmetric)
+//   k_apply         argmin (redundantly per CTA) + quantize + codes
+// HBM traffic: x is read 2x (3x for the clip search), xq written once: 12-16 B/element; the
+// clip search itself is ALU work (num_attempts evaluations per element) on staged data.
+#include "search.cuh"
+
+namespace admmq {
+
+struct ProjectHeader {        // lives at the start of the workspace, zeroed by cudaMemsetAsync
+  unsigned int max_key;       // max over float_key(x)
+  unsigned int inv_min_key;   // max over ~float_key(x)  ==  ~min key
+  unsigned int pad[2];
+};
+
+__global__ void __launch_bounds__(kThreads) k_minmax_keys(const float* x, long long n, ProjectHeader* hdr) {
+  unsigned int kmax = 0u, kinv = 0u;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const unsigned int k = float_key(x[i]);
+    kmax = max(kmax, k);
+    kinv = max(kinv, ~k);
+  }
+  kmax = warp_max_u32(kmax);
+  kinv = warp_max_u32(kinv);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&hdr->max_key, kmax);
+    atomicMax(&hdr->inv_min_key, kinv);
+  }
+}
+
+__device__ __forceinline__ void read_minmax(const ProjectHeader* hdr, float& tmin, float& tmax, float& absmax) {
+  tmax = key_float(__ldcg(&hdr->max_key));
+  tmin = key_float(~__ldcg(&hdr->inv_min_key));
+  absmax = fmaxf(fabsf(tmin), fabsf(tmax));  // source/quantization.py:129
+  if (tmin != tmin || tmax != tmax) absmax = __int_as_float(0x7fc00000);
+}
+
+__global__ void __launch_bounds__(kThreads) k_mse_sums(const float* x, long long n, int bits, int Nc,
+                                                      const ProjectHeader* hdr, unsigned long long* cand_sums) {
+  __shared__ SearchSmem sm;
+  float tmin, tmax, absmax;
+  read_minmax(hdr, tmin, tmax, absmax);
+  if (!(absmax > 0.0f) || isinf(absmax)) return;  // all-zero / non-finite input: output is NaN (k_apply)
+  const Levels L = make_levels(bits);
+  const long long cs = chunk_size(n, gridDim.x);
+  const long long e0 = min(n, (long long)blockIdx.x * cs), e1 = min(n, e0 + cs);
+  cta_candidate_sums([x](long long e) { return x[e]; }, e0, e1, absmax, Nc, L, (double)n, cand_sums, sm);
+}
+
+__global__ void __launch_bounds__(kThreads) k_apply(const float* x, long long n, int bits, int scheme, int Nc,
+                                                   const ProjectHeader* hdr, const unsigned long long* cand_sums,
+                                                   const float* tmin_in, const float* tmax_in, float* xq,
+                                                   int8_t* codes, float* info) {
+  __shared__ SearchSmem sm;
+  float tmin, tmax, absmax;
+  read_minmax(hdr, tmin, tmax, absmax);
+  const Levels L = make_levels(bits);
+  QParams p;
+  int best = -1;
+  bool nan_fill = false;
+  if (scheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) {
+    p.scheme = scheme;
+    p.bits = bits;
+    p.aux = 0.0f;
+    p.n = 0.0f;
+    if (!(absmax > 0.0f) || isinf(absmax)) {
+      nan_fill = true;  // reference: scale 0 or inf/NaN -> every output NaN
+      p.scale = __int_as_float(0x7fc00000);
+    } else {
+      best = cta_best_candidate(cand_sums, Nc, absmax, (double)n, sm);
+      p.scale = scale_of(clip_candidate(make_clip_grid(absmax, Nc), best), L);
+    }
+  } else {
+    if (scheme == ADMMQ_Q_AFFINE && tmin_in != nullptr && tmax_in != nullptr) {
+      tmin = *tmin_in;
+      tmax = *tmax_in;
+    }
+    p = params_from_minmax(scheme, bits, tmin, tmax, L);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && info != nullptr) {
+    info[0] = p.scale;
+    info[1] = p.aux;
+    info[2] = (float)best;
+    info[3] = absmax;
+  }
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    float code = 0.0f;
+    float v;
+    if (nan_fill) {
+      v = __int_as_float(0x7fc00000);
+    } else {
+      v = quantize_value(x[i], p, L, code);
+    }
+    xq[i] = v;
+    if (codes != nullptr) codes[i] = (int8_t)code;
+  }
+}
+
+}  // namespace admmq
+
+using namespace admmq;
+
+extern "C" size_t admmq_project_workspace_bytes(int64_t n, int num_attempts) {
+  (void)n;
+  const int nc = num_attempts > 0 ? num_attempts : 1;
+  return align_up(sizeof(ProjectHeader), 256) + align_up((size_t)nc * sizeof(unsigned long long), 256);
+}
+
+extern "C" int admmq_project(const float* x, int64_t n, int bits, int qscheme, int num_attempts,
+                             const float* tmin, const float* tmax, float* xq, int8_t* codes, float* info,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (x == nullptr || xq == nullptr || n <= 0) return fail(ADMMQ_E_BADARG, "admmq_project: null pointer or n <= 0");
+  if (bits < 1 || bits > 8) return fail(ADMMQ_E_BADARG, "admmq_project: bits must be in 1..8, got %d", bits);
+  if (qscheme < 0 || qscheme > 3) return fail(ADMMQ_E_BADARG, "admmq_project: unknown qscheme %d", qscheme);
+  if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC && (num_attempts < 1 || num_attempts > kMaxCandidates))
+    return fail(ADMMQ_E_BADARG, "admmq_project: num_attempts must be in 1..%d, got %d", kMaxCandidates, num_attempts);
+  if (workspace == nullptr || workspace_bytes < admmq_project_workspace_bytes(n, num_attempts) ||
+      ((uintptr_t)workspace & 15) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_project: workspace too small or misaligned");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  ProjectHeader* hdr = (ProjectHeader*)workspace;
+  unsigned long long* cand = (unsigned long long*)((char*)workspace + align_up(sizeof(ProjectHeader), 256));
+  ADMMQ_CUDA_OK(cudaMemsetAsync(workspace, 0, admmq_project_workspace_bytes(n, num_attempts), stream));
+  const long long max_ctas = (long long)dp.sm_count * 8;
+  const int g_stream = (int)std::min<long long>(max_ctas, (n + kThreads * 4 - 1) / (kThreads * 4));
+  k_minmax_keys<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, hdr);
+  if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) {
+    // one chunk of >= 64 elements per CTA, at most 4 CTAs per SM
+    const long long want = (n + kChunkAlign - 1) / kChunkAlign;
+    const int g = (int)std::max<long long>(1, std::min<long long>((long long)dp.sm_count * 4, want));
+    k_mse_sums<<<g, kThreads, 0, stream>>>(x, n, bits, num_attempts, hdr, cand);
+  }
+  k_apply<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, bits, qscheme, num_attempts, hdr, cand, tmin, tmax,
+                                                            xq, codes, info);
+  ADMMQ_CUDA_OK(cudaGetLastError());
+  return ADMMQ_OK;
+}

@@ -1,0 +1,234 @@
+"""ctypes binding of libadmmq.so (include/admmq.h).  There is no CPU fallback: importing this
+module without the built library, or calling it with non-CUDA tensors, raises."""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libadmmq.so")
+
+QSCHEME_IDS = {
+    "tensor_mseminmax_symmetric": 0,
+    "tensor_minmax": 1,
+    "tensor_symmetric": 2,
+    "tensor_affine": 3,
+}
+
+E_BADARG, E_WORKSPACE, E_CUDA, E_NOT_PD, E_UNSUPPORTED = -1, -2, -3, -4, -5
+ST_CONVERGED, ST_NONFINITE = 1, 2
+
+
+class LoopReport(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("rho", ctypes.c_float),
+                ("scale", ctypes.c_float), ("r", ctypes.c_float), ("s", ctypes.c_float),
+                ("best_index", ctypes.c_int32), ("absmax", ctypes.c_float)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python admm-quantization_b200/csrc/build.py` "
+            "(the solver has no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    c_int, c_i64, c_sz, c_f, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p
+    sig = {
+        "admmq_version": (c_int, []),
+        "admmq_last_error": (ctypes.c_char_p, []),
+        "admmq_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+        "admmq_project_workspace_bytes": (c_sz, [c_i64, c_int]),
+        "admmq_project": (c_int, [vp, c_i64, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, c_sz, vp]),
+        "admmq_gram_hadamard": (c_int, [vp, c_int, vp, c_int, c_int, vp, vp]),
+        "admmq_unfold3": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
+        "admmq_mttkrp_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
+        "admmq_mttkrp": (c_int, [vp, c_int, vp, c_int, vp, c_int, c_int, vp, c_int, vp, c_sz, vp]),
+        "admmq_recon_error_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "admmq_recon_error": (c_int, [vp, c_int, vp, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
+        "admmq_padded_ld": (c_int, [c_int]),
+        "admmq_spd_inverse_workspace_bytes": (c_sz, [c_int]),
+        "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, vp, c_sz, vp]),
+        "admmq_admm_iteration_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "admmq_admm_iteration": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, vp, vp,
+                                         vp, c_sz, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_project_workspace_bytes admmq_project "
+           "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp "
+           "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
+           "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration").split()
+
+
+def last_error() -> str:
+    return lib.admmq_last_error().decode()
+
+
+def check(rc: int):
+    """Translate an ADMMQ_E_* code into the exception type the reference raises."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == E_BADARG:
+        raise ValueError(msg)
+    if rc == E_NOT_PD:
+        raise torch.linalg.LinAlgError(msg)
+    if rc == E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"libadmmq error {rc}: {msg}")
+
+
+def qscheme_id(qscheme: str) -> int:
+    if qscheme not in QSCHEME_IDS:
+        raise NotImplementedError(qscheme)  # source/quantization.py:115
+    return QSCHEME_IDS[qscheme]
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libadmmq kernels need CUDA tensors (there is no CPU fallback); got device "
+                               f"{t.device}")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_tls = threading.local()
+
+
+def workspace(nbytes: int, device, tag: str = "main") -> torch.Tensor:
+    """Caller-owned scratch (the library never allocates).  One growing buffer per (device, tag)."""
+    cache = getattr(_tls, "ws", None)
+    if cache is None:
+        cache = _tls.ws = {}
+    key = (torch.device(device).index, tag)
+    buf = cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        cache[key] = buf
+    return buf
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------- thin wrappers
+def project(x, bits, qscheme, num_attempts=200, tmin=None, tmax=None, want_codes=False, want_info=False):
+    require_cuda(x)
+    xc = f32c(x)
+    n = xc.numel()
+    out = torch.empty_like(xc)
+    codes = torch.empty(xc.shape, dtype=torch.int8, device=xc.device) if want_codes else None
+    info = torch.empty(4, dtype=torch.float32, device=xc.device) if want_info else None
+    nbytes = lib.admmq_project_workspace_bytes(n, int(num_attempts))
+    ws = workspace(nbytes, xc.device)
+    tmin_t = None if tmin is None else torch.as_tensor(tmin, dtype=torch.float32, device=xc.device).reshape(1)
+    tmax_t = None if tmax is None else torch.as_tensor(tmax, dtype=torch.float32, device=xc.device).reshape(1)
+    check(lib.admmq_project(ptr(xc), n, int(bits), qscheme_id(qscheme), int(num_attempts), ptr(tmin_t), ptr(tmax_t),
+                            ptr(out), ptr(codes), ptr(info), ptr(ws), ws.numel(), stream_ptr(xc.device)))
+    return out, codes, info
+
+
+def gram_hadamard(U1, U2=None):
+    require_cuda(U1, U2)
+    U1 = f32c(U1)
+    U2 = None if U2 is None else f32c(U2)
+    R = U1.shape[1]
+    G = torch.empty(R, R, dtype=torch.float32, device=U1.device)
+    check(lib.admmq_gram_hadamard(ptr(U1), U1.shape[0], ptr(U2), 0 if U2 is None else U2.shape[0], R, ptr(G),
+                                  stream_ptr(U1.device)))
+    return G
+
+
+def unfold3(W, mode):
+    require_cuda(W)
+    W = f32c(W)
+    I, J, K = W.shape
+    shape = [(I, J * K), (J, I * K), (K, I * J)][mode]
+    out = torch.empty(shape, dtype=torch.float32, device=W.device)
+    check(lib.admmq_unfold3(ptr(W), I, J, K, int(mode), ptr(out), stream_ptr(W.device)))
+    return out
+
+
+def mttkrp(Wn, X, Y=None, precision=0):
+    """F = Wn @ khatri_rao(X, Y); Wn is the (M, nx*ny) unfolding."""
+    require_cuda(Wn, X, Y)
+    Wn, X = f32c(Wn), f32c(X)
+    Y = None if Y is None else f32c(Y)
+    M, R = Wn.shape[0], X.shape[1]
+    nx, ny = X.shape[0], (1 if Y is None else Y.shape[0])
+    assert Wn.shape[1] == nx * ny, (Wn.shape, nx, ny)
+    F = torch.empty(M, R, dtype=torch.float32, device=Wn.device)
+    nbytes = lib.admmq_mttkrp_workspace_bytes(M, nx, ny, R, int(precision))
+    ws = workspace(nbytes, Wn.device)
+    check(lib.admmq_mttkrp(ptr(Wn), M, ptr(X), nx, ptr(Y), ny, R, ptr(F), int(precision), ptr(ws), ws.numel(),
+                           stream_ptr(Wn.device)))
+    return F
+
+
+def recon_error_sums(W0, A, X, Y=None):
+    """Device double[2] = {sum (W - [[A, X, Y]])^2, sum W^2}; W0 is the (M, nx*ny) mode-0 unfolding."""
+    require_cuda(W0, A, X, Y)
+    W0, A, X = f32c(W0), f32c(A), f32c(X)
+    Y = None if Y is None else f32c(Y)
+    M, R = A.shape
+    nx, ny = X.shape[0], (1 if Y is None else Y.shape[0])
+    assert W0.shape == (M, nx * ny)
+    out = torch.empty(2, dtype=torch.float64, device=W0.device)
+    nbytes = lib.admmq_recon_error_workspace_bytes(M, nx, ny)
+    ws = workspace(nbytes, W0.device)
+    check(lib.admmq_recon_error(ptr(W0), M, ptr(A), ptr(X), nx, ptr(Y), ny, R, ptr(out), ptr(ws), ws.numel(),
+                                stream_ptr(W0.device)))
+    return out
+
+
+def spd_inverse(G):
+    """(Minv [R, ld], rho [1], status [1]) of G + trace(G)/R * I."""
+    require_cuda(G)
+    G = f32c(G)
+    R = G.shape[0]
+    ld = lib.admmq_padded_ld(R)
+    Minv = torch.empty(R, ld, dtype=torch.float32, device=G.device)
+    rho = torch.empty(1, dtype=torch.float32, device=G.device)
+    status = torch.empty(1, dtype=torch.int32, device=G.device)
+    ws = workspace(lib.admmq_spd_inverse_workspace_bytes(R), G.device)
+    check(lib.admmq_spd_inverse(ptr(G), R, ptr(Minv), ptr(rho), ptr(status), ptr(ws), ws.numel(), stream_ptr(G.device)))
+    return Minv, rho, status
+
+
+def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, codes=None):
+    """Runs the persistent loop on contiguous float32 CUDA tensors, updating H and U in place.
+    Returns the device report (uint8[32]); decode with `read_report` (synchronises)."""
+    require_cuda(H, U, F, G)
+    for t in (H, U, F, G):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    I, R = H.shape
+    assert U.shape == H.shape and F.shape == H.shape and G.shape == (R, R)
+    report = torch.empty(ctypes.sizeof(LoopReport), dtype=torch.uint8, device=H.device)
+    nbytes = lib.admmq_admm_iteration_workspace_bytes(I, R, int(num_attempts))
+    ws = workspace(nbytes, H.device)
+    check(lib.admmq_admm_iteration(ptr(H), ptr(U), ptr(F), ptr(G), I, R, int(max_iter), float(eps), int(bits),
+                                   qscheme_id(qscheme), int(num_attempts), ptr(codes), ptr(report), ptr(ws),
+                                   ws.numel(), stream_ptr(H.device)))
+    return report
+
+
+def read_report(report: torch.Tensor) -> LoopReport:
+    raw = bytes(report.cpu().numpy().tobytes())
+    rep = LoopReport.from_buffer_copy(raw)
+    if rep.status == E_NOT_PD:
+        raise torch.linalg.LinAlgError("admm_iteration: G + rho*I is not positive-definite (Cholesky failed)")
+    return rep

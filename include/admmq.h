@@ -1,0 +1,140 @@
+/*
+ * admmq.h - C ABI of libadmmq.so: the B200 (sm_100a) kernels behind the
+ * quantization-aware CP factorization hot path of KamikaziZen/admm-quantization.
+ *
+ * The reference has no FFI: its boundary is the Python API of source/admm.py,
+ * source/quantization.py and the loop in scripts/factorize.py.  Every entry point
+ * below names the reference call site it replaces (file:line relative to the
+ * reference repository).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers on the current CUDA device, float32
+ *     row-major contiguous unless stated.  The caller owns every buffer, including
+ *     workspaces (size them with the *_workspace_bytes functions); the library
+ *     never allocates or frees device memory and keeps no pointer after return.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising unless stated.
+ *   - Return value: 0 on success, a negative ADMMQ_E_* code on failure; the message
+ *     is available from admmq_last_error() (thread-local).  No C++ exception crosses.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails
+ *     with ADMMQ_E_CUDA.
+ */
+#ifndef ADMMQ_H_
+#define ADMMQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMMQ_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define ADMMQ_API __attribute__((visibility("default")))
+#else
+#define ADMMQ_API
+#endif
+
+/* error codes */
+#define ADMMQ_OK 0
+#define ADMMQ_E_BADARG (-1)      /* ValueError / NotImplementedError on the Python side */
+#define ADMMQ_E_WORKSPACE (-2)   /* workspace too small or misaligned */
+#define ADMMQ_E_CUDA (-3)        /* CUDA runtime / launch failure (no device, OOM, ...) */
+#define ADMMQ_E_NOT_PD (-4)      /* G + rho I not positive definite: torch.linalg.LinAlgError */
+#define ADMMQ_E_UNSUPPORTED (-5) /* shape outside what the kernels handle */
+
+/* quantization schemes, source/quantization.py:91-115 (tensor_* branches) */
+#define ADMMQ_Q_MSEMINMAX_SYMMETRIC 0 /* 'tensor_mseminmax_symmetric' :107-108, :118-144 */
+#define ADMMQ_Q_MINMAX 1              /* 'tensor_minmax'              :110-111, :48-66  */
+#define ADMMQ_Q_SYMMETRIC 2           /* 'tensor_symmetric'           :91-95           */
+#define ADMMQ_Q_AFFINE 3              /* 'tensor_affine'              :97-106          */
+
+/* status bits written by the ADMM loop into admmq_loop_report.status */
+#define ADMMQ_ST_CONVERGED 1 /* r < eps and s < eps fired (source/admm.py:64-65) */
+#define ADMMQ_ST_NONFINITE 2 /* projection input had abs-max 0, inf or NaN: outputs are NaN like the reference */
+
+ADMMQ_API int admmq_version(void);
+ADMMQ_API const char* admmq_last_error(void);
+/* sm count / compute capability of the current device; fails without one. */
+ADMMQ_API int admmq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ projection
+ * Replaces quantize_tensor(tensor, bits, qscheme, **kw)  source/quantization.py:69-115
+ * and quantize_tensor_mse(x, bits, num_attempts)          source/quantization.py:118-144.
+ *   x, xq       n floats (xq may alias x)
+ *   codes       n int8 integer codes or NULL (mse/symmetric: clamp(rint(x/scale),-q,q-1);
+ *               affine: code incl. zero point; minmax: level index - 2^(bits-1))
+ *   info        device float[4] or NULL: {scale, zero_point or min, chosen candidate index, abs-max}
+ *   tmin,tmax   only for ADMMQ_Q_AFFINE: device float scalars or NULL (= tensor min/max) (:98-101)
+ */
+ADMMQ_API size_t admmq_project_workspace_bytes(int64_t n, int num_attempts);
+ADMMQ_API int admmq_project(const float* x, int64_t n, int bits, int qscheme, int num_attempts,
+                  const float* tmin, const float* tmax, float* xq, int8_t* codes, float* info,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ per-sweep contractions
+ * Gram-Hadamard  G = (U1^T U1) * (U2^T U2)   scripts/factorize.py:215,226,236 (3-D), :276,286 (2-D, U2 = NULL)
+ *   U1 (n1 x R), U2 (n2 x R) or NULL, G (R x R).  Each Gram is accumulated in float64 and
+ *   rounded to float32 before the float32 Hadamard product. */
+ADMMQ_API int admmq_gram_hadamard(const float* U1, int n1, const float* U2, int n2, int R, float* G, void* stream);
+
+/* Mode-n unfolding copy of a 3-way tensor (source/utils.py:60-74): out = reshape(moveaxis(W, mode, 0)). */
+ADMMQ_API int admmq_unfold3(const float* W, int I, int J, int K, int mode, float* out, void* stream);
+
+/* MTTKRP  F = Wn . KhatriRao(X, Y)   scripts/factorize.py:217,227,237 (einsum) and :277,287 (W@B, W.T@A)
+ *   Wn  (M x P) row-major unfolding, P = nx*ny;  X (nx x R), Y (ny x R) or NULL (ny = 1, matrix case);
+ *   KR row p = x*ny + y is X[x,:] * Y[y,:];  F (M x R).
+ *   precision 0: float64 accumulation on CUDA cores (parity mode)
+ *   precision 1: 3xTF32 tcgen05 tensor-core path (throughput mode)  */
+ADMMQ_API size_t admmq_mttkrp_workspace_bytes(int M, int nx, int ny, int R, int precision);
+ADMMQ_API int admmq_mttkrp(const float* Wn, int M, const float* X, int nx, const float* Y, int ny, int R,
+                 float* F, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reconstruction error pieces for squared_relative_diff  source/admm.py:14-15 with the einsum of
+ * scripts/factorize.py:246-253 (3-D) / :296-297 (2-D):  out2 (device double[2]) = { sum (W - [[A,X,Y]])^2, sum W^2 }.
+ *   W0 (M x P) mode-0 unfolding, A (M x R), X (nx x R), Y (ny x R) or NULL.  The reconstruction is never stored. */
+ADMMQ_API size_t admmq_recon_error_workspace_bytes(int M, int nx, int ny);
+ADMMQ_API int admmq_recon_error(const float* W0, int M, const float* A, const float* X, int nx, const float* Y, int ny,
+                      int R, double* out2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ ridge system
+ * rho = trace(G)/R and Minv = (G + rho I)^-1  (replaces torch.linalg.cholesky at source/admm.py:52-54;
+ * the per-iteration cholesky_solve of :56 becomes a product with Minv).  Blocked float64 Cholesky +
+ * triangular inverse run by one cooperative kernel; Minv is (R x ldm) float32, ldm = admmq_padded_ld(R).
+ * status (device int): 0 or ADMMQ_E_NOT_PD.  rho_out: device float. */
+ADMMQ_API int admmq_padded_ld(int R);
+ADMMQ_API size_t admmq_spd_inverse_workspace_bytes(int R);
+ADMMQ_API int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ ADMM inner loop
+ * Replaces admm_iteration(H, U, F, G, max_iter, eps, bits, qscheme)  source/admm.py:51-67.
+ * One persistent cooperative kernel runs all max_iter-1 iterations: Minv product (:56), projection (:59),
+ * dual update (:60), residuals and exit test (:62-65).  H (I x R) and U (I x R) are updated IN PLACE
+ * (the Python wrapper returns a fresh H tensor and the caller's U, like the reference).
+ *   codes   I*R int8 codes of the final H, or NULL
+ *   report  device struct, see below
+ * The call itself runs admmq_spd_inverse first (same stream). */
+typedef struct admmq_loop_report {
+  int32_t iterations; /* inner iterations executed (max_iter-1 unless the exit test fired) */
+  int32_t status;     /* ADMMQ_ST_* bits, or a negative ADMMQ_E_* */
+  float rho;          /* trace(G)/R */
+  float scale;        /* grid scale of the last projection (mse/symmetric/affine); (max-min) for minmax */
+  float r;            /* last primal residual  sum (H-H_ls)^2 / sum H^2      source/admm.py:62 */
+  float s;            /* last dual residual    sum (H-H_prev)^2 / sum U^2    source/admm.py:63 */
+  int32_t best_index; /* chosen clip candidate of the last projection, -1 for other schemes */
+  float absmax;       /* abs-max of the last projection input */
+} admmq_loop_report;
+
+ADMMQ_API size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts);
+ADMMQ_API int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R,
+                         int max_iter, float eps, int bits, int qscheme, int num_attempts,
+                         int8_t* codes, admmq_loop_report* report,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMMQ_H_ */

@@ -1,0 +1,155 @@
+"""CPU-only: the kernels' float32 recipe (csrc/numerics.cuh, compiled for the host by
+tests/hostcheck) against the oracle and the reference golden vectors; ABI surface checks."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import admm_oracle as orc
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "admm-quantization_b200")
+torch.set_num_threads(1)
+
+
+@pytest.fixture(scope="session")
+def hc():
+    src = os.path.join(REPO, "tests", "hostcheck", "hostcheck.cpp")
+    out_dir = os.path.join(REPO, "oracle", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libhostcheck.so")
+    deps = [src, os.path.join(PKG, "csrc", "numerics.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", src, "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.hc_mse.restype = ctypes.c_longlong
+    lib.hc_fastpath_violations.restype = ctypes.c_longlong
+    return lib
+
+
+def fp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_candidate_grid_and_scales_match_oracle(hc):
+    g = torch.Generator().manual_seed(1)
+    for _ in range(300):
+        mx = float((torch.rand(1, generator=g) * 10 ** float(torch.randint(-8, 8, (1,), generator=g))).float())
+        for n in (1, 2, 7, 200, 1000):
+            for bits in (2, 4, 8):
+                clip = np.empty(n, np.float32)
+                scale = np.empty(n, np.float32)
+                hc.hc_candidates(ctypes.c_float(mx), n, bits, fp(clip), fp(scale))
+                ref = orc.candidate_grid(mx, n)
+                assert np.array_equal(clip, ref)
+                q = 2 ** (bits - 1)
+                ref_scale = (2 * torch.from_numpy(ref) / (2 * q - 1)).numpy()
+                assert np.array_equal(scale, ref_scale)
+
+
+def test_kernel_mse_recipe_selects_reference_candidate(hc, golden_projection):
+    gp = golden_projection
+    for m in gp.meta:
+        if "scheme" in m or m["name"] == "all_zero_b4":
+            continue
+        x = np.ascontiguousarray(gp[m["name"] + "/x"]).reshape(-1)
+        mx = np.float32(max(abs(x.min()), abs(x.max())))
+        nc = m["num_attempts"]
+        mse = np.empty(nc, np.float32)
+        best = ctypes.c_int()
+        hc.hc_mse(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(mx), m["bits"], nc, fp(mse), ctypes.byref(best), 0)
+        idx, scale = gp[m["name"] + "/idx_scale"]
+        assert best.value == int(idx), m["name"]
+        xq = np.empty_like(x)
+        codes = np.empty(x.size, np.int8)
+        hc.hc_quantize(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(scale), m["bits"], fp(xq), fp(codes))
+        assert np.array_equal(xq.view(np.uint32), gp[m["name"] + "/xq"].reshape(-1).view(np.uint32)), m["name"]
+        assert np.array_equal(codes, gp[m["name"] + "/codes"].reshape(-1))
+
+
+def test_fast_path_equals_exact_division(hc):
+    """x*(1/s) + magic-number rounding agrees with rint(x/s) whenever the fast path accepts, incl.
+    values placed right at the rounding boundaries (k + 0.5) * s."""
+    g = torch.Generator().manual_seed(9)
+    total_slow = 0
+    for bits in (2, 3, 4, 6, 8):
+        q = 2 ** (bits - 1)
+        for trial in range(40):
+            scale = np.float32(float(torch.rand(1, generator=g)) * 10 ** float(torch.randint(-6, 6, (1,), generator=g)) + 1e-30)
+            ks = np.arange(-q - 2, q + 2, dtype=np.float64) + 0.5
+            edge = (ks * float(scale)).astype(np.float32)
+            near = np.concatenate([np.nextafter(edge, np.float32(np.inf)), np.nextafter(edge, np.float32(-np.inf)), edge])
+            rnd = (torch.randn(4000, generator=g).numpy() * float(scale) * q * 0.7).astype(np.float32)
+            x = np.ascontiguousarray(np.concatenate([near, rnd, np.zeros(3, np.float32)]))
+            bad = hc.hc_fastpath_violations(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(scale), bits)
+            assert bad == 0, (bits, scale)
+            # and the whole per-candidate recipe with/without forcing the exact path gives the same MSEs
+            mx = np.float32(np.abs(x).max())
+            a, b = np.empty(50, np.float32), np.empty(50, np.float32)
+            best = ctypes.c_int()
+            slow = hc.hc_mse(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(mx), bits, 50, fp(a), ctypes.byref(best), 0)
+            hc.hc_mse(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(mx), bits, 50, fp(b), ctypes.byref(best), 1)
+            assert np.array_equal(a, b)
+            total_slow += slow
+    assert total_slow > 0  # the boundary inputs do exercise the fallback
+
+
+def test_other_scheme_recipes_match_reference(hc, golden_projection):
+    gp = golden_projection
+    for m in gp.meta:
+        if m.get("scheme") not in ("tensor_minmax", "tensor_affine"):
+            continue
+        x = np.ascontiguousarray(gp[m["name"] + "/x"]).reshape(-1)
+        out = np.empty_like(x)
+        fn = hc.hc_minmax if m["scheme"] == "tensor_minmax" else hc.hc_affine
+        fn(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(x.min()), ctypes.c_float(x.max()), m["bits"], fp(out))
+        assert np.array_equal(out.view(np.uint32), gp[m["name"] + "/xq"].reshape(-1).view(np.uint32)), m["name"]
+
+
+# ------------------------------------------------------------------ ABI surface (no compute without a GPU)
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "admmq.h")).read()
+    return sorted(set(re.findall(r"ADMMQ_API [\w\s\*]*?\b(admmq_\w+)\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import sys
+    sys.path.insert(0, PKG)
+    from source import _native
+    names = _declared_symbols()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(_native.lib, n), n
+    assert sorted(_native.EXPORTS) == names
+    assert _native.lib.admmq_version() == 100
+    assert _native.lib.admmq_padded_ld(134) == 136
+    assert _native.lib.admmq_admm_iteration_workspace_bytes(64, 134, 200) > 0
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA")
+    from source import _native
+    from source.quantization import quantize_tensor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        quantize_tensor(torch.randn(4, 4), 4, "tensor_mseminmax_symmetric")
+    a = ctypes.c_int()
+    assert _native.lib.admmq_device_info(ctypes.byref(a), ctypes.byref(a), ctypes.byref(a)) == _native.E_CUDA
+    assert "no CPU fallback" in _native.last_error()
+
+
+def test_product_never_touches_the_oracle():
+    bad = []
+    for root, _, files in os.walk(PKG):
+        if os.path.basename(root) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text or "admm_oracle" in text:
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad
