@@ -20,11 +20,16 @@ namespace admmq {
 constexpr int kKeySlots = 3;
 
 struct LoopHeader {  // start of the workspace; zeroed by cudaMemsetAsync before every call
-  unsigned int barrier_inv;
   unsigned int barrier_loop;
+  unsigned int pad[3];
+  unsigned int keys[kKeySlots][4];  // rotating {max key, ~min key, -, -} of V
+};
+
+struct IterationHeader {  // admmq_admm_iteration only: scalars handed from the inverse to the loop
+  unsigned int barrier_inv;
   int status;  // ADMMQ_E_NOT_PD from the inverse
   float rho;
-  unsigned int keys[kKeySlots][4];  // rotating {max key, ~min key, -, -} of V
+  unsigned int pad;
 };
 
 struct LoopParams {
@@ -37,6 +42,8 @@ struct LoopParams {
   int bits, scheme, Nc;
   int8_t* codes;
   admmq_loop_report* report;
+  const float* rho;       // device scalar: trace(G)/R
+  const int* inv_status;  // device scalar or nullptr
   LoopHeader* hdr;
   unsigned long long* cand;  // [kKeySlots][kMaxCandidates]
   double* slots;             // [gridDim.x][4]
@@ -142,17 +149,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
   admmq_loop_report rep;
   rep.iterations = 0;
   rep.status = 0;
-  rep.rho = hdr->rho;
+  rep.rho = *p.rho;
   rep.scale = 0.0f;
   rep.r = 0.0f;
   rep.s = 0.0f;
   rep.best_index = -1;
   rep.absmax = 0.0f;
-  if (hdr->status != 0) {  // G + rho I was not positive definite: nothing is touched
-    rep.status = hdr->status;
+  rep.phase_ns[0] = rep.phase_ns[1] = rep.phase_ns[2] = rep.phase_ns[3] = 0ull;
+  if (p.inv_status != nullptr && *p.inv_status != 0) {  // G + rho I was not positive definite: nothing is touched
+    rep.status = *p.inv_status;
     if (blockIdx.x == 0 && t == 0) *p.report = rep;
     return;
   }
+  const unsigned long long t_begin = global_ns();
+  unsigned long long t_mark = t_begin;
+  auto lap = [&](int phase) {
+    const unsigned long long now = global_ns();
+    rep.phase_ns[phase] += now - t_mark;
+    t_mark = now;
+  };
   GridBarrier bar;
   bar.init(&hdr->barrier_loop);
   const float rho = rep.rho;
@@ -179,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
       for (int c = t; c < p.Nc; c += kThreads) p.cand[(size_t)next_slot * kMaxCandidates + c] = 0ull;
     }
     bar.sync();
+    lap(0);
     // ---------------- P2
     const float tmax = key_float(__ldcg(&hdr->keys[slot][0]));
     const float tmin = key_float(~__ldcg(&hdr->keys[slot][1]));
@@ -206,6 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
             },
             e0, e1, absmax, p.Nc, L, (double)N, cand, sm);
         bar.sync();
+        lap(1);
         // ---------------- P3
         rep.best_index = cta_best_candidate(cand, p.Nc, absmax, (double)N, sm);
         qp.scale = scale_of(clip_candidate(make_clip_grid(absmax, p.Nc), rep.best_index), L);
@@ -279,25 +296,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
     rep.r = div_rn((float)sred[0][0], (float)sred[1][0]);
     rep.s = div_rn((float)sred[2][0], (float)sred[3][0]);
     __syncthreads();
+    lap(2);
     if (rep.r < p.eps && rep.s < p.eps) {
       rep.status |= ADMMQ_ST_CONVERGED;
       break;
     }
   }
+  rep.phase_ns[3] = global_ns() - t_begin;
   if (blockIdx.x == 0 && t == 0) *p.report = rep;
 }
 
 // ------------------------------------------------------------------------------------ host side
-struct LoopLayout {
-  size_t header, cand, slots, hls, rhs, minv, lw, xw, total;
-  int Rp, nb, Rb;
+struct LoopLayout {  // workspace of admmq_admm_loop
+  size_t header, cand, slots, hls, rhs, total;
+  int Rp;
 };
 
 static LoopLayout loop_layout(int I, int R, int grid) {
   LoopLayout l;
   l.Rp = (R + 3) / 4 * 4;
-  l.nb = (R + kNB - 1) / kNB;
-  l.Rb = l.nb * kNB;
   size_t off = 0;
   auto take = [&off](size_t bytes) {
     const size_t o = off;
@@ -309,12 +326,37 @@ static LoopLayout loop_layout(int I, int R, int grid) {
   l.slots = take((size_t)grid * 4 * sizeof(double));
   l.rhs = take((size_t)I * l.Rp * sizeof(float));
   l.hls = take((size_t)I * l.Rp * sizeof(float));
-  l.minv = take((size_t)R * l.Rp * sizeof(float));
-  l.lw = take((size_t)l.Rb * l.Rb * sizeof(double));
-  l.xw = take((size_t)l.Rb * l.Rb * sizeof(double));
   l.total = off;
   return l;
 }
+
+struct IterationLayout {  // workspace of admmq_admm_iteration = scalars + Minv + inverse scratch + loop workspace
+  size_t header, minv, inv_ws, loop_ws, total;
+};
+
+static size_t spd_scratch_bytes(int R) {
+  const size_t Rb = (size_t)((R + kNB - 1) / kNB) * kNB;
+  return 2 * align_up(Rb * Rb * sizeof(double), 256);
+}
+
+static IterationLayout iteration_layout(int I, int R, int grid) {
+  IterationLayout l;
+  const int Rp = (R + 3) / 4 * 4;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) {
+    const size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  l.header = take(sizeof(IterationHeader));
+  l.minv = take((size_t)R * Rp * sizeof(float));
+  l.inv_ws = take(spd_scratch_bytes(R));
+  l.loop_ws = take(loop_layout(I, R, grid).total);
+  l.total = off;
+  return l;
+}
+
+constexpr int kMaxGrid = 1024;  // workspaces are sized for any cooperative grid up to this many CTAs
 
 static int coop_grid(const DeviceProps& dp) { return dp.sm_count; }
 
@@ -334,6 +376,7 @@ static int launch_spd_inverse(const float* G, int R, float* Minv, int ldm, float
   ip.barrier = barrier;
   void* args[] = {&ip};
   ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_spd_inverse, dim3(grid), dim3(kInvThreads), args, 0, stream));
+  count_launches(1);
   return ADMMQ_OK;
 }
 
@@ -355,69 +398,25 @@ static int pick_tile(int I, int R, int grid) {
   return best;
 }
 
-}  // namespace admmq
-
-using namespace admmq;
-
-extern "C" int admmq_padded_ld(int R) { return (R + 3) / 4 * 4; }
-
-extern "C" size_t admmq_spd_inverse_workspace_bytes(int R) {
-  if (R <= 0) return 0;
-  const size_t Rb = (size_t)((R + kNB - 1) / kNB) * kNB;
-  return 256 + 2 * align_up(Rb * Rb * sizeof(double), 256);
-}
-
-extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, void* workspace,
-                                 size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (G == nullptr || Minv == nullptr || rho_out == nullptr || status == nullptr || R <= 0)
-    return fail(ADMMQ_E_BADARG, "admmq_spd_inverse: bad argument");
-  if (workspace == nullptr || workspace_bytes < admmq_spd_inverse_workspace_bytes(R) || ((uintptr_t)workspace & 255) != 0)
-    return fail(ADMMQ_E_WORKSPACE, "admmq_spd_inverse: workspace too small or not 256-byte aligned");
-  DeviceProps dp;
-  if (int e = device_props(&dp)) return e;
-  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
-  const size_t Rb = (size_t)((R + kNB - 1) / kNB) * kNB;
-  char* ws = (char*)workspace;
-  ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, 256, stream));
-  ADMMQ_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), stream));
-  double* Lw = (double*)(ws + 256);
-  double* Xw = (double*)(ws + 256 + align_up(Rb * Rb * sizeof(double), 256));
-  return launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp), stream);
-}
-
-extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts) {
-  (void)num_attempts;
-  if (I <= 0 || R <= 0) return 0;
-  return loop_layout(I, R, 1024).total;  // sized for any grid up to 1024 CTAs
-}
-
-extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R, int max_iter,
-                                    float eps, int bits, int qscheme, int num_attempts, int8_t* codes,
-                                    admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (H == nullptr || U == nullptr || F == nullptr || G == nullptr || report == nullptr || I <= 0 || R <= 0)
-    return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: null pointer or empty shape");
-  if (bits < 1 || bits > 8) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: bits must be in 1..8, got %d", bits);
-  if (qscheme < 0 || qscheme > 3) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: unknown qscheme %d", qscheme);
+static int check_loop_args(const char* who, const void* H, const void* U, const void* F, const void* M, const void* report,
+                           int I, int R, int bits, int qscheme, int num_attempts) {
+  if (H == nullptr || U == nullptr || F == nullptr || M == nullptr || report == nullptr || I <= 0 || R <= 0)
+    return fail(ADMMQ_E_BADARG, "%s: null pointer or empty shape", who);
+  if (bits < 1 || bits > 8) return fail(ADMMQ_E_BADARG, "%s: bits must be in 1..8, got %d", who, bits);
+  if (qscheme < 0 || qscheme > 3) return fail(ADMMQ_E_BADARG, "%s: unknown qscheme %d", who, qscheme);
   if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC && (num_attempts < 1 || num_attempts > kMaxCandidates))
-    return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: num_attempts must be in 1..%d", kMaxCandidates);
-  if ((long long)I * R >= (1ll << 31)) return fail(ADMMQ_E_UNSUPPORTED, "admmq_admm_iteration: I*R must be < 2^31");
-  DeviceProps dp;
-  if (int e = device_props(&dp)) return e;
-  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
-  const int grid = coop_grid(dp);
+    return fail(ADMMQ_E_BADARG, "%s: num_attempts must be in 1..%d", who, kMaxCandidates);
+  if ((long long)I * R >= (1ll << 31)) return fail(ADMMQ_E_UNSUPPORTED, "%s: I*R must be < 2^31", who);
+  return ADMMQ_OK;
+}
+
+static int launch_loop(float* H, float* U, const float* F, const float* Minv, const float* rho, const int* inv_status,
+                       int I, int R, int max_iter, float eps, int bits, int qscheme, int num_attempts, int8_t* codes,
+                       admmq_loop_report* report, char* ws, int grid, cudaStream_t stream) {
   const LoopLayout l = loop_layout(I, R, grid);
-  if (workspace == nullptr || workspace_bytes < l.total || ((uintptr_t)workspace & 255) != 0)
-    return fail(ADMMQ_E_WORKSPACE, "admmq_admm_iteration: workspace needs %zu bytes, 256-byte aligned", l.total);
-  char* ws = (char*)workspace;
   // header + candidate accumulators + RHS (its pad columns must be zero)
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, l.slots, stream));
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws + l.rhs, 0, (size_t)I * l.Rp * sizeof(float), stream));
-  LoopHeader* hdr = (LoopHeader*)(ws + l.header);
-  if (int e = launch_spd_inverse(G, R, (float*)(ws + l.minv), l.Rp, &hdr->rho, &hdr->status, &hdr->barrier_inv,
-                                 (double*)(ws + l.lw), (double*)(ws + l.xw), grid, stream))
-    return e;
   LoopParams p;
   p.H = H;
   p.U = U;
@@ -432,12 +431,14 @@ extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const fl
   p.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
   p.codes = codes;
   p.report = report;
-  p.hdr = hdr;
+  p.rho = rho;
+  p.inv_status = inv_status;
+  p.hdr = (LoopHeader*)(ws + l.header);
   p.cand = (unsigned long long*)(ws + l.cand);
   p.slots = (double*)(ws + l.slots);
   p.Hls = (float*)(ws + l.hls);
   p.RHS = (float*)(ws + l.rhs);
-  p.Minv = (const float*)(ws + l.minv);
+  p.Minv = Minv;
   void* args[] = {&p};
   const void* fn = nullptr;
   switch (pick_tile(I, R, grid)) {
@@ -446,5 +447,87 @@ extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const fl
     default: fn = (const void*)k_admm_loop<16, 32, 1, 2>; break;
   }
   ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
+  count_launches(1);
   return ADMMQ_OK;
+}
+
+}  // namespace admmq
+
+using namespace admmq;
+
+extern "C" int admmq_padded_ld(int R) { return (R + 3) / 4 * 4; }
+
+extern "C" size_t admmq_spd_inverse_workspace_bytes(int R) {
+  if (R <= 0) return 0;
+  return 256 + spd_scratch_bytes(R);
+}
+
+extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (G == nullptr || Minv == nullptr || rho_out == nullptr || status == nullptr || R <= 0)
+    return fail(ADMMQ_E_BADARG, "admmq_spd_inverse: bad argument");
+  if (workspace == nullptr || workspace_bytes < admmq_spd_inverse_workspace_bytes(R) || ((uintptr_t)workspace & 255) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_spd_inverse: workspace too small or not 256-byte aligned");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
+  char* ws = (char*)workspace;
+  ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, 256, stream));
+  ADMMQ_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), stream));
+  double* Lw = (double*)(ws + 256);
+  double* Xw = (double*)(ws + 256 + spd_scratch_bytes(R) / 2);
+  return launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp), stream);
+}
+
+extern "C" size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts) {
+  (void)num_attempts;
+  if (I <= 0 || R <= 0) return 0;
+  return loop_layout(I, R, kMaxGrid).total;
+}
+
+extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
+                               const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
+                               int num_attempts, int8_t* codes, admmq_loop_report* report, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  if (int e = check_loop_args("admmq_admm_loop", H, U, F, Minv, report, I, R, bits, qscheme, num_attempts)) return e;
+  if (rho == nullptr) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: rho is null");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
+  if (workspace == nullptr || workspace_bytes < admmq_admm_loop_workspace_bytes(I, R, num_attempts) ||
+      ((uintptr_t)workspace & 255) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_admm_loop: workspace needs %zu bytes, 256-byte aligned",
+                admmq_admm_loop_workspace_bytes(I, R, num_attempts));
+  return launch_loop(H, U, F, Minv, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, codes, report,
+                     (char*)workspace, coop_grid(dp), (cudaStream_t)stream_);
+}
+
+extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts) {
+  (void)num_attempts;
+  if (I <= 0 || R <= 0) return 0;
+  return iteration_layout(I, R, kMaxGrid).total;
+}
+
+extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R, int max_iter,
+                                    float eps, int bits, int qscheme, int num_attempts, int8_t* codes,
+                                    admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_loop_args("admmq_admm_iteration", H, U, F, G, report, I, R, bits, qscheme, num_attempts)) return e;
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
+  const int grid = coop_grid(dp);
+  const IterationLayout l = iteration_layout(I, R, kMaxGrid);
+  if (workspace == nullptr || workspace_bytes < l.total || ((uintptr_t)workspace & 255) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_admm_iteration: workspace needs %zu bytes, 256-byte aligned", l.total);
+  char* ws = (char*)workspace;
+  ADMMQ_CUDA_OK(cudaMemsetAsync(ws + l.header, 0, 256, stream));
+  IterationHeader* ih = (IterationHeader*)(ws + l.header);
+  float* Minv = (float*)(ws + l.minv);
+  if (int e = launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), &ih->rho, &ih->status, &ih->barrier_inv,
+                                 (double*)(ws + l.inv_ws), (double*)(ws + l.inv_ws + spd_scratch_bytes(R) / 2), grid, stream))
+    return e;
+  return launch_loop(H, U, F, Minv, &ih->rho, &ih->status, I, R, max_iter, eps, bits, qscheme, num_attempts, codes, report,
+                     ws + l.loop_ws, grid, stream);
 }

@@ -1,8 +1,13 @@
 // api.cu - version, error string and device query of the C ABI (include/admmq.h).
+#include <atomic>
 #include <cstring>
 #include "common.cuh"
 
 namespace admmq {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 char* error_buffer() {
   static thread_local char buf[512] = {0};
@@ -46,6 +51,8 @@ int device_props(DeviceProps* out) {
 }  // namespace admmq
 
 extern "C" int admmq_version(void) { return ADMMQ_VERSION; }
+
+extern "C" uint64_t admmq_launch_count(void) { return (uint64_t)admmq::launches_so_far(); }
 
 extern "C" const char* admmq_last_error(void) { return admmq::error_buffer(); }
 

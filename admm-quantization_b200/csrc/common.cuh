@@ -20,6 +20,9 @@ int fail(int code, const char* fmt, ...);
                            __FILE__, __LINE__);                                               \
   } while (0)
 
+// process-wide count of kernel launches (admmq_launch_count)
+void count_launches(int n);
+
 struct DeviceProps {
   int sm_count = 0, cc_major = 0, cc_minor = 0, coop = 0;
   size_t smem_optin = 0;
@@ -57,6 +60,12 @@ struct GridBarrier {
     __syncthreads();
   }
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }

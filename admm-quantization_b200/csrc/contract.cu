@@ -269,6 +269,7 @@ extern "C" int admmq_gram_hadamard(const float* U1, int n1, const float* U2, int
   dim3 grid((R + 31) / 32, (R + 31) / 32);
   k_gram_hadamard<<<grid, kCT, 0, (cudaStream_t)stream_>>>(U1, n1, U2, n2, R, G);
   ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return ADMMQ_OK;
 }
 
@@ -279,6 +280,7 @@ extern "C" int admmq_unfold3(const float* W, int I, int J, int K, int mode, floa
   const int g = (int)std::min<long long>((n + kCT - 1) / kCT, 148 * 16);
   k_unfold3<<<g, kCT, 0, (cudaStream_t)stream_>>>(W, I, J, K, mode, out);
   ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return ADMMQ_OK;
 }
 
@@ -323,6 +325,7 @@ extern "C" int admmq_mttkrp(const float* Wn, int M, const float* X, int nx, cons
                                                                                             splits, n, F);
   }
   ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(splits > 1 ? 2 : 1);
   return ADMMQ_OK;
 }
 
@@ -345,5 +348,6 @@ extern "C" int admmq_recon_error(const float* W0, int M, const float* A, const f
   k_recon_error<<<grid, kCT, 0, stream>>>(W0, M, P, A, X, Y, ny, R, (double*)workspace);
   k_sum_pairs<<<1, kCT, 0, stream>>>((const double*)workspace, (long long)grid.x * grid.y, out2);
   ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(2);
   return ADMMQ_OK;
 }

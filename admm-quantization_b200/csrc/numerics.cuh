@@ -182,7 +182,7 @@ ADMMQ_HD float minmax_value(float x, const QParams& p, float& level) {
 // tensor_affine, source/quantization.py:97-106
 ADMMQ_HD float affine_value(float x, const QParams& p, const Levels& L, float& code) {
   float k = add_rn(rint_rn(div_rn(x, p.scale)), p.aux);
-  k = fminf(fmaxf(k, L.lo), L.hi);
+  k = add_rn(fminf(fmaxf(k, L.lo), L.hi), 0.0f);  // `.to(int)` (:105) has no negative zero
   code = k;
   return mul_rn(sub_rn(k, p.aux), p.scale);
 }

@@ -140,5 +140,6 @@ extern "C" int admmq_project(const float* x, int64_t n, int bits, int qscheme, i
   k_apply<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, bits, qscheme, num_attempts, hdr, cand, tmin, tmax,
                                                             xq, codes, info);
   ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC ? 3 : 2);
   return ADMMQ_OK;
 }

@@ -161,6 +161,9 @@ __device__ __forceinline__ float quantize_value(float x, const QParams& p, const
   }
   if (p.scheme == ADMMQ_Q_AFFINE) return affine_value(x, p, L, code);
   code = code_exact(x, p.scale, L);
+  // tensor_symmetric multiplies the INTEGER code by the scale (source/quantization.py:95 `.to(int)`),
+  // which has no negative zero; the clip search (:127, :144) stays in float and keeps -0.
+  if (p.scheme == ADMMQ_Q_SYMMETRIC) code = add_rn(code, 0.0f);
   return mul_rn(code, p.scale);
 }
 

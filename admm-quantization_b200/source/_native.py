@@ -23,7 +23,7 @@ ST_CONVERGED, ST_NONFINITE = 1, 2
 class LoopReport(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("rho", ctypes.c_float),
                 ("scale", ctypes.c_float), ("r", ctypes.c_float), ("s", ctypes.c_float),
-                ("best_index", ctypes.c_int32), ("absmax", ctypes.c_float)]
+                ("best_index", ctypes.c_int32), ("absmax", ctypes.c_float), ("phase_ns", ctypes.c_uint64 * 4)]
 
 
 def _load():
@@ -37,6 +37,7 @@ def _load():
         "admmq_version": (c_int, []),
         "admmq_last_error": (ctypes.c_char_p, []),
         "admmq_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+        "admmq_launch_count": (ctypes.c_uint64, []),
         "admmq_project_workspace_bytes": (c_sz, [c_i64, c_int]),
         "admmq_project": (c_int, [vp, c_i64, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, c_sz, vp]),
         "admmq_gram_hadamard": (c_int, [vp, c_int, vp, c_int, c_int, vp, vp]),
@@ -48,6 +49,9 @@ def _load():
         "admmq_padded_ld": (c_int, [c_int]),
         "admmq_spd_inverse_workspace_bytes": (c_sz, [c_int]),
         "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, vp, c_sz, vp]),
+        "admmq_admm_loop_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, vp, vp,
+                                    vp, c_sz, vp]),
         "admmq_admm_iteration_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_admm_iteration": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, vp, vp,
                                          vp, c_sz, vp]),
@@ -60,7 +64,8 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_project_workspace_bytes admmq_project "
+EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count admmq_project_workspace_bytes "
+           "admmq_project admmq_admm_loop_workspace_bytes admmq_admm_loop "
            "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
            "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration").split()
@@ -126,15 +131,30 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------- thin wrappers
-def project(x, bits, qscheme, num_attempts=200, tmin=None, tmax=None, want_codes=False, want_info=False):
+# Every wrapper takes optional `out=` / `ws=` tensors so that a solver can preallocate once and enqueue
+# sweeps without touching the allocator; without them a result tensor / the thread-local scratch is used.
+def _ws(nbytes, device, ws):
+    if ws is None:
+        return workspace(nbytes, device)
+    assert ws.is_cuda and ws.numel() * ws.element_size() >= nbytes, "workspace too small"
+    return ws
+
+
+def project_workspace_bytes(n, num_attempts=200):
+    return int(lib.admmq_project_workspace_bytes(int(n), int(num_attempts)))
+
+
+def project(x, bits, qscheme, num_attempts=200, tmin=None, tmax=None, want_codes=False, want_info=False,
+            out=None, codes=None, info=None, ws=None):
     require_cuda(x)
     xc = f32c(x)
     n = xc.numel()
-    out = torch.empty_like(xc)
-    codes = torch.empty(xc.shape, dtype=torch.int8, device=xc.device) if want_codes else None
-    info = torch.empty(4, dtype=torch.float32, device=xc.device) if want_info else None
-    nbytes = lib.admmq_project_workspace_bytes(n, int(num_attempts))
-    ws = workspace(nbytes, xc.device)
+    out = torch.empty_like(xc) if out is None else out
+    if want_codes and codes is None:
+        codes = torch.empty(xc.shape, dtype=torch.int8, device=xc.device)
+    if want_info and info is None:
+        info = torch.empty(4, dtype=torch.float32, device=xc.device)
+    ws = _ws(project_workspace_bytes(n, num_attempts), xc.device, ws)
     tmin_t = None if tmin is None else torch.as_tensor(tmin, dtype=torch.float32, device=xc.device).reshape(1)
     tmax_t = None if tmax is None else torch.as_tensor(tmax, dtype=torch.float32, device=xc.device).reshape(1)
     check(lib.admmq_project(ptr(xc), n, int(bits), qscheme_id(qscheme), int(num_attempts), ptr(tmin_t), ptr(tmax_t),
@@ -142,28 +162,32 @@ def project(x, bits, qscheme, num_attempts=200, tmin=None, tmax=None, want_codes
     return out, codes, info
 
 
-def gram_hadamard(U1, U2=None):
+def gram_hadamard(U1, U2=None, out=None):
     require_cuda(U1, U2)
     U1 = f32c(U1)
     U2 = None if U2 is None else f32c(U2)
     R = U1.shape[1]
-    G = torch.empty(R, R, dtype=torch.float32, device=U1.device)
+    G = torch.empty(R, R, dtype=torch.float32, device=U1.device) if out is None else out
     check(lib.admmq_gram_hadamard(ptr(U1), U1.shape[0], ptr(U2), 0 if U2 is None else U2.shape[0], R, ptr(G),
                                   stream_ptr(U1.device)))
     return G
 
 
-def unfold3(W, mode):
+def unfold3(W, mode, out=None):
     require_cuda(W)
     W = f32c(W)
     I, J, K = W.shape
     shape = [(I, J * K), (J, I * K), (K, I * J)][mode]
-    out = torch.empty(shape, dtype=torch.float32, device=W.device)
+    out = torch.empty(shape, dtype=torch.float32, device=W.device) if out is None else out
     check(lib.admmq_unfold3(ptr(W), I, J, K, int(mode), ptr(out), stream_ptr(W.device)))
     return out
 
 
-def mttkrp(Wn, X, Y=None, precision=0):
+def mttkrp_workspace_bytes(M, nx, ny, R, precision=0):
+    return int(lib.admmq_mttkrp_workspace_bytes(int(M), int(nx), int(ny), int(R), int(precision)))
+
+
+def mttkrp(Wn, X, Y=None, precision=0, out=None, ws=None):
     """F = Wn @ khatri_rao(X, Y); Wn is the (M, nx*ny) unfolding."""
     require_cuda(Wn, X, Y)
     Wn, X = f32c(Wn), f32c(X)
@@ -171,15 +195,18 @@ def mttkrp(Wn, X, Y=None, precision=0):
     M, R = Wn.shape[0], X.shape[1]
     nx, ny = X.shape[0], (1 if Y is None else Y.shape[0])
     assert Wn.shape[1] == nx * ny, (Wn.shape, nx, ny)
-    F = torch.empty(M, R, dtype=torch.float32, device=Wn.device)
-    nbytes = lib.admmq_mttkrp_workspace_bytes(M, nx, ny, R, int(precision))
-    ws = workspace(nbytes, Wn.device)
+    F = torch.empty(M, R, dtype=torch.float32, device=Wn.device) if out is None else out
+    ws = _ws(mttkrp_workspace_bytes(M, nx, ny, R, precision), Wn.device, ws)
     check(lib.admmq_mttkrp(ptr(Wn), M, ptr(X), nx, ptr(Y), ny, R, ptr(F), int(precision), ptr(ws), ws.numel(),
                            stream_ptr(Wn.device)))
     return F
 
 
-def recon_error_sums(W0, A, X, Y=None):
+def recon_error_workspace_bytes(M, nx, ny):
+    return int(lib.admmq_recon_error_workspace_bytes(int(M), int(nx), int(ny)))
+
+
+def recon_error_sums(W0, A, X, Y=None, out=None, ws=None):
     """Device double[2] = {sum (W - [[A, X, Y]])^2, sum W^2}; W0 is the (M, nx*ny) mode-0 unfolding."""
     require_cuda(W0, A, X, Y)
     W0, A, X = f32c(W0), f32c(A), f32c(X)
@@ -187,24 +214,30 @@ def recon_error_sums(W0, A, X, Y=None):
     M, R = A.shape
     nx, ny = X.shape[0], (1 if Y is None else Y.shape[0])
     assert W0.shape == (M, nx * ny)
-    out = torch.empty(2, dtype=torch.float64, device=W0.device)
-    nbytes = lib.admmq_recon_error_workspace_bytes(M, nx, ny)
-    ws = workspace(nbytes, W0.device)
+    out = torch.empty(2, dtype=torch.float64, device=W0.device) if out is None else out
+    ws = _ws(recon_error_workspace_bytes(M, nx, ny), W0.device, ws)
     check(lib.admmq_recon_error(ptr(W0), M, ptr(A), ptr(X), nx, ptr(Y), ny, R, ptr(out), ptr(ws), ws.numel(),
                                 stream_ptr(W0.device)))
     return out
 
 
-def spd_inverse(G):
-    """(Minv [R, ld], rho [1], status [1]) of G + trace(G)/R * I."""
+def spd_inverse_workspace_bytes(R):
+    return int(lib.admmq_spd_inverse_workspace_bytes(int(R)))
+
+
+def spd_inverse(G, out=None, ws=None):
+    """(Minv [R, ld], rho [1], status [1]) of G + trace(G)/R * I.  `out` = preallocated (Minv, rho, status)."""
     require_cuda(G)
     G = f32c(G)
     R = G.shape[0]
     ld = lib.admmq_padded_ld(R)
-    Minv = torch.empty(R, ld, dtype=torch.float32, device=G.device)
-    rho = torch.empty(1, dtype=torch.float32, device=G.device)
-    status = torch.empty(1, dtype=torch.int32, device=G.device)
-    ws = workspace(lib.admmq_spd_inverse_workspace_bytes(R), G.device)
+    if out is None:
+        Minv = torch.empty(R, ld, dtype=torch.float32, device=G.device)
+        rho = torch.empty(1, dtype=torch.float32, device=G.device)
+        status = torch.empty(1, dtype=torch.int32, device=G.device)
+    else:
+        Minv, rho, status = out
+    ws = _ws(spd_inverse_workspace_bytes(R), G.device, ws)
     check(lib.admmq_spd_inverse(ptr(G), R, ptr(Minv), ptr(rho), ptr(status), ptr(ws), ws.numel(), stream_ptr(G.device)))
     return Minv, rho, status
 
@@ -224,6 +257,34 @@ def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempt
                                    qscheme_id(qscheme), int(num_attempts), ptr(codes), ptr(report), ptr(ws),
                                    ws.numel(), stream_ptr(H.device)))
     return report
+
+
+def admm_loop_workspace_bytes(I, R, num_attempts=200):
+    return int(lib.admmq_admm_loop_workspace_bytes(int(I), int(R), int(num_attempts)))
+
+
+def new_report(device):
+    return torch.empty(ctypes.sizeof(LoopReport), dtype=torch.uint8, device=device)
+
+
+def admm_loop_inplace(H, U, F, Minv, rho, inv_status, max_iter, eps, bits, qscheme, num_attempts=200, codes=None,
+                      report=None, ws=None):
+    """The persistent loop alone, given (Minv, rho, status) from `spd_inverse`; H and U are updated in place."""
+    require_cuda(H, U, F, Minv, rho)
+    for t in (H, U, F, Minv):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    I, R = H.shape
+    assert U.shape == H.shape and F.shape == H.shape and Minv.shape == (R, lib.admmq_padded_ld(R))
+    report = new_report(H.device) if report is None else report
+    ws = _ws(admm_loop_workspace_bytes(I, R, num_attempts), H.device, ws)
+    check(lib.admmq_admm_loop(ptr(H), ptr(U), ptr(F), ptr(Minv), ptr(rho), ptr(inv_status), I, R, int(max_iter),
+                              float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), ptr(codes), ptr(report),
+                              ptr(ws), ws.numel(), stream_ptr(H.device)))
+    return report
+
+
+def launch_count() -> int:
+    return int(lib.admmq_launch_count())
 
 
 def read_report(report: torch.Tensor) -> LoopReport:

@@ -1,19 +1,26 @@
 """Outer AO-ADMM loop of the reference CLI (scripts/factorize.py:176-318) as a reusable object.
 
-One `LayerSolver` owns one layer's problem on one GPU: the three unfoldings of W (made once),
-the factors, the scaled duals and the loss histories.  A sweep enqueues, per mode, the
-Gram-Hadamard, the MTTKRP, the persistent ADMM kernel and the re-projection, then two
-reconstruction-error reductions; the host synchronises once per sweep to apply the reference's
-stop rules (:259-263 / :303-307)."""
+One `LayerSolver` owns one layer's problem on one GPU: the unfoldings of W (made once), the
+factors, the scaled duals, every scratch buffer and the loss histories.  `enqueue_sweep()` puts one
+outer iteration on the current CUDA stream without allocating or synchronising - per mode the
+Gram-Hadamard, the MTTKRP, the ridge-system inverse, the persistent ADMM kernel and the
+re-projection, then the two reconstruction-error reductions - and `collect()` reads the two error
+sums and the loop reports back (one host sync per sweep) to apply the reference's stop rules
+(:259-263 / :303-307).  Several solvers can be enqueued back to back before the first `collect()`.
+"""
 import numpy as np
 import torch
 
 from . import _native
 
 
+def _bytes(n, device):
+    return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
+
+
 class LayerSolver:
     def __init__(self, weight, factors, bits, qscheme, max_iter_admm=1000, eps=1e-8, tol=1e-5,
-                 num_attempts=200, mttkrp_precision=0, init_is_random=True):
+                 num_attempts=200, mttkrp_precision=0, init_is_random=True, time_loops=False):
         _native.require_cuda(weight)
         assert weight.ndim in (2, 3), "Incorrect number of dimentions in weight tensor"
         self.W = _native.f32c(weight)
@@ -25,61 +32,125 @@ class LayerSolver:
         dev = self.W.device
         self.factors = [_native.f32c(f).to(dev).clone() for f in factors]
         self.duals = [torch.zeros_like(f) for f in self.factors]       # :209-212 / :272-273
-        self.factors_q = [None] * self.N
+        self.factors_q = [torch.empty_like(f) for f in self.factors]
         self.loss_hist, self.loss_quant_hist = [], []
-        self.reports = []
+        self.R = R = self.factors[0].shape[1]
         if self.N == 3:
             I, J, K = self.W.shape
             self.unfoldings = [self.W.reshape(I, J * K), _native.unfold3(self.W, 1), _native.unfold3(self.W, 2)]
         else:
             self.unfoldings = [self.W, self.W.t().contiguous()]
+        # ---- preallocated scratch (the C ABI never allocates; neither does a sweep)
+        dims = [f.shape[0] for f in self.factors]
+        ld = _native.lib.admmq_padded_ld(R)
+        self.G = torch.empty(R, R, dtype=torch.float32, device=dev)
+        self.F = [torch.empty(d, R, dtype=torch.float32, device=dev) for d in dims]
+        self.Minv = torch.empty(R, ld, dtype=torch.float32, device=dev)
+        self.rho = torch.empty(1, dtype=torch.float32, device=dev)
+        self.inv_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.reports_dev = [_native.new_report(dev) for _ in range(self.N)]
+        self.err_sums = torch.zeros(2, 2, dtype=torch.float64, device=dev)
+        others = [[k for k in range(self.N) if k != m] for m in range(self.N)]
+        self._others = others
+        nxny = [(dims[o[0]], dims[o[1]] if self.N == 3 else 1) for o in others]
+        self.ws_inv = _bytes(_native.spd_inverse_workspace_bytes(R), dev)
+        self.ws_loop = _bytes(max(_native.admm_loop_workspace_bytes(d, R, self.num_attempts) for d in dims), dev)
+        self.ws_proj = _bytes(_native.project_workspace_bytes(max(dims) * R, self.num_attempts), dev)
+        self.ws_mttkrp = _bytes(max(_native.mttkrp_workspace_bytes(dims[m], nxny[m][0], nxny[m][1], R,
+                                                                   self.mttkrp_precision) for m in range(self.N)), dev)
+        self.ws_err = _bytes(_native.recon_error_workspace_bytes(dims[0], nxny[0][0], nxny[0][1]), dev)
+        self.time_loops = bool(time_loops)
+        self.loop_events = []      # (mode, start, stop) CUDA events around the persistent kernel
+        self.last_reports = []
+        self._pending = False
         if not init_is_random:                                          # :192-201
             fq = [_native.project(f, self.bits, qscheme, self.num_attempts)[0] for f in self.factors]
             self.loss_hist.append(self._error(self.factors))
             self.loss_quant_hist.append(self._error(fq))
 
     # ---- pieces
-    def _others(self, mode):
-        return [self.factors[k] for k in range(self.N) if k != mode]
-
-    def _error_sums(self, fac):
-        if self.N == 3:
-            return _native.recon_error_sums(self.unfoldings[0], fac[0], fac[1], fac[2])
-        return _native.recon_error_sums(self.unfoldings[0], fac[0], fac[1], None)
+    def _error_sums(self, fac, out=None):
+        y = fac[2] if self.N == 3 else None
+        return _native.recon_error_sums(self.unfoldings[0], fac[0], fac[1], y, out=out, ws=self.ws_err)
 
     @staticmethod
     def _finish_error(sums):
-        num, den = (np.float32(v) for v in sums.cpu().numpy())
+        num, den = (np.float32(v) for v in sums)
         return float(np.sqrt(np.float32(num / den)))                    # source/admm.py:15 in float32
 
     def _error(self, fac):
-        return self._finish_error(self._error_sums(fac))
+        return self._finish_error(self._error_sums(fac).cpu().numpy())
 
     def update_mode(self, mode, codes=None):
         """One ALS step for `mode`: scripts/factorize.py:215-224 (and the two analogous blocks)."""
-        others = self._others(mode)
-        G = _native.gram_hadamard(others[0], others[1] if self.N == 3 else None)
-        F = _native.mttkrp(self.unfoldings[mode], others[0], others[1] if self.N == 3 else None,
-                           self.mttkrp_precision)
-        rep = _native.admm_iteration_inplace(self.factors[mode], self.duals[mode], F, G, self.max_iter_admm,
-                                             self.eps, self.bits, self.qscheme, self.num_attempts, codes)
-        self.reports.append(rep)
-        self.factors_q[mode] = _native.project(self.factors[mode], self.bits, self.qscheme, self.num_attempts)[0]
-        return F, G
+        o = self._others[mode]
+        X = self.factors[o[0]]
+        Y = self.factors[o[1]] if self.N == 3 else None
+        _native.gram_hadamard(X, Y, out=self.G)                                          # :215
+        _native.mttkrp(self.unfoldings[mode], X, Y, self.mttkrp_precision, out=self.F[mode], ws=self.ws_mttkrp)  # :217
+        _native.spd_inverse(self.G, out=(self.Minv, self.rho, self.inv_status), ws=self.ws_inv)  # source/admm.py:52-54
+        if self.time_loops:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        _native.admm_loop_inplace(self.factors[mode], self.duals[mode], self.F[mode], self.Minv, self.rho,
+                                  self.inv_status, self.max_iter_admm, self.eps, self.bits, self.qscheme,
+                                  self.num_attempts, codes, report=self.reports_dev[mode], ws=self.ws_loop)  # :218
+        if self.time_loops:
+            ev1.record()
+            self.loop_events.append((mode, ev0, ev1))
+        _native.project(self.factors[mode], self.bits, self.qscheme, self.num_attempts,
+                        out=self.factors_q[mode], ws=self.ws_proj)                       # :222
 
-    def sweep(self):
-        """One outer iteration (:214-258); returns (error, quantized_error) after one host sync."""
-        self.reports = []
+    def enqueue_sweep(self):
+        """One outer iteration (:214-255) on the current stream; no allocation, no host sync."""
         for mode in range(self.N):
             self.update_mode(mode)
-        s1 = self._error_sums(self.factors)                             # :246-248
-        s2 = self._error_sums(self.factors_q)                           # :249-253
-        for rep in self.reports:
-            _native.read_report(rep)                                    # LinAlgError on a non-PD system
-        err, errq = self._finish_error(s1), self._finish_error(s2)
+        self._error_sums(self.factors, out=self.err_sums[0])           # :246-248
+        self._error_sums(self.factors_q, out=self.err_sums[1])         # :249-253
+        self._pending = True
+
+    def collect(self):
+        """Host side of the sweep: read errors + reports (synchronises), append to the histories."""
+        assert self._pending, "collect() without enqueue_sweep()"
+        sums = self.err_sums.cpu().numpy()
+        self.last_reports = [_native.read_report(r) for r in self.reports_dev]  # LinAlgError on a non-PD system
+        err, errq = self._finish_error(sums[0]), self._finish_error(sums[1])
         self.loss_hist.append(err)
         self.loss_quant_hist.append(errq)
+        self._pending = False
         return err, errq
+
+    def sweep(self):
+        self.enqueue_sweep()
+        return self.collect()
+
+    # ---- host-buffer interface (the call a user with CPU tensors makes; bench.py's end-to-end leg)
+    def load_from_host(self, weight, factors, duals):
+        """Host -> device copy of the layer state (pinned tensors copy asynchronously on the current stream)
+        and re-derivation of the unfoldings.  Returns the number of bytes copied."""
+        n = 0
+        self.W.copy_(weight.reshape(self.W.shape), non_blocking=True)
+        n += self.W.numel() * 4
+        if self.N == 3:
+            _native.unfold3(self.W, 1, out=self.unfoldings[1])
+            _native.unfold3(self.W, 2, out=self.unfoldings[2])
+        else:
+            self.unfoldings[1].copy_(self.W.t())
+        for dst, src in zip(self.factors + self.duals, list(factors) + list(duals)):
+            dst.copy_(src, non_blocking=True)
+            n += dst.numel() * 4
+        return n
+
+    def store_to_host(self, factors, duals, factors_q, err_sums):
+        """Device -> host copy of the sweep's results into (pinned) host tensors; asynchronous - synchronise
+        the stream before reading them.  Returns the number of bytes copied."""
+        n = 0
+        for dst, src in zip(list(factors) + list(duals) + list(factors_q), self.factors + self.duals + self.factors_q):
+            dst.copy_(src, non_blocking=True)
+            n += src.numel() * 4
+        err_sums.copy_(self.err_sums, non_blocking=True)
+        self._pending = False
+        return n + self.err_sums.numel() * 8
 
     def should_stop(self):
         """Stop rules of scripts/factorize.py:259-263 (3-D) and :303-307 (2-D)."""
@@ -101,8 +172,24 @@ class LayerSolver:
                 break
         return sweeps
 
+    # ---- accounting used by bench.py (the unit of work is one inner iteration of one factor)
     def inner_iterations_per_sweep(self):
         return self.N * max(self.max_iter_admm - 1, 0)
+
+    def loop_algorithmic_bytes_per_sweep(self):
+        """16 B per element of H (read H, U, F; write H, U - counted once) + one pass over Minv, per inner
+        iteration, summed over the modes of one sweep (DESIGN.md 'roofline')."""
+        it = max(self.max_iter_admm - 1, 0)
+        return sum(it * (16 * f.shape[0] * self.R + 4 * self.R * self.R) for f in self.factors)
+
+    def candidate_evaluations_per_sweep(self):
+        it = max(self.max_iter_admm - 1, 0)
+        nc = self.num_attempts if self.qscheme == "tensor_mseminmax_symmetric" else 0
+        return sum(it * nc * f.shape[0] * self.R for f in self.factors)
+
+    def solve_flops_per_sweep(self):
+        it = max(self.max_iter_admm - 1, 0)
+        return sum(it * 2 * f.shape[0] * self.R * self.R for f in self.factors)
 
 
 def rank_from_reduction_rate(weight, reduction_rate):

@@ -59,6 +59,9 @@ ADMMQ_API int admmq_version(void);
 ADMMQ_API const char* admmq_last_error(void);
 /* sm count / compute capability of the current device; fails without one. */
 ADMMQ_API int admmq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernels this library has launched in the calling process so far (all threads).
+ * bench.py differences it around the timed region for its "gpu_launches" claim. */
+ADMMQ_API uint64_t admmq_launch_count(void);
 
 /* ------------------------------------------------------------------ projection
  * Replaces quantize_tensor(tensor, bits, qscheme, **kw)  source/quantization.py:69-115
@@ -126,7 +129,20 @@ typedef struct admmq_loop_report {
   float s;            /* last dual residual    sum (H-H_prev)^2 / sum U^2    source/admm.py:63 */
   int32_t best_index; /* chosen clip candidate of the last projection, -1 for other schemes */
   float absmax;       /* abs-max of the last projection input */
+  /* device-side profile of CTA 0 (%globaltimer, nanoseconds, barriers included in the phase they end):
+   * [0] ridge product H_ls = RHS.Minv, [1] clip search, [2] quantize + dual + residuals + exit test,
+   * [3] whole loop.  This is what a --profile run reports per layer without any host sync in the loop. */
+  uint64_t phase_ns[4];
 } admmq_loop_report;
+
+/* The loop alone, for callers that keep (Minv, rho) of a ridge system around (admmq_spd_inverse):
+ *   Minv  R x admmq_padded_ld(R) float32, rho / inv_status device scalars written by admmq_spd_inverse
+ *         (inv_status may be NULL; a non-zero value makes the loop return it in report->status untouched). */
+ADMMQ_API size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts);
+ADMMQ_API int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
+                    const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
+                    int num_attempts, int8_t* codes, admmq_loop_report* report,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 ADMMQ_API size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts);
 ADMMQ_API int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R,

@@ -269,6 +269,45 @@ def outer_loop_cases(ref):
     return out
 
 
+def self_divergence_cases(ref):
+    """How far the UNMODIFIED reference drifts from itself when every MTTKRP output is multiplied
+    by (1 +- 6e-8) (half a float32 ulp): BASELINE config 1, full inner budget, 2 sweeps.  This is the
+    yardstick for free-running error-history parity: an implementation
+    whose float32 ridge solve is not bit-identical to LAPACK's cannot track closer than this."""
+    W = config1_weight()
+    out, meta = {}, []
+    for trial, noise_seed in enumerate((101, 202)):
+        gn = torch.Generator().manual_seed(noise_seed)
+        A, B, C = ref.init_factors(W, 134, init="random", device=None, seed=42)
+        U_A, U_B, U_C = torch.zeros_like(A), torch.zeros_like(B), torch.zeros_like(C)
+
+        def jitter(F):
+            sign = torch.randint(0, 2, F.shape, generator=gn).float() * 2 - 1
+            return F * (1 + 6e-8 * sign)
+
+        loss, lossq = [], []
+        for _ in range(2):
+            G = B.T @ B * (C.T @ C)
+            F = jitter(torch.einsum("abc,cr,br->ar", W, C, B))
+            A, U_A = ref.admm_iteration(A, U_A, F, G, max_iter=1000, eps=1e-8, bits=4, qscheme=MSE)
+            Aq = ref.quantize_tensor(A, qscheme=MSE, bits=4)
+            G = A.T @ A * (C.T @ C)
+            F = jitter(torch.einsum("abc,cr,ar->br", W, C, A))
+            B, U_B = ref.admm_iteration(B, U_B, F, G, max_iter=1000, eps=1e-8, bits=4, qscheme=MSE)
+            Bq = ref.quantize_tensor(B, qscheme=MSE, bits=4)
+            G = A.T @ A * (B.T @ B)
+            F = jitter(torch.einsum("abc,br,ar->cr", W, B, A))
+            C, U_C = ref.admm_iteration(C, U_C, F, G, max_iter=1000, eps=1e-8, bits=4, qscheme=MSE)
+            Cq = ref.quantize_tensor(C, qscheme=MSE, bits=4)
+            loss.append(ref.squared_relative_diff(W, torch.einsum("ir,jr,kr->ijk", A, B, C)))
+            lossq.append(ref.squared_relative_diff(W, torch.einsum("ir,jr,kr->ijk", Aq, Bq, Cq)))
+        out[f"trial{trial}/loss"], out[f"trial{trial}/lossq"] = np.array(loss), np.array(lossq)
+        meta.append(dict(name=f"trial{trial}", noise_seed=noise_seed, eps=6e-8, sweeps=2, max_iter_admm=1000))
+        print("self-divergence trial", trial, loss, flush=True)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
 def rank_table():
     """source/rank_map.py is pure data; it pins the rank rule (scripts/factorize.py:157-158)."""
     spec = importlib.util.spec_from_file_location("ref_rank_map", os.path.join(REFERENCE_ROOT, "source", "rank_map.py"))
@@ -289,7 +328,8 @@ def main():
     os.makedirs(args.out, exist_ok=True)
     ref = import_reference()
     jobs = dict(projection=projection_cases, contractions=contraction_cases,
-                admm_iteration=admm_iteration_cases, outer_loop=outer_loop_cases)
+                admm_iteration=admm_iteration_cases, outer_loop=outer_loop_cases,
+                self_divergence=self_divergence_cases)
     for name, fn in jobs.items():
         if args.only and name not in args.only.split(","):
             continue
