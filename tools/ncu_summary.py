@@ -1,0 +1,61 @@
+"""Dev tool: turn ncu outputs under gpurun_out/ into the markdown summaries committed under profiles/."""
+import collections, csv, subprocess, sys
+
+
+def launches(csv_path, out_path, title):
+    rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
+    hdr = rows[0]
+    i_name, i_val, i_unit, i_grid, i_blk = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Unit", "Grid Size", "Block Size"))
+    agg = collections.defaultdict(lambda: [0, 0.0, set()])
+    for r in rows[1:]:
+        v = float(r[i_val].replace(",", ""))
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[i_unit], 1e-6)
+        k = r[i_name].split("(")[0].replace("void ", "")[:64]
+        agg[k][0] += 1
+        agg[k][1] += v
+        agg[k][2].add(f"{r[i_grid]}x{r[i_blk]}")
+    tot = sum(v[1] for v in agg.values())
+    with open(out_path, "w") as f:
+        f.write(f"# {title}\n\nPer-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
+        f.write(f"total {tot:.1f} ms over {sum(v[0] for v in agg.values())} launches\n\n| kernel | launches | total ms | share | grid x block |\n|---|---:|---:|---:|---|\n")
+        for k, (n, t, g) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"| `{k}` | {n} | {t:.2f} | {100 * t / tot:.1f} % | {', '.join(sorted(g))[:60]} |\n")
+
+
+def full(rep_path, out_path, title, top=25):
+    raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg.per_second",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+    src = subprocess.run(["ncu", "-i", rep_path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    with open(out_path, "w") as f:
+        f.write(f"# {title}\n\n| metric | unit | value |\n|---|---|---|\n")
+        for h, u, v in zip(hdr, units, vals):
+            if h in want:
+                f.write(f"| {h} | {u} | {v} |\n")
+        if len(srows) > 3:
+            sh = srows[1]
+            idx = {h: i for i, h in enumerate(sh)}
+            data = [r for r in srows[2:] if len(r) == len(sh)]
+            S = idx["# Samples"]
+            tot = sum(int(r[S] or 0) for r in data) or 1
+            f.write(f"\n## warp-stall sampling ({tot} samples)\n\n| reason | share |\n|---|---:|\n")
+            st = {h: sum(int(r[idx[h]] or 0) for r in data) for h in sh if h.startswith("stall_") and "Not Issued" not in h}
+            for h, v in sorted(st.items(), key=lambda x: -x[1])[:10]:
+                f.write(f"| {h} | {100 * v / tot:.1f} % |\n")
+            f.write(f"\n## hottest SASS instructions\n\n| samples | executed | SASS |\n|---:|---:|---|\n")
+            for r in sorted(data, key=lambda r: -int(r[S] or 0))[:top]:
+                f.write(f"| {r[S]} | {r[idx['Instructions Executed']]} | `{r[1][:80]}` |\n")
+
+
+if __name__ == "__main__":
+    kind = sys.argv[1]
+    (launches if kind == "launches" else full)(sys.argv[2], sys.argv[3], sys.argv[4])
