@@ -40,6 +40,7 @@ struct LoopParams {
   int max_iter;
   float eps;
   int bits, scheme, Nc;
+  float neg_zero;  // -0.0f as a run-time value (see search.cuh)
   int8_t* codes;
   admmq_loop_report* report;
   const float* rho;       // device scalar: trace(G)/R
@@ -52,22 +53,30 @@ struct LoopParams {
   const float* Minv;         // R x Rp
 };
 
+// P1 shared memory: two K-groups (256 threads each) work on alternating 16-deep slabs of the same
+// output tile and are summed at the end, so that 16 warps hide the L2 latency of the operand loads.
 template <int BM, int BN>
 struct __align__(16) GemmSmem {
-  float a[16][BM + 4];
-  float b[16][BN + 4];
+  float a[2][16][BM + 4];
+  float b[2][16][BN + 4];
+  float red[BM * BN];
+};
+
+struct ResidualSmem {
+  double red[4][kWarps];
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// P1: every CTA takes tiles round-robin; 256 threads as (BM/TM) x (BN/TN).
+// P1: every CTA takes tiles round-robin; each K-group of 256 threads as (BM/TM) x (BN/TN).
 template <int BM, int BN, int TM, int TN>
 __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned int* keys) {
   constexpr int TX = BN / TN, TY = BM / TM;
-  static_assert(TX * TY == kThreads, "thread tiling must cover the CTA");
-  const int t = threadIdx.x, tx = t % TX, ty = t / TX;
+  static_assert(TX * TY == 256, "thread tiling must cover the tile with one K-group");
+  const int kg = threadIdx.x >> 8, t = threadIdx.x & 255, tx = t % TX, ty = t / TX;
   const int I = p.I, R = p.R, Rp = p.Rp;
   const int tilesN = (R + BN - 1) / BN, tilesM = (I + BM - 1) / BM;
+  const int nslab = (R + 15) / 16, nstep = (nslab + 1) / 2;   // slab = 2 * step + kg
   const int arow = t >> 2, akq = (t & 3) * 4;                 // A loader: BM rows x 4 float4
   const int brow = t / (BN / 4), bc4 = (t % (BN / 4)) * 4;    // B loader: 16 rows x BN/4 float4
   unsigned int kmax = 0u, kinv = 0u;
@@ -79,54 +88,67 @@ __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned i
 #pragma unroll
       for (int n = 0; n < TN; ++n) acc[m][n] = 0.0f;
     float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-    auto fetch = [&](int k0) {
+    auto fetch = [&](int step) {
+      const int k0 = (2 * step + kg) * 16;
       ra = make_float4(0.f, 0.f, 0.f, 0.f);
       rb = ra;
       if (t < BM * 4 && i0 + arow < I && k0 + akq < Rp) ra = ldcg4(p.RHS + (size_t)(i0 + arow) * Rp + k0 + akq);
       if (t < 4 * BN && k0 + brow < R && n0 + bc4 < Rp) rb = __ldg(reinterpret_cast<const float4*>(p.Minv + (size_t)(k0 + brow) * Rp + n0 + bc4));
     };
     fetch(0);
-    for (int k0 = 0; k0 < R; k0 += 16) {
+    for (int step = 0; step < nstep; ++step) {
       __syncthreads();
       if (t < BM * 4) {
-        gs.a[akq + 0][arow] = ra.x;
-        gs.a[akq + 1][arow] = ra.y;
-        gs.a[akq + 2][arow] = ra.z;
-        gs.a[akq + 3][arow] = ra.w;
+        gs.a[kg][akq + 0][arow] = ra.x;
+        gs.a[kg][akq + 1][arow] = ra.y;
+        gs.a[kg][akq + 2][arow] = ra.z;
+        gs.a[kg][akq + 3][arow] = ra.w;
       }
-      if (t < 4 * BN) *reinterpret_cast<float4*>(&gs.b[brow][bc4]) = rb;
+      if (t < 4 * BN) *reinterpret_cast<float4*>(&gs.b[kg][brow][bc4]) = rb;
       __syncthreads();
-      if (k0 + 16 < R) fetch(k0 + 16);
+      if (step + 1 < nstep) fetch(step + 1);
 #pragma unroll
       for (int kk = 0; kk < 16; ++kk) {
         float av[TM], bv[TN];
 #pragma unroll
-        for (int m = 0; m < TM; ++m) av[m] = gs.a[kk][ty * TM + m];
+        for (int m = 0; m < TM; ++m) av[m] = gs.a[kg][kk][ty * TM + m];
 #pragma unroll
-        for (int n = 0; n < TN; ++n) bv[n] = gs.b[kk][tx * TN + n];
+        for (int n = 0; n < TN; ++n) bv[n] = gs.b[kg][kk][tx * TN + n];
 #pragma unroll
         for (int m = 0; m < TM; ++m)
 #pragma unroll
           for (int n = 0; n < TN; ++n) acc[m][n] = fmaf(av[m], bv[n], acc[m][n]);
       }
     }
+    // K-group 1 hands its partial tile to K-group 0 (fixed order: acc0 + acc1)
+    __syncthreads();
+    if (kg == 1) {
 #pragma unroll
-    for (int m = 0; m < TM; ++m)
+      for (int m = 0; m < TM; ++m)
 #pragma unroll
-      for (int n = 0; n < TN; ++n) {
-        const int i = i0 + ty * TM + m, c = n0 + tx * TN + n;
-        if (i < I && c < R) {
-          p.Hls[(size_t)i * Rp + c] = acc[m][n];
-          const float v = sub_rn(acc[m][n], __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
-          const unsigned int k = float_key(v);
-          kmax = max(kmax, k);
-          kinv = max(kinv, ~k);
+        for (int n = 0; n < TN; ++n) gs.red[(ty * TM + m) * BN + tx * TN + n] = acc[m][n];
+    }
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) {
+          const int i = i0 + ty * TM + m, c = n0 + tx * TN + n;
+          if (i < I && c < R) {
+            const float h = add_rn(acc[m][n], gs.red[(ty * TM + m) * BN + tx * TN + n]);
+            p.Hls[(size_t)i * Rp + c] = h;
+            const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
+            const unsigned int k = float_key(v);
+            kmax = max(kmax, k);
+            kinv = max(kinv, ~k);
+          }
         }
-      }
+    }
   }
   kmax = warp_max_u32(kmax);
   kinv = warp_max_u32(kinv);
-  if ((t & 31) == 0 && (kmax | kinv) != 0u) {
+  if ((threadIdx.x & 31) == 0 && (kmax | kinv) != 0u) {
     atomicMax(&keys[0], kmax);
     atomicMax(&keys[1], kinv);
   }
@@ -139,11 +161,37 @@ __global__ void __launch_bounds__(kInvThreads, 1) k_spd_inverse(InvParams p) {
   spd_inverse_body(p, sm, bar);
 }
 
+template <int BM, int BN>
+union LoopSmem {
+  SearchSmem search;
+  GemmSmem<BM, BN> gemm;
+  ResidualSmem res;
+};
+
+// sum over the CTA of four per-thread doubles, result valid in every thread
+__device__ __forceinline__ void cta_sum4(double v[4], ResidualSmem& rs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rs.red[q][warp] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += rs.red[q][w];
+    v[q] = s;
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
-  __shared__ SearchSmem sm;
-  __shared__ GemmSmem<BM, BN> gs;
-  __shared__ double sred[4][kThreads];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LoopSmem<BM, BN>& sm = *reinterpret_cast<LoopSmem<BM, BN>*>(smem_raw);
   const int t = threadIdx.x;
   LoopHeader* hdr = p.hdr;
   admmq_loop_report rep;
@@ -177,18 +225,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
   const long long e0 = min(N, (long long)blockIdx.x * cs), e1 = min(N, e0 + cs);
   const Levels L = make_levels(p.bits);
   const float qnan = __int_as_float(0x7fc00000);
+  // (row, column) of this thread's first element; advanced by kThreads elements at a time
+  const int row0 = (int)((e0 + t) / R), col0 = (int)((e0 + t) - (long long)row0 * R);
+  const int drow = kThreads / R, dcol = kThreads - drow * R;
 
   // RHS = F + rho * (H + U) for the first iteration (:56)
-  for (long long e = e0 + t; e < e1; e += kThreads) {
-    const int ei = (int)e, i = ei / R, n = ei - i * R;
-    p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(p.H[e], p.U[e])));
+  {
+    int i = row0, n = col0;
+    for (long long e = e0 + t; e < e1; e += kThreads) {
+      p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(p.H[e], p.U[e])));
+      i += drow;
+      n += dcol;
+      if (n >= R) {
+        n -= R;
+        ++i;
+      }
+    }
   }
   bar.sync();
 
   for (int j = 1; j < p.max_iter; ++j) {  // range(1, max_iter), :55
     const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
     // ---------------- P1
-    gemm_phase<BM, BN, TM, TN>(p, gs, hdr->keys[slot]);
+    gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
     if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
       if (t < 4) hdr->keys[next_slot][t] = 0u;
       for (int c = t; c < p.Nc; c += kThreads) p.cand[(size_t)next_slot * kMaxCandidates + c] = 0ull;
@@ -220,11 +279,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
               const int ei = (int)e, i = ei / R, n = ei - i * R;  // I*R < 2^31 is checked on the host
               return sub_rn(__ldcg(Hls + (size_t)i * Rp + n), __ldcg(U + e));
             },
-            e0, e1, absmax, p.Nc, L, (double)N, cand, sm);
+            e0, e1, absmax, p.Nc, L, (double)N, cand, sm.search, p.neg_zero);
         bar.sync();
         lap(1);
         // ---------------- P3
-        rep.best_index = cta_best_candidate(cand, p.Nc, absmax, (double)N, sm);
+        rep.best_index = cta_best_candidate(cand, p.Nc, absmax, (double)N, sm.search);
         qp.scale = scale_of(clip_candidate(make_clip_grid(absmax, p.Nc), rep.best_index), L);
       }
     } else {
@@ -232,25 +291,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
       qp = params_from_minmax(p.scheme, p.bits, tmin, tmax, L);
     }
     rep.scale = qp.scale;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (long long e = e0 + t; e < e1; e += kThreads) {
-      const int ei = (int)e, i = ei / R, n = ei - i * R;
-      const float hls = __ldcg(p.Hls + (size_t)i * Rp + n);
-      const float u = __ldcg(p.U + e);
-      const float v = sub_rn(hls, u);
-      float code = 0.0f;
-      const float hq = degenerate ? qnan : quantize_value(v, qp, L, code);   // H = Q(H_ls - U)   (:59)
-      const float d1 = sub_rn(hq, hls);
-      const float un = add_rn(u, d1);                                        // U += H - H_ls     (:60)
-      const float d2 = sub_rn(hq, __ldcg(p.H + e));
-      s0 += (double)mul_rn(d1, d1);  // sum (H - H_ls)^2     (:62)
-      s1 += (double)mul_rn(hq, hq);  // sum H^2
-      s2 += (double)mul_rn(d2, d2);  // sum (H - H_prev)^2   (:63)
-      s3 += (double)mul_rn(un, un);  // sum U^2
-      p.H[e] = hq;
-      p.U[e] = un;
-      p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(hq, un)));
-      if (p.codes != nullptr) p.codes[e] = (int8_t)code;
+    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f, f3 = 0.0f;
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+      int i = row0, n = col0, cnt = 0;
+      for (long long e = e0 + t; e < e1; e += kThreads) {
+        const float hls = __ldcg(p.Hls + (size_t)i * Rp + n);
+        const float u = __ldcg(p.U + e);
+        const float v = sub_rn(hls, u);
+        float code = 0.0f;
+        const float hq = degenerate ? qnan : quantize_value(v, qp, L, code);   // H = Q(H_ls - U)   (:59)
+        const float d1 = sub_rn(hq, hls);
+        const float un = add_rn(u, d1);                                        // U += H - H_ls     (:60)
+        const float d2 = sub_rn(hq, p.H[e]);
+        f0 = fmaf(d1, d1, f0);  // sum (H - H_ls)^2     (:62)
+        f1 = fmaf(hq, hq, f1);  // sum H^2
+        f2 = fmaf(d2, d2, f2);  // sum (H - H_prev)^2   (:63)
+        f3 = fmaf(un, un, f3);  // sum U^2
+        p.H[e] = hq;
+        p.U[e] = un;
+        p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(hq, un)));
+        if (p.codes != nullptr) p.codes[e] = (int8_t)code;
+        i += drow;
+        n += dcol;
+        if (n >= R) {
+          n -= R;
+          ++i;
+        }
+        if (++cnt == 16) {  // float32 partial sums over at most 16 elements, float64 beyond
+          sums[0] += (double)f0;
+          sums[1] += (double)f1;
+          sums[2] += (double)f2;
+          sums[3] += (double)f3;
+          f0 = f1 = f2 = f3 = 0.0f;
+          cnt = 0;
+        }
+      }
+      sums[0] += (double)f0;
+      sums[1] += (double)f1;
+      sums[2] += (double)f2;
+      sums[3] += (double)f3;
     }
     if (degenerate) {  // uniform: the reference would carry NaN through every remaining iteration
       rep.status |= ADMMQ_ST_NONFINITE;
@@ -258,44 +338,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
       rep.s = qnan;
       break;
     }
-    sred[0][t] = s0;
-    sred[1][t] = s1;
-    sred[2][t] = s2;
-    sred[3][t] = s3;
-    __syncthreads();
-    for (int s = kThreads / 2; s > 0; s >>= 1) {
-      if (t < s) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sred[q][t] += sred[q][t + s];
-      }
-      __syncthreads();
-    }
-    if (t < 4) p.slots[(size_t)blockIdx.x * 4 + t] = sred[t][0];
+    cta_sum4(sums, sm.res);
+    if (t < 4) p.slots[(size_t)blockIdx.x * 4 + t] = sums[t];
     bar.sync();
     // ---------------- exit test (:62-65), evaluated identically by every CTA
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = t; c < (int)gridDim.x; c += kThreads) {
-      a0 += __ldcg(p.slots + (size_t)c * 4 + 0);
-      a1 += __ldcg(p.slots + (size_t)c * 4 + 1);
-      a2 += __ldcg(p.slots + (size_t)c * 4 + 2);
-      a3 += __ldcg(p.slots + (size_t)c * 4 + 3);
-    }
-    __syncthreads();
-    sred[0][t] = a0;
-    sred[1][t] = a1;
-    sred[2][t] = a2;
-    sred[3][t] = a3;
-    __syncthreads();
-    for (int s = kThreads / 2; s > 0; s >>= 1) {
-      if (t < s) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sred[q][t] += sred[q][t + s];
-      }
-      __syncthreads();
+      for (int q = 0; q < 4; ++q) tot[q] += __ldcg(p.slots + (size_t)c * 4 + q);
     }
-    rep.r = div_rn((float)sred[0][0], (float)sred[1][0]);
-    rep.s = div_rn((float)sred[2][0], (float)sred[3][0]);
-    __syncthreads();
+    cta_sum4(tot, sm.res);
+    rep.r = div_rn((float)tot[0], (float)tot[1]);
+    rep.s = div_rn((float)tot[2], (float)tot[3]);
     lap(2);
     if (rep.r < p.eps && rep.s < p.eps) {
       rep.status |= ADMMQ_ST_CONVERGED;
@@ -429,6 +483,7 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.bits = bits;
   p.scheme = qscheme;
   p.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
+  p.neg_zero = -0.0f;
   p.codes = codes;
   p.report = report;
   p.rho = rho;
@@ -441,12 +496,14 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.Minv = Minv;
   void* args[] = {&p};
   const void* fn = nullptr;
+  size_t smem = 0;
   switch (pick_tile(I, R, grid)) {
-    case 0: fn = (const void*)k_admm_loop<64, 64, 4, 4>; break;
-    case 1: fn = (const void*)k_admm_loop<32, 32, 2, 2>; break;
-    default: fn = (const void*)k_admm_loop<16, 32, 1, 2>; break;
+    case 0: fn = (const void*)k_admm_loop<64, 64, 4, 4>; smem = sizeof(LoopSmem<64, 64>); break;
+    case 1: fn = (const void*)k_admm_loop<32, 32, 2, 2>; smem = sizeof(LoopSmem<32, 32>); break;
+    default: fn = (const void*)k_admm_loop<16, 32, 1, 2>; smem = sizeof(LoopSmem<16, 32>); break;
   }
-  ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
+  ADMMQ_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
   count_launches(1);
   return ADMMQ_OK;
 }

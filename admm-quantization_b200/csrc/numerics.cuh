@@ -123,18 +123,46 @@ ADMMQ_HD float sqerr_exact(float x, float scale, const Levels& L) {
   return mul_rn(d, d);
 }
 
+// Deviation (x - code*scale) with every intermediate rounded to float32 (:127, :138) - exact form.
+ADMMQ_HD float dev_exact(float x, float scale, const Levels& L) {
+  return sub_rn(x, mul_rn(code_exact(x, scale, L), scale));
+}
+
 // Fast path used inside the 200-candidate search: the code is obtained from x * (1/scale)
 // (no division); `frac` returns |t - k| so that the caller can detect the rare inputs whose
 // quotient lies too close to a rounding boundary for the shortcut to be provably equal to
-// code_exact() and redo them with sqerr_exact().  MAGIC rounding = round-half-even for |t| < 2^22.
-ADMMQ_HD float sqerr_fast(float x, float scale, float rcp_scale, const Levels& L, float& frac) {
+// code_exact() and redo them with dev_exact().  MAGIC rounding = round-half-even for |t| < 2^22
+// (|t| <= 37.5 here: |x| <= absmax and scale >= 0.2 * absmax * 2 / denom).
+ADMMQ_HD float dev_fast(float x, float scale, float rcp_scale, const Levels& L, float& frac) {
   const float MAGIC = 12582912.0f;  // 1.5 * 2^23
   float t = mul_rn(x, rcp_scale);
   t = fminf(fmaxf(t, L.fast_lo), L.fast_hi);
   const float k = sub_rn(add_rn(t, MAGIC), MAGIC);
   frac = fabsf(sub_rn(t, k));
-  const float d = sub_rn(x, mul_rn(k, scale));
+  return sub_rn(x, mul_rn(k, scale));
+}
+ADMMQ_HD float sqerr_fast(float x, float scale, float rcp_scale, const Levels& L, float& frac) {
+  const float d = dev_fast(x, scale, rcp_scale, L, frac);
   return mul_rn(d, d);
+}
+
+// --- the summation recipe of the clip search ---------------------------------------------
+// The reference takes `mean((x - xq)**2)` in float32 with ATen's reduction order, which no other
+// implementation can reproduce bit for bit.  The kernels define the per-candidate sum as follows
+// (tests/hostcheck pins this definition against the reference's argmin on the golden vectors):
+//   * elements are taken in aligned groups of 8 (kSumGroup); missing tail elements count as x = 0,
+//     which contributes exactly 0;
+//   * within a group two float32 FMA chains accumulate d*d, one over the even and one over the odd
+//     positions (the two lanes of a packed f32x2 FMA), and are added in float32;
+//   * group sums are added in float64 in element order, the CTA/chunk totals in 64-bit fixed point.
+constexpr int kSumGroup = 8;
+ADMMQ_HD float group_sum8(const float d[kSumGroup]) {
+  float even = 0.0f, odd = 0.0f;
+  for (int i = 0; i < kSumGroup; i += 2) {
+    even = fma_rn(d[i], d[i], even);
+    odd = fma_rn(d[i + 1], d[i + 1], odd);
+  }
+  return add_rn(even, odd);
 }
 
 // --- fixed-point accumulation of the per-candidate squared-error sums --------------------

@@ -41,7 +41,8 @@ __device__ __forceinline__ void read_minmax(const ProjectHeader* hdr, float& tmi
 }
 
 __global__ void __launch_bounds__(kThreads) k_mse_sums(const float* x, long long n, int bits, int Nc,
-                                                      const ProjectHeader* hdr, unsigned long long* cand_sums) {
+                                                      const ProjectHeader* hdr, unsigned long long* cand_sums,
+                                                      float neg_zero) {
   __shared__ SearchSmem sm;
   float tmin, tmax, absmax;
   read_minmax(hdr, tmin, tmax, absmax);
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(kThreads) k_mse_sums(const float* x, long long
   const Levels L = make_levels(bits);
   const long long cs = chunk_size(n, gridDim.x);
   const long long e0 = min(n, (long long)blockIdx.x * cs), e1 = min(n, e0 + cs);
-  cta_candidate_sums([x](long long e) { return x[e]; }, e0, e1, absmax, Nc, L, (double)n, cand_sums, sm);
+  cta_candidate_sums([x](long long e) { return x[e]; }, e0, e1, absmax, Nc, L, (double)n, cand_sums, sm, neg_zero);
 }
 
 __global__ void __launch_bounds__(kThreads) k_apply(const float* x, long long n, int bits, int scheme, int Nc,
@@ -128,14 +129,14 @@ extern "C" int admmq_project(const float* x, int64_t n, int bits, int qscheme, i
   ProjectHeader* hdr = (ProjectHeader*)workspace;
   unsigned long long* cand = (unsigned long long*)((char*)workspace + align_up(sizeof(ProjectHeader), 256));
   ADMMQ_CUDA_OK(cudaMemsetAsync(workspace, 0, admmq_project_workspace_bytes(n, num_attempts), stream));
-  const long long max_ctas = (long long)dp.sm_count * 8;
+  const long long max_ctas = (long long)dp.sm_count * 4;
   const int g_stream = (int)std::min<long long>(max_ctas, (n + kThreads * 4 - 1) / (kThreads * 4));
   k_minmax_keys<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, hdr);
   if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) {
-    // one chunk of >= 64 elements per CTA, at most 4 CTAs per SM
-    const long long want = (n + kChunkAlign - 1) / kChunkAlign;
-    const int g = (int)std::max<long long>(1, std::min<long long>((long long)dp.sm_count * 4, want));
-    k_mse_sums<<<g, kThreads, 0, stream>>>(x, n, bits, num_attempts, hdr, cand);
+    // one chunk of >= 512 elements (4 groups of 8 per warp) per CTA, at most one CTA per SM
+    const long long want = (n + 511) / 512;
+    const int g = (int)std::max<long long>(1, std::min<long long>((long long)dp.sm_count, want));
+    k_mse_sums<<<g, kThreads, 0, stream>>>(x, n, bits, num_attempts, hdr, cand, -0.0f);
   }
   k_apply<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, bits, qscheme, num_attempts, hdr, cand, tmin, tmax,
                                                             xq, codes, info);

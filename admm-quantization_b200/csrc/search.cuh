@@ -3,31 +3,75 @@
 // projection kernels (project.cu) and the persistent ADMM loop (admm_loop.cu).
 //
 // Work split: the CTA's elements are staged through shared memory; every warp walks its
-// slice of the stage reading one element at a time as a warp-wide broadcast, and each LANE
-// owns CPL candidates (scale and 1/scale in registers) -> no per-candidate warp reduction.
-// Squared errors are added in float32 over aligned groups of 8 consecutive elements and the
-// group sums go into float64; the CTA total is converted to fixed point and added to the
-// global per-candidate accumulators with integer atomics (order independent).
+// slice of the stage in aligned groups of 8 elements read as warp-wide broadcasts (2 x LDS.128),
+// and each LANE owns kCPL candidates (scale and 1/scale in registers, duplicated into both
+// halves of a packed f32x2 register) -> no per-candidate warp reduction.  One candidate
+// evaluation is ~6 issue slots: the multiplies/adds run as packed FFMA2/FADD2/FMUL2 on two
+// elements at a time, only the clamp (FMNMX) and the boundary check (FMNMX3) are scalar.
+// Group sums follow the group_sum8 recipe of numerics.cuh, go into float64 per lane, and the
+// CTA total is converted to fixed point and added to the global per-candidate accumulators
+// with integer atomics (order independent => deterministic for any grid size).
 #pragma once
 #include "common.cuh"
 #include "numerics.cuh"
 
 namespace admmq {
 
-constexpr int kThreads = 256;               // CTA size of every kernel that uses these helpers
+constexpr int kThreads = 512;               // CTA size of every kernel that uses these helpers
 constexpr int kWarps = kThreads / 32;
 constexpr int kCPL = 7;                     // candidates per lane per pass (200 = 6.25 * 32)
 constexpr int kCandPerPass = 32 * kCPL;     // 224
-constexpr int kStage = 2048;                // elements staged in shared memory at a time
-constexpr int kGroup = 8;                   // float32 accumulation group (aligned, see header)
+constexpr int kStage = 4096;                // elements staged in shared memory at a time
+constexpr int kGroup = kSumGroup;           // accumulation group (aligned, see numerics.cuh)
 constexpr int kMaxCandidates = 1024;        // num_attempts limit (custom_benchmark.py uses 1000)
 constexpr int kChunkAlign = 64;             // CTA chunks are multiples of this many elements
 
 struct SearchSmem {
-  float stage[kStage];
+  __align__(16) float stage[kStage];
   double red[kWarps * kCandPerPass];
   unsigned long long key[kWarps];
 };
+
+// ---- packed pairs of float32 (two independent IEEE round-to-nearest operations per instruction).
+// NOTE: ptxas fuses a single-use mul.rn.f32x2 feeding an add/sub.rn.f32x2 into one FFMA2 (unlike the
+// scalar .rn forms), and it also folds fma(a, b, -0.0) back into a multiply when the -0.0 is a visible
+// constant.  The product k*scale must be rounded on its own (the reference rounds `codes * scale`, then
+// `x - xq`), so it is written as fma(k, scale, nz) with nz = -0.0 taken from a KERNEL PARAMETER, which
+// ptxas cannot constant-fold: adding -0.0 is the identity for every value including both zeros.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
 // Elements [e0, e1) of the flattened tensor belong to this CTA.
 __host__ __device__ inline long long chunk_size(long long n, int ctas) {
@@ -35,60 +79,93 @@ __host__ __device__ inline long long chunk_size(long long n, int ctas) {
   return (c + kChunkAlign - 1) / kChunkAlign * kChunkAlign;
 }
 
+// One candidate (scale s, 1/s duplicated in both halves) on two elements x = (x0, x1):
+// acc += d*d per half with d = x - k*s, k = clamp(rint(x/s)) via the reciprocal + magic-number
+// shortcut (numerics.cuh dev_fast); `worst` collects the distance of the quotient from its rounded value.
+__device__ __forceinline__ void eval_pair(f32x2 x, f32x2 s, f32x2 rc, const Levels& L, f32x2 magic, f32x2 nmagic,
+                                          f32x2 nzero, f32x2& acc, float& worst) {
+  const f32x2 t = mul2(x, rc);
+  float t0, t1;
+  unpack2(t, t0, t1);
+  t0 = fminf(fmaxf(t0, L.fast_lo), L.fast_hi);
+  t1 = fminf(fmaxf(t1, L.fast_lo), L.fast_hi);
+  const f32x2 tc = pack2(t0, t1);
+  const f32x2 k = add2(add2(tc, magic), nmagic);
+  float f0, f1;
+  unpack2(sub2(tc, k), f0, f1);
+  worst = max3(worst, fabsf(f0), fabsf(f1));
+  const f32x2 d = sub2(x, fma2(k, s, nzero));
+  acc = fma2(d, d, acc);
+}
+
 // Adds this CTA's share of sum_e (x_e - Q_c(x_e))^2 for every candidate c < Nc into
 // cand_sums[c] (fixed point, see numerics.cuh).  loadv(e) returns element e.
 template <class LoadV>
 __device__ void cta_candidate_sums(LoadV loadv, long long e0, long long e1, float absmax, int Nc,
                                    const Levels L, double n_total, unsigned long long* cand_sums,
-                                   SearchSmem& sm) {
+                                   SearchSmem& sm, float opaque_neg_zero) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (e0 >= e1) return;  // uniform per CTA
   const ClipGrid g = make_clip_grid(absmax, Nc);
   const double unit_inv = fixed_point_unit_inv(n_total, absmax);
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  const f32x2 nzero = pack2(opaque_neg_zero, opaque_neg_zero);
   for (int c0 = 0; c0 < Nc; c0 += kCandPerPass) {
-    float sc[kCPL], rc[kCPL];
+    f32x2 sc[kCPL], rc[kCPL];
     double dacc[kCPL];
 #pragma unroll
     for (int j = 0; j < kCPL; ++j) {
       const int c = c0 + j * 32 + lane;
       const float s = (c < Nc) ? scale_of(clip_candidate(g, c), L) : 1.0f;
-      sc[j] = s;
-      rc[j] = (c < Nc) ? div_rn(1.0f, s) : 0.0f;
+      const float r = (c < Nc) ? div_rn(1.0f, s) : 0.0f;
+      sc[j] = pack2(s, s);
+      rc[j] = pack2(r, r);
       dacc[j] = 0.0;
     }
     for (long long base = e0; base < e1; base += kStage) {
       const int cnt = (int)min((long long)kStage, e1 - base);
+      const int cnt8 = (cnt + kGroup - 1) / kGroup * kGroup;  // zero padding contributes exactly 0
       __syncthreads();
-      for (int i = threadIdx.x; i < cnt; i += kThreads) sm.stage[i] = loadv(base + i);
+      for (int i = threadIdx.x; i < cnt8; i += kThreads) sm.stage[i] = (i < cnt) ? loadv(base + i) : 0.0f;
       __syncthreads();
       // warp slice, multiple of kGroup (base and e0 are multiples of kChunkAlign)
-      int per = (cnt + kWarps - 1) / kWarps;
+      int per = (cnt8 + kWarps - 1) / kWarps;
       per = (per + kGroup - 1) / kGroup * kGroup;
-      const int wb = min(warp * per, cnt), we = min(wb + per, cnt);
+      const int wb = min(warp * per, cnt8), we = min(wb + per, cnt8);
       for (int gb = wb; gb < we; gb += kGroup) {
-        float acc[kCPL];
+        const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&sm.stage[gb]);
+        const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&sm.stage[gb + 4]);
+        const f32x2 xs[4] = {va.x, va.y, vb.x, vb.y};
+        f32x2 acc[kCPL];
+        float worst = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kCPL; ++j) acc[j] = 0.0f;
-        const int ge = min(gb + kGroup, we);
-        for (int i = gb; i < ge; ++i) {
-          const float x = sm.stage[i];
-          float c[kCPL];
-          float worst = 0.0f;
+        for (int j = 0; j < kCPL; ++j) {
+          acc[j] = 0ull;  // (+0.0f, +0.0f)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) eval_pair(xs[q], sc[j], rc[j], L, magic, nmagic, nzero, acc[j], worst);
+        }
+        if (!(worst <= L.fast_thr)) {  // rare: a quotient too close to a rounding boundary (or non-finite)
 #pragma unroll
           for (int j = 0; j < kCPL; ++j) {
-            float frac;
-            c[j] = sqerr_fast(x, sc[j], rc[j], L, frac);
-            worst = fmaxf(worst, frac);
-          }
-          if (!(worst <= L.fast_thr)) {  // rare: quotient too close to a rounding boundary (or non-finite)
+            float s0, s1, even = 0.0f, odd = 0.0f;
+            unpack2(sc[j], s0, s1);
 #pragma unroll
-            for (int j = 0; j < kCPL; ++j) c[j] = sqerr_exact(x, sc[j], L);
+            for (int q = 0; q < 4; ++q) {
+              float x0, x1;
+              unpack2(xs[q], x0, x1);
+              const float d0 = dev_exact(x0, s0, L), d1 = dev_exact(x1, s0, L);
+              even = fma_rn(d0, d0, even);
+              odd = fma_rn(d1, d1, odd);
+            }
+            acc[j] = pack2(even, odd);
           }
-#pragma unroll
-          for (int j = 0; j < kCPL; ++j) acc[j] = add_rn(acc[j], c[j]);
         }
 #pragma unroll
-        for (int j = 0; j < kCPL; ++j) dacc[j] += (double)acc[j];
+        for (int j = 0; j < kCPL; ++j) {
+          float even, odd;
+          unpack2(acc[j], even, odd);
+          dacc[j] += (double)add_rn(even, odd);
+        }
       }
     }
     // fixed-order reduction over the CTA's warps, then one integer atomic per candidate

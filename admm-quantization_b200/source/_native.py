@@ -46,6 +46,7 @@ def _load():
         "admmq_mttkrp": (c_int, [vp, c_int, vp, c_int, vp, c_int, c_int, vp, c_int, vp, c_sz, vp]),
         "admmq_recon_error_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_recon_error": (c_int, [vp, c_int, vp, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
+        "admmq_gemm_nt": (c_int, [vp, c_int, c_int, vp, c_int, c_int, c_int, vp, c_int, vp]),
         "admmq_padded_ld": (c_int, [c_int]),
         "admmq_spd_inverse_workspace_bytes": (c_sz, [c_int]),
         "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, vp, c_sz, vp]),
@@ -65,7 +66,7 @@ def _load():
 
 lib = _load()
 EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count admmq_project_workspace_bytes "
-           "admmq_project admmq_admm_loop_workspace_bytes admmq_admm_loop "
+           "admmq_project admmq_admm_loop_workspace_bytes admmq_admm_loop admmq_gemm_nt "
            "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
            "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration").split()
@@ -219,6 +220,18 @@ def recon_error_sums(W0, A, X, Y=None, out=None, ws=None):
     check(lib.admmq_recon_error(ptr(W0), M, ptr(A), ptr(X), nx, ptr(Y), ny, R, ptr(out), ptr(ws), ws.numel(),
                                 stream_ptr(W0.device)))
     return out
+
+
+def gemm_nt(A, B, out=None):
+    """C = A @ B.T in 3xTF32 on the tensor cores; A (M, K), B (N, K) float32 with K % 4 == 0 (or zero padded)."""
+    require_cuda(A, B)
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.stride(1) == 1 and B.stride(1) == 1
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device) if out is None else out
+    check(lib.admmq_gemm_nt(ptr(A), A.stride(0), M, ptr(B), B.stride(0), N, K, ptr(C), C.stride(0), stream_ptr(A.device)))
+    return C
 
 
 def spd_inverse_workspace_bytes(R):

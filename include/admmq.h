@@ -102,6 +102,15 @@ ADMMQ_API size_t admmq_recon_error_workspace_bytes(int M, int nx, int ny);
 ADMMQ_API int admmq_recon_error(const float* W0, int M, const float* A, const float* X, int nx, const float* Y, int ny,
                       int R, double* out2, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ tensor-core building block
+ * C (M x N, ldc) = A (M x K, lda) . B (N x K, ldb)^T in 3xTF32 on tcgen05/TMEM: float32 operands are split into
+ * tf32 hi + lo on the fly and accumulated as lo.hi + hi.lo + hi.hi in float32 (csrc/tc_gemm.cuh).  This is the tile
+ * product behind the throughput mode of the ridge product (source/admm.py:56) and of the 2-D MTTKRP
+ * (scripts/factorize.py:277,287).  lda, ldb multiples of 4 and >= K; columns [K, round_up(K, 4)) of A and B must be
+ * readable and zero; A, B 16-byte aligned. */
+ADMMQ_API int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int ldb, int N, int K, float* C, int ldc,
+                  void* stream);
+
 /* ------------------------------------------------------------------ ridge system
  * rho = trace(G)/R and Minv = (G + rho I)^-1  (replaces torch.linalg.cholesky at source/admm.py:52-54;
  * the per-iteration cholesky_solve of :56 becomes a product with Minv).  Blocked float64 Cholesky +

@@ -20,9 +20,9 @@ void hc_candidates(float absmax, int n, int bits, float* clip, float* scale) {
   }
 }
 
-// per-candidate MSE exactly as the kernels form it: fast path with exact fallback, float32 sums over
-// aligned groups of 8, float64 across groups, fixed point, float32 mean.  Returns the number of
-// elements that needed the exact-division fallback.
+// per-candidate MSE exactly as the kernels form it: fast path with exact fallback per group of 8,
+// the group_sum8 recipe of numerics.cuh, float64 across groups, fixed point, float32 mean.
+// Returns the number of groups that needed the exact-division fallback.
 long long hc_mse(const float* x, long long n, float absmax, int bits, int nc, float* mse, int* best, int force_exact) {
   const Levels L = make_levels(bits);
   const ClipGrid g = make_clip_grid(absmax, nc);
@@ -33,18 +33,20 @@ long long hc_mse(const float* x, long long n, float absmax, int bits, int nc, fl
     const float s = scale_of(clip_candidate(g, c), L);
     const float r = div_rn(1.0f, s);
     double tot = 0.0;
-    for (long long b = 0; b < n; b += 8) {
-      float acc = 0.0f;
-      for (long long i = b; i < n && i < b + 8; ++i) {
+    for (long long b = 0; b < n; b += kSumGroup) {
+      float d[kSumGroup];
+      float worst = 0.0f;
+      for (int i = 0; i < kSumGroup; ++i) {
+        const float xv = (b + i < n) ? x[b + i] : 0.0f;
         float frac;
-        float v = sqerr_fast(x[i], s, r, L, frac);
-        if (force_exact || !(frac <= L.fast_thr)) {
-          v = sqerr_exact(x[i], s, L);
-          ++slow;
-        }
-        acc = add_rn(acc, v);
+        d[i] = dev_fast(xv, s, r, L, frac);
+        worst = fmaxf(worst, frac);
       }
-      tot += (double)acc;
+      if (force_exact || !(worst <= L.fast_thr)) {
+        for (int i = 0; i < kSumGroup; ++i) d[i] = dev_exact((b + i < n) ? x[b + i] : 0.0f, s, L);
+        ++slow;
+      }
+      tot += (double)group_sum8(d);
     }
     const long long fx = llrint(tot * unit_inv);
     mse[c] = mse_from_fixed(fx, unit, (float)n);

@@ -1,0 +1,52 @@
+// Dev tool: cycle breakdown of the tcgen05 tile pipeline (compiled with -DADMMQ_TC_PROFILE).
+#include <cstdio>
+#include <vector>
+#define ADMMQ_TC_PROFILE 1
+#include "../../admm-quantization_b200/csrc/tc_gemm.cuh"
+namespace admmq { char* error_buffer() { static char b[8]; return b; } int fail(int c, const char*, ...) { return c; } void count_launches(int) {} int device_props(DeviceProps*) { return 0; } }
+using namespace admmq;
+template <int BN>
+__global__ void __launch_bounds__(512, 1) k(const float* A, int lda, int M, const float* B, int ldb, int N, int K, float* C, int ldc, long long* dbg) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ tc::Pipe pipe;
+  tc::PipeState st;
+  tc::pipe_setup(pipe, st, BN < 32 ? 32 : BN);
+  const long long t_begin = clock64();
+  const int tilesM = (M + 127) / 128, tilesN = (N + BN - 1) / BN;
+  long long epi = 0;
+  for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
+    const int i0 = (tile / tilesN) * 128, n0 = (tile % tilesN) * BN;
+    tc::tile_3xtf32<BN>(A, lda, i0, M, B, ldb, n0, N, K, smem_dyn, pipe, st);
+    const long long e0 = clock64();
+    float v[BN / 4]; int row, col0;
+    tc::load_acc<BN>(pipe, v, row, col0);
+    if (i0 + row < M) for (int i = 0; i < BN / 4; ++i) if (n0 + col0 + i < N) C[(size_t)(i0 + row) * ldc + n0 + col0 + i] = v[i];
+    tc::release_acc();
+    epi += clock64() - e0;
+  }
+  const long long total = clock64() - t_begin;
+  if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 480)) {
+    long long* d = dbg + (threadIdx.x == 0 ? 0 : 8);
+    for (int i = 0; i < 6; ++i) d[i] = st.cyc[i];
+    d[6] = epi; d[7] = total;
+  }
+  tc::pipe_teardown(pipe, BN < 32 ? 32 : BN);
+}
+template <int BN> void run(int M, int N, int K) {
+  float *A, *B, *C; long long* dbg;
+  cudaMalloc(&A, (size_t)M * K * 4); cudaMalloc(&B, (size_t)N * K * 4); cudaMalloc(&C, (size_t)M * N * 4); cudaMalloc(&dbg, 128);
+  cudaMemset(A, 0, (size_t)M * K * 4); cudaMemset(B, 0, (size_t)N * K * 4);
+  const int smem = tc::TileSmem<BN>::kBytes;
+  cudaFuncSetAttribute(k<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+  const int grid = tiles < 148 ? tiles : 148;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int rep = 0; rep < 3; ++rep) { cudaEventRecord(e0); k<BN><<<grid, 512, smem>>>(A, K, M, B, K, N, K, C, N, dbg); cudaEventRecord(e1); cudaDeviceSynchronize(); }
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  long long h[16]; cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+  const int nkb = (K + 31) / 32; const int tiles_cta0 = (tiles + grid - 1) / grid;
+  printf("BN=%d M=%d N=%d K=%d: %.1f us (%s), CTA0: %d tiles x %d K-blocks, total %lld cyc\n", BN, M, N, K, ms * 1e3, cudaGetErrorString(cudaGetLastError()), tiles_cta0, nkb, h[7]);
+  printf("   producer(thread 0): cp.async wait %lld, stage_free wait %lld, convert+issue %lld, tile_done wait %lld, epilogue %lld\n", h[0], h[1], h[2], h[5], h[6]);
+  printf("   mma warp (lane 0) : full wait %lld, issue %lld, tile_done wait %lld   => per K-block: full-wait %.0f issue %.0f\n", h[8 + 3], h[8 + 4], h[8 + 5], (double)h[11] / (tiles_cta0 * nkb), (double)h[12] / (tiles_cta0 * nkb));
+}
+int main() { run<32>(512, 1141, 1144); run<64>(4096, 4096, 4096); run<16>(256, 566, 568); return 0; }
