@@ -5,19 +5,47 @@
 
 namespace admmq {
 
+namespace tc {
+int make_operand_tmap(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr)
+      return fail(ADMMQ_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ADMMQ_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ADMMQ_OK;
+}
+}  // namespace tc
+
+struct GemmMaps {
+  CUtensorMap a, b;
+};
+
 template <int BN>
 __global__ void __launch_bounds__(tc::kThreadsTC, 1)
-k_gemm_nt_tc(const float* __restrict__ A, int lda, int M, const float* __restrict__ B, int ldb, int N, int K,
-             float* __restrict__ C, int ldc) {
+k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* __restrict__ C, int ldc) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ tc::Pipe pipe;
   tc::PipeState st;
-  constexpr unsigned int kCols = BN < 32 ? 32 : BN;
-  tc::pipe_setup(pipe, st, kCols);
+  tc::pipe_setup(pipe, st);
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM, tilesN = (N + BN - 1) / BN;
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * BN;
-    tc::tile_3xtf32<BN>(A, lda, i0, M, B, ldb, n0, N, K, smem_dyn, pipe, st);
+    tc::tile_3xtf32<BN>(&maps.a, i0, &maps.b, n0, K, smem_dyn, pipe, st);
     float v[BN / 4];
     int row, col0;
     tc::load_acc<BN>(pipe, v, row, col0);
@@ -28,7 +56,7 @@ k_gemm_nt_tc(const float* __restrict__ A, int lda, int M, const float* __restric
     }
     tc::release_acc();
   }
-  tc::pipe_teardown(pipe, kCols);
+  tc::pipe_teardown(pipe);
 }
 
 }  // namespace admmq
@@ -50,18 +78,21 @@ extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int
   const int bn = ((long long)tilesM * ((N + 63) / 64) >= dp.sm_count) ? 64 : ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count ? 32 : 16);
   const int tiles = tilesM * ((N + bn - 1) / bn);
   const int grid = std::min(tiles, dp.sm_count);
+  GemmMaps maps;
+  if (int e = tc::make_operand_tmap(&maps.a, A, M, K, lda, tc::kTileM)) return e;
+  if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
   if (bn == 64) {
     const int smem = tc::TileSmem<64>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(A, lda, M, B, ldb, N, K, C, ldc);
+    k_gemm_nt_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc);
   } else if (bn == 32) {
     const int smem = tc::TileSmem<32>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<32><<<grid, tc::kThreadsTC, smem, stream>>>(A, lda, M, B, ldb, N, K, C, ldc);
+    k_gemm_nt_tc<32><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc);
   } else {
     const int smem = tc::TileSmem<16>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<16><<<grid, tc::kThreadsTC, smem, stream>>>(A, lda, M, B, ldb, N, K, C, ldc);
+    k_gemm_nt_tc<16><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc);
   }
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);

@@ -7,14 +7,27 @@
 // per 8-deep k-step into one TMEM accumulator, which keeps float32-level accuracy (the dropped lo.lo term
 // and the split residuals are 2^-22 relative) at 1/3 of the TF32 rate.
 //
-// Staging (warp specialised, 512 threads): warps 0-14 are producers, warp 15 issues the MMAs.  Operands are read
-// from global/L2 ONCE as float32 with cp.async (16-byte chunks, 3-4 K-blocks in flight) into a raw ring in
-// shared memory; each producer thread then splits ITS OWN chunks into hi/lo in registers and writes them to the
-// operand stage in the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect (row r of a K-block =
-// 128 bytes = 32 floats; 16-byte chunk c of row r is stored at chunk c ^ (r & 7); 8-row groups are 1024 bytes apart).
-// full[s] (one arrival per producer warp) hands a stage to the MMA warp; tcgen05.commit on free[s] hands it back
-// when the tensor pipe has read it, so the MMAs of K-block k overlap the staging of k+1, k+2.
+// Operand paths.  Measured on B200: with BOTH operands in shared memory one tcgen05.mma of 128 x N x 8 tf32 costs
+// ~90 cycles for every N <= 64 - the tensor core re-reads the 128-row A slab (32 bytes from each of 128 rows) for
+// every instruction - so narrow tiles, which this path needs to keep 148 SMs busy on 512 x 1141 outputs, were
+// MMA-issue bound.  The A operand therefore lives in TENSOR MEMORY (TS form of tcgen05.mma): lane = tile row,
+// column = k, written there by the producers with tcgen05.st, and only the small B slab (N rows x 32 bytes) is read
+// from shared memory per instruction.
+//
+// Staging (512 threads, all 16 warps produce): warp w owns TMEM lanes 32 * (w % 4) .. +31 (the hardware restricts a
+// warp to its lane quarter) and a share of the k-columns of each 32-deep K-block.  Operands are fetched from
+// global/L2 ONCE as float32 by TMA (cp.async.bulk.tensor, 128B swizzle, out-of-range rows/columns zero-filled by the
+// hardware; 4 K-blocks in flight; LDGSTS-based fetching measured ~1000 cycles per 20 KB K-block and was the
+// bottleneck) into a raw ring in shared memory whose swizzle makes the row-per-lane read-back conflict free;
+// raw_full[d] (expect_tx / complete_tx) publishes a K-block to the CTA.  Each producer thread then splits the chunks of
+// ITS row into hi/lo in registers and
+// stores A to TMEM (tcgen05.st) and B to shared memory in the canonical K-major SWIZZLE_128B layout (row r of a
+// K-block = 128 bytes; 16-byte chunk c of row r is stored at chunk c ^ (r & 7); 8-row groups 1024 bytes apart).
+// full[s] (one arrival per producer warp) hands a stage to warp 15, whose elected lane issues the 12 MMAs of the
+// K-block, commits them to free[s] (which hands the stage back once the tensor pipe has consumed it) and then
+// re-arms the raw slot the producers have just finished with by issuing the TMA loads of K-block k + 4.
 #pragma once
+#include <cuda.h>
 #include <cstdint>
 #include "common.cuh"
 
@@ -22,27 +35,30 @@ namespace admmq {
 namespace tc {
 
 constexpr int kThreadsTC = 512;
-constexpr int kProducers = 480;  // warps 0..14; warp 15 issues the MMAs
-constexpr int kMmaWarp = 15;
+constexpr int kMmaWarp = 15;     // its lane 0 also issues the MMAs
 constexpr int kBlockK = 32;      // floats per K-block (one 128-byte swizzle row)
 constexpr int kUmmaK = 8;        // k per tcgen05.mma.kind::tf32
 constexpr int kStages = 3;       // operand stages (hi/lo, swizzled)
 constexpr int kTileM = 128;
 
+constexpr int kRawDepth = 4;     // K-blocks of raw float32 in flight (cp.async)
+constexpr int kAccStride = 64;   // TMEM columns between the three accumulators (BN <= 64)
+constexpr int kAccCols = 192;    // three accumulators: hi.hi at +0, hi.lo at +64, lo.hi at +128
+constexpr int kTmemCols = 512;   // accumulators + kStages x (A_hi 32 + A_lo 32 columns) = 384 -> next power of two
+
 template <int BN>
 struct TileSmem {
-  static constexpr int kABytes = kTileM * 128;
+  static_assert(BN == 16 || BN == 32 || BN == 64, "BN must be 16, 32 or 64");
+  static constexpr int kABytes = kTileM * 128;                   // one K-block of A as raw float32
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // A_hi, A_lo, B_hi, B_lo
+  static constexpr int kStageBytes = 2 * kBBytes;                // B_hi, B_lo (A goes to tensor memory)
   static constexpr int kRawBytes = kABytes + kBBytes;            // one K-block of raw float32
-  static constexpr int kChunks = (kABytes + kBBytes) / 16;       // 16-byte chunks per K-block
-  static constexpr int kPerThread = (kChunks + kProducers - 1) / kProducers;
-  static constexpr int kRawDepth = (BN >= 64) ? 3 : 4;           // K-blocks of raw float32 in flight (cp.async)
   static constexpr int kBytes = kStages * kStageBytes + kRawDepth * kRawBytes + 1024;  // + slack for 1024-byte alignment
   static_assert(kBytes <= 227 * 1024, "tile does not fit in shared memory");
 };
 
 struct Pipe {  // lives in shared memory (static), one per CTA
+  unsigned long long raw_full[kRawDepth];  // cp.async data of a K-block has landed (one arrival per thread)
   unsigned long long stage_full[kStages];
   unsigned long long stage_free[kStages];
   unsigned long long tile_done;
@@ -51,6 +67,7 @@ struct Pipe {  // lives in shared memory (static), one per CTA
 };
 
 struct PipeState {  // per-thread copy, uniform across the CTA
+  unsigned int raw_uses[kRawDepth];  // how often each raw slot has been filled so far
   unsigned int uses[kStages];  // how often each stage has been filled / consumed so far
   unsigned int tiles;          // commits issued so far on tile_done
 #ifdef ADMMQ_TC_PROFILE
@@ -91,6 +108,31 @@ __device__ __forceinline__ void cp_async16(unsigned int dst_smem, const void* sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// arrive on `bar` once every cp.async issued so far by this thread has landed (the barrier's count includes it)
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMA: one arrival + `bytes` expected on `bar`, then a 2-D tile load (coordinates: c0 = innermost = column, c1 = row)
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned int dst_smem, const CUtensorMap* tmap, int c0, int c1,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// true in exactly one (always the same) lane of a fully active warp; the surrounding code stays warp-uniform,
+// which lets ptxas keep MMA descriptors in uniform registers instead of broadcasting them lane by lane
+__device__ __forceinline__ bool elect_one() {
+  unsigned int pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,6 +154,24 @@ __device__ __forceinline__ void umma_tf32(unsigned int d_tmem, unsigned long lon
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// TS form: A from tensor memory (lane = row, column = k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(unsigned int d_tmem, unsigned int a_tmem, unsigned long long b_desc,
+                                             unsigned int idesc, unsigned int accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 8 consecutive columns of the calling thread's TMEM lane
+__device__ __forceinline__ void tmem_store8(unsigned int taddr, const float v[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -128,10 +188,12 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned int smem_addr) 
          (1ull << 46) | (2ull << 61);
 }
 
+// round-to-nearest (ties away from zero) to the 10-bit tf32 mantissa with two integer operations: IEEE floats are
+// sign-magnitude, so adding half a tf32 ulp to the bit pattern and clearing the low 13 bits rounds the magnitude
+// (a carry into the exponent is the correct round-up to the next binade).  cvt.rna.tf32.f32 does the same but runs
+// on the quarter-rate conversion pipe, which made the producers the bottleneck of the tile pipeline.
 __device__ __forceinline__ float tf32_rn(float x) {
-  unsigned int r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   hi.x = tf32_rn(v.x); lo.x = tf32_rn(v.x - hi.x);
@@ -143,10 +205,12 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ unsigned int sw128(int r, int c) { return (unsigned int)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, unsigned int tmem_cols) {
+__device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st) {
+  const unsigned int tmem_cols = kTmemCols;
   if (threadIdx.x == 0) {
+    for (int d = 0; d < kRawDepth; ++d) mbar_init(&pipe.raw_full[d], 1);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&pipe.stage_full[s], kProducers / 32);
+      mbar_init(&pipe.stage_full[s], kThreadsTC / 32 - 1);
       mbar_init(&pipe.stage_free[s], 1);
     }
     mbar_init(&pipe.tile_done, 1);
@@ -157,125 +221,172 @@ __device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, unsigned i
   __syncthreads();
   tc_fence_after();
   for (int s = 0; s < kStages; ++s) st.uses[s] = 0u;
+  for (int d = 0; d < kRawDepth; ++d) st.raw_uses[d] = 0u;
   st.tiles = 0u;
 #ifdef ADMMQ_TC_PROFILE
   for (int i = 0; i < 6; ++i) st.cyc[i] = 0;
 #endif
 }
-__device__ __forceinline__ void pipe_teardown(Pipe& pipe, unsigned int tmem_cols) {
+__device__ __forceinline__ void pipe_teardown(Pipe& pipe) {
+  const unsigned int tmem_cols = kTmemCols;
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tmem_free(pipe.tmem_base, tmem_cols);
 }
 
-// One 128 x BN tile: rows [a_row0, a_row0+128) of A (valid while < a_rows) against rows [b_row0, b_row0+BN) of B
-// (valid while < b_rows); A and B are float32 row-major with leading dimensions lda/ldb (multiples of 4, 16-byte aligned
-// rows).  K valid columns; columns in [K, round_up(K, 4)) must be readable zeros, nothing beyond is touched.
-// On return the accumulator is complete in TMEM (pipe.tmem_base) and visible to every thread.
+// 4 consecutive columns of the calling thread's TMEM lane
+__device__ __forceinline__ void tmem_store4(unsigned int taddr, const float4 v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+               "r"(__float_as_uint(v.w))
+               : "memory");
+}
+
+// One 128 x BN tile: the 128 rows of A starting at a_row0 against the BN rows of B starting at b_row0, over K
+// columns.  tmA / tmB are TMA descriptors of the two row-major float32 matrices with boxes {32, 128} and {32, BN}
+// (make_operand_tmap); rows and columns outside the matrices read as zero.
+// On return the accumulator is complete in TMEM (columns [0, BN) at pipe.tmem_base) and visible to every thread.
+//
+// Roles: warp 15 issues MMAs and TMA loads.  Warps 0..14 convert: warp w writes TMEM lanes 32 * (w % 4) .. +31; the
+// 8 chunks (4 k-columns each) of a K-block row are split 2/2/2/2 over the four warps of quarters 0-2 and 3/3/2 over
+// warps 3, 7, 11 of quarter 3; the B chunks go to the twelve warps of quarters 0-2.
 template <int BN>
-__device__ void tile_3xtf32(const float* __restrict__ A, int lda, int a_row0, int a_rows, const float* __restrict__ B,
-                            int ldb, int b_row0, int b_rows, int K, unsigned char* smem_tiles, Pipe& pipe, PipeState& st) {
+__device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMap* tmB, int b_row0, int K,
+                            unsigned char* smem_tiles, Pipe& pipe, PipeState& st) {
   using TS = TileSmem<BN>;
+  constexpr int kChunksB = BN * 8;  // 16-byte chunks of B per K-block
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const unsigned int tiles_base = (smem_u32(smem_tiles) + 1023u) & ~1023u;
   unsigned char* tiles_ptr = smem_tiles + (tiles_base - smem_u32(smem_tiles));
   const unsigned int raw_base = tiles_base + (unsigned int)(kStages * TS::kStageBytes);
   unsigned char* raw_ptr = tiles_ptr + (size_t)kStages * TS::kStageBytes;
   const int nkb = (K + kBlockK - 1) / kBlockK;
-  if (warp != kMmaWarp) {
-    // ---------------- producers: chunk ids t, t + 480, ...; ids < 1024 belong to A (row = id / 8), the rest to B
-    auto issue = [&](int kb) {
-      if (kb < nkb) {
-        const unsigned int slot = raw_base + (unsigned int)((kb % TS::kRawDepth) * TS::kRawBytes);
-#pragma unroll
-        for (int i = 0; i < TS::kPerThread; ++i) {
-          const int id = t + i * kProducers;
-          if (id < TS::kChunks) {
-            const int k4 = kb * kBlockK + (id & 7) * 4;
-            if (id < kTileM * 8) {
-              const int row = a_row0 + (id >> 3);
-              const bool ok = (k4 < K) && (row < a_rows);
-              cp_async16(slot + (unsigned int)id * 16u, ok ? (const void*)(A + (size_t)row * lda + k4) : (const void*)A, ok);
-            } else {
-              const int row = b_row0 + ((id - kTileM * 8) >> 3);
-              const bool ok = (k4 < K) && (row < b_rows);
-              cp_async16(slot + (unsigned int)id * 16u, ok ? (const void*)(B + (size_t)row * ldb + k4) : (const void*)B, ok);
-            }
-          }
-        }
-      }
-      cp_async_commit();  // always: keeps the group count uniform
-    };
-#pragma unroll
-    for (int d = 0; d < TS::kRawDepth; ++d) issue(d);
-    for (int kb = 0; kb < nkb; ++kb) {
-      { TC_T0(); cp_async_wait<TS::kRawDepth - 1>(); TC_ACC(0); }  // this thread's chunks of K-block kb have landed
-      const int s = kb % kStages;
-      { TC_T0(); if (st.uses[s] > 0u) mbar_wait(&pipe.stage_free[s], (st.uses[s] - 1u) & 1u); TC_ACC(1); }  // tensor pipe is done with stage s
-      TC_T0();
-      unsigned char* stage = tiles_ptr + (size_t)s * TS::kStageBytes;
-      const unsigned char* raw = raw_ptr + (size_t)(kb % TS::kRawDepth) * TS::kRawBytes;
-#pragma unroll
-      for (int i = 0; i < TS::kPerThread; ++i) {
-        const int id = t + i * kProducers;
-        if (id < TS::kChunks) {
-          const float4 v = *reinterpret_cast<const float4*>(raw + (size_t)id * 16);
-          float4 hi, lo;
-          split4(v, hi, lo);
-          if (id < kTileM * 8) {
-            const unsigned int off = sw128(id >> 3, id & 7);
-            *reinterpret_cast<float4*>(stage + off) = hi;
-            *reinterpret_cast<float4*>(stage + TS::kABytes + off) = lo;
-          } else {
-            const int bid = id - kTileM * 8;
-            const unsigned int off = sw128(bid >> 3, bid & 7);
-            *reinterpret_cast<float4*>(stage + 2 * TS::kABytes + off) = hi;
-            *reinterpret_cast<float4*>(stage + 2 * TS::kABytes + TS::kBBytes + off) = lo;
-          }
-        }
-      }
-      issue(kb + TS::kRawDepth);     // refill the raw slot just consumed (only this thread reads these chunks)
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pipe.stage_full[s]);
-      st.uses[s] += 1u;
-      TC_ACC(2);
-    }
-    cp_async_wait<0>();
-  } else {
-    // ---------------- MMA warp: one elected lane issues, the tensor pipe runs asynchronously
+  const unsigned int tmem = pipe.tmem_base;  // keep in a register: the asm memory clobbers would re-read it
+
+  if (warp == kMmaWarp) {
+    // ---------------- MMA + TMA warp: the whole warp runs the loop, one elected lane issues
     const unsigned int idesc = make_idesc<BN>();
+    auto fetch = [&](int kb) {  // elected lane only
+      const int d = kb % kRawDepth;
+      const unsigned int slot = raw_base + (unsigned int)(d * TS::kRawBytes);
+      mbar_expect_tx(&pipe.raw_full[d], (unsigned int)TS::kRawBytes);
+      tma_load_2d(slot, tmA, kb * kBlockK, a_row0, &pipe.raw_full[d]);
+      tma_load_2d(slot + (unsigned int)TS::kABytes, tmB, kb * kBlockK, b_row0, &pipe.raw_full[d]);
+    };
+    if (elect_one()) {
+      for (int d = 0; d < kRawDepth; ++d)
+        if (d < nkb) fetch(d);
+    }
+    __syncwarp();
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       { TC_T0(); mbar_wait(&pipe.stage_full[s], st.uses[s] & 1u); TC_ACC(3); }
+      st.uses[s] += 1u;
       tc_fence_after();
       TC_T0();
-      if (lane == 0) {
-        const unsigned int sa = tiles_base + (unsigned int)(s * TS::kStageBytes);
-        const unsigned long long a_hi = make_desc(sa), a_lo = make_desc(sa + TS::kABytes);
-        const unsigned long long b_hi = make_desc(sa + 2 * TS::kABytes), b_lo = make_desc(sa + 2 * TS::kABytes + TS::kBBytes);
+      const unsigned int a_col = tmem + (unsigned int)(kAccCols + s * 64);
+      const unsigned int sb = tiles_base + (unsigned int)(s * TS::kStageBytes);
+      const unsigned long long b_hi = make_desc(sb), b_lo = make_desc(sb + TS::kBBytes);
+      const unsigned int first = kb != 0 ? 1u : 0u;
+      unsigned long long* free_bar = &pipe.stage_free[s];
+      unsigned long long* done_bar = &pipe.tile_done;
+      const bool last = kb + 1 == nkb;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
           const unsigned long long adv = (unsigned long long)((ks * kUmmaK * 4) >> 4);  // +32 bytes per k-step
-          umma_tf32(pipe.tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-          umma_tf32(pipe.tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(pipe.tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+          const unsigned int a_hi = a_col + (unsigned int)(ks * kUmmaK), a_lo = a_hi + 32u;
+          // three independent accumulation chains (dependent MMAs on one accumulator serialise on the tensor
+          // pipe's latency when the tile is this narrow); the epilogue adds them, small terms first
+          const unsigned int acc = ks != 0 ? 1u : first;
+          umma_tf32_ts(tmem + 2u * kAccStride, a_lo, b_hi + adv, idesc, acc);
+          umma_tf32_ts(tmem + 1u * kAccStride, a_hi, b_lo + adv, idesc, acc);
+          umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
         }
-        umma_commit(&pipe.stage_free[s]);
-        if (kb + 1 == nkb) umma_commit(&pipe.tile_done);
+        umma_commit(free_bar);
+        if (last) umma_commit(done_bar);
+        // every producer has finished reading raw slot kb % kRawDepth (stage_full completed): refill it
+        if (kb + kRawDepth < nkb) fetch(kb + kRawDepth);
       }
       __syncwarp();
-      st.uses[s] += 1u;
       TC_ACC(4);
     }
+  } else {
+    // ---------------- producers
+    const int q = warp & 3, kgi = warp >> 2;
+    const int ar = q * 32 + lane;                       // tile row = TMEM lane of this thread
+    const int c_begin = (q == 3) ? kgi * 3 : kgi * 2;   // first chunk of the row this thread converts
+    const int c_count = (q == 3) ? (kgi == 2 ? 2 : 3) : 2;
+    const unsigned int lane_addr = tmem + ((unsigned int)(q * 32) << 16);
+    // B chunk ids handled by this thread: bi0, bi0 + 384, ... (warps of quarters 0-2)
+    const int bi0 = (q == 3) ? kChunksB : (kgi * 3 + q) * 32 + lane;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int d = kb % kRawDepth;
+      { TC_T0(); mbar_wait(&pipe.raw_full[d], (st.raw_uses[d] + (unsigned int)(kb / kRawDepth)) & 1u); TC_ACC(0); }  // K-block kb has landed
+      const int s = kb % kStages;
+      { TC_T0(); if (st.uses[s] > 0u) { mbar_wait(&pipe.stage_free[s], (st.uses[s] - 1u) & 1u); tc_fence_after(); } TC_ACC(1); }
+      TC_T0();
+      const unsigned char* raw = raw_ptr + (size_t)d * TS::kRawBytes;
+      const unsigned int col0 = lane_addr + (unsigned int)(kAccCols + s * 64);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < c_count) {
+          const int c = c_begin + i;
+          const float4 v = *reinterpret_cast<const float4*>(raw + sw128(ar, c));
+          float4 hi, lo;
+          split4(v, hi, lo);
+          tmem_store4(col0 + (unsigned int)(c * 4), hi);
+          tmem_store4(col0 + 32u + (unsigned int)(c * 4), lo);
+        }
+      }
+      unsigned char* stage = tiles_ptr + (size_t)s * TS::kStageBytes;
+      for (int bi = bi0; bi < kChunksB; bi += 384) {
+        const unsigned int off = sw128(bi >> 3, bi & 7);
+        const float4 v = *reinterpret_cast<const float4*>(raw + TS::kABytes + off);
+        float4 hi, lo;
+        split4(v, hi, lo);
+        *reinterpret_cast<float4*>(stage + off) = hi;
+        *reinterpret_cast<float4*>(stage + TS::kBBytes + off) = lo;
+      }
+      tmem_store_wait();
+      tc_fence_before();
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pipe.stage_full[s]);
+      TC_ACC(2);
+      st.uses[s] += 1u;
+    }
   }
+  // raw slot use counts advance identically in both roles (fills == consumptions)
+  for (int kb = 0; kb < nkb; ++kb) st.raw_uses[kb % kRawDepth] += 1u;
   { TC_T0(); mbar_wait(&pipe.tile_done, st.tiles & 1u); TC_ACC(5); }
   st.tiles += 1u;
   tc_fence_after();
 }
 
 // Accumulator read-back for the calling warp: TMEM lanes 32 * (warp % 4) .. +31 (= tile rows), BN / 4 columns
-// starting at (warp / 4) * BN / 4.  v[i] = D[row = 32 * (warp % 4) + lane][col0 + i].
+// starting at (warp / 4) * BN / 4.  v[i] = D[row = 32 * (warp % 4) + lane][col0 + i] = (lo.hi + hi.lo) + hi.hi.
+template <int N>
+__device__ __forceinline__ void tmem_load(unsigned int taddr, unsigned int r[N]) {
+  if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+  } else {
+    static_assert(N == 16, "unsupported width");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+  }
+}
 template <int BN>
 __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int& row, int& col0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,27 +394,12 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
   row = q * 32 + lane;
   col0 = cgp * (BN / 4);
   const unsigned int taddr = pipe.tmem_base + ((unsigned int)(q * 32) << 16) + (unsigned int)col0;
-  unsigned int r[BN / 4];
-  if constexpr (BN == 32) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-  } else if constexpr (BN == 16) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr)
-                 : "memory");
-  } else {
-    static_assert(BN == 64, "unsupported BN");
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr)
-                 : "memory");
-  }
+  unsigned int hh[BN / 4], hl[BN / 4], lh[BN / 4];
+  tmem_load<BN / 4>(taddr, hh);
+  tmem_load<BN / 4>(taddr + 1u * kAccStride, hl);
+  tmem_load<BN / 4>(taddr + 2u * kAccStride, lh);
 #pragma unroll
-  for (int i = 0; i < BN / 4; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < BN / 4; ++i) v[i] = (__uint_as_float(lh[i]) + __uint_as_float(hl[i])) + __uint_as_float(hh[i]);
 }
 
 // all accumulator reads of this tile are done: the next tile may overwrite TMEM
@@ -311,6 +407,10 @@ __device__ __forceinline__ void release_acc() {
   tc_fence_before();
   __syncthreads();
 }
+
+// Host: TMA descriptor of a row-major float32 matrix (rows x cols, leading dimension ld floats, ld % 4 == 0, base
+// 16-byte aligned) with box {32 columns, box_rows rows} and 128-byte swizzle.  Returns 0 or ADMMQ_E_CUDA.
+int make_operand_tmap(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_rows);
 
 }  // namespace tc
 }  // namespace admmq

@@ -2,21 +2,20 @@
 #include <cstdio>
 #include <vector>
 #define ADMMQ_TC_PROFILE 1
-#include "../../admm-quantization_b200/csrc/tc_gemm.cuh"
+#include "../../admm-quantization_b200/csrc/tc_gemm.cu"
 namespace admmq { char* error_buffer() { static char b[8]; return b; } int fail(int c, const char*, ...) { return c; } void count_launches(int) {} int device_props(DeviceProps*) { return 0; } }
-using namespace admmq;
 template <int BN>
-__global__ void __launch_bounds__(512, 1) k(const float* A, int lda, int M, const float* B, int ldb, int N, int K, float* C, int ldc, long long* dbg) {
+__global__ void __launch_bounds__(512, 1) k(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* C, int ldc, long long* dbg) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ tc::Pipe pipe;
   tc::PipeState st;
-  tc::pipe_setup(pipe, st, BN < 32 ? 32 : BN);
+  tc::pipe_setup(pipe, st);
   const long long t_begin = clock64();
   const int tilesM = (M + 127) / 128, tilesN = (N + BN - 1) / BN;
   long long epi = 0;
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
     const int i0 = (tile / tilesN) * 128, n0 = (tile % tilesN) * BN;
-    tc::tile_3xtf32<BN>(A, lda, i0, M, B, ldb, n0, N, K, smem_dyn, pipe, st);
+    tc::tile_3xtf32<BN>(&maps.a, i0, &maps.b, n0, K, smem_dyn, pipe, st);
     const long long e0 = clock64();
     float v[BN / 4]; int row, col0;
     tc::load_acc<BN>(pipe, v, row, col0);
@@ -30,7 +29,7 @@ __global__ void __launch_bounds__(512, 1) k(const float* A, int lda, int M, cons
     for (int i = 0; i < 6; ++i) d[i] = st.cyc[i];
     d[6] = epi; d[7] = total;
   }
-  tc::pipe_teardown(pipe, BN < 32 ? 32 : BN);
+  tc::pipe_teardown(pipe);
 }
 template <int BN> void run(int M, int N, int K) {
   float *A, *B, *C; long long* dbg;
@@ -41,7 +40,8 @@ template <int BN> void run(int M, int N, int K) {
   const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
   const int grid = tiles < 148 ? tiles : 148;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int rep = 0; rep < 3; ++rep) { cudaEventRecord(e0); k<BN><<<grid, 512, smem>>>(A, K, M, B, K, N, K, C, N, dbg); cudaEventRecord(e1); cudaDeviceSynchronize(); }
+  GemmMaps maps; tc::make_operand_tmap(&maps.a, A, M, K, K, 128); tc::make_operand_tmap(&maps.b, B, N, K, K, BN);
+  for (int rep = 0; rep < 3; ++rep) { cudaEventRecord(e0); k<BN><<<grid, 512, smem>>>(maps, M, N, K, C, N, dbg); cudaEventRecord(e1); cudaDeviceSynchronize(); }
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   long long h[16]; cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
   const int nkb = (K + 31) / 32; const int tiles_cta0 = (tiles + grid - 1) / grid;
