@@ -2,7 +2,9 @@
 // inverse (admmq_spd_inverse).  Replaces admm_iteration() of source/admm.py:51-67.
 //
 // One cooperative launch (one CTA per SM) runs ALL max_iter-1 inner iterations; per iteration
-//   P1  H_ls = RHS . Minv            float32 FFMA tile product, RHS = F + rho (H + U)   (:56-57)
+//   P1  H_ls = RHS . Minv            RHS = F + rho (H + U)                                (:56-57)
+//       precision 0: float32 FFMA tile product (parity mode); precision 1: 3xTF32 on tcgen05/TMEM, operands
+//       fetched by TMA (tc_gemm.cuh; throughput mode)
 //       epilogue: abs-max key of V = H_ls - U                                          (:59, q.py:129)
 //   --- device-wide barrier
 //   P2  per-candidate squared-error sums of the clip search over V (search.cuh)         (q.py:136-139)
@@ -12,8 +14,10 @@
 // State (H, U, F, H_ls, RHS, Minv) stays L2 resident for the whole call: per iteration the
 // algorithmic traffic is 16 B per element of H plus one pass over Minv, all served from L2.
 #include <algorithm>
+#include <cstring>
 #include "search.cuh"
 #include "spd_inverse.cuh"
+#include "tc_gemm.cuh"
 
 namespace admmq {
 
@@ -33,6 +37,8 @@ struct IterationHeader {  // admmq_admm_iteration only: scalars handed from the 
 };
 
 struct LoopParams {
+  CUtensorMap tm_rhs;   // TMA descriptors of RHS (I x R, ld Rp) and Minv (R x R, ld Rp); only used by the
+  CUtensorMap tm_minv;  // tensor-core variant of P1
   float* H;
   float* U;
   const float* F;
@@ -154,6 +160,46 @@ __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned i
   }
 }
 
+// P1 on the tensor cores: 128 x TCBN tiles of H_ls = RHS . Minv^T (Minv is symmetric) in 3xTF32.
+template <int TCBN>
+__device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc::Pipe& pipe, tc::PipeState& st,
+                              unsigned int* keys) {
+  const int I = p.I, R = p.R, Rp = p.Rp;
+  const int tilesN = (R + TCBN - 1) / TCBN, tilesM = (I + tc::kTileM - 1) / tc::kTileM;
+  unsigned int kmax = 0u, kinv = 0u;
+  // RHS was written with ordinary stores by other CTAs before the grid barrier; the TMA engine reads through the
+  // async proxy
+  asm volatile("fence.proxy.async;" ::: "memory");
+  for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
+    const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * TCBN;
+    tc::tile_3xtf32<TCBN>(&p.tm_rhs, i0, &p.tm_minv, n0, R, smem_tiles, pipe, st);
+    float v[TCBN / 4];
+    int row, col0;
+    tc::load_acc<TCBN>(pipe, v, row, col0);
+    const int i = i0 + row;
+    if (i < I) {
+#pragma unroll
+      for (int c = 0; c < TCBN / 4; ++c) {
+        const int n = n0 + col0 + c;
+        if (n < R) {
+          p.Hls[(size_t)i * Rp + n] = v[c];
+          const float d = sub_rn(v[c], __ldcg(p.U + (size_t)i * R + n));  // V = H_ls - U (:59)
+          const unsigned int k = float_key(d);
+          kmax = max(kmax, k);
+          kinv = max(kinv, ~k);
+        }
+      }
+    }
+    tc::release_acc();
+  }
+  kmax = warp_max_u32(kmax);
+  kinv = warp_max_u32(kinv);
+  if ((threadIdx.x & 31) == 0 && (kmax | kinv) != 0u) {
+    atomicMax(&keys[0], kmax);
+    atomicMax(&keys[1], kinv);
+  }
+}
+
 __global__ void __launch_bounds__(kInvThreads, 1) k_spd_inverse(InvParams p) {
   __shared__ InvSmem sm;
   GridBarrier bar;
@@ -161,11 +207,12 @@ __global__ void __launch_bounds__(kInvThreads, 1) k_spd_inverse(InvParams p) {
   spd_inverse_body(p, sm, bar);
 }
 
-template <int BM, int BN>
+template <int BM, int BN, int TCBN>
 union LoopSmem {
   SearchSmem search;
   GemmSmem<BM, BN> gemm;
   ResidualSmem res;
+  unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16)>::kBytes : 16];
 };
 
 // sum over the CTA of four per-thread doubles, result valid in every thread
@@ -188,10 +235,13 @@ __device__ __forceinline__ void cta_sum4(double v[4], ResidualSmem& rs) {
   }
 }
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
+// TCBN = 0: P1 as float32 FFMA tiles (BM x BN, TM x TN per thread); TCBN = 16 / 32: P1 on the tensor cores.
+template <int BM, int BN, int TM, int TN, int TCBN>
+__global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant__ LoopParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  LoopSmem<BM, BN>& sm = *reinterpret_cast<LoopSmem<BM, BN>*>(smem_raw);
+  LoopSmem<BM, BN, TCBN>& sm = *reinterpret_cast<LoopSmem<BM, BN, TCBN>*>(smem_raw);
+  __shared__ tc::Pipe pipe;
+  tc::PipeState pst;
   const int t = threadIdx.x;
   LoopHeader* hdr = p.hdr;
   admmq_loop_report rep;
@@ -209,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
     if (blockIdx.x == 0 && t == 0) *p.report = rep;
     return;
   }
+  if constexpr (TCBN > 0) tc::pipe_setup(pipe, pst, p.neg_zero);
   const unsigned long long t_begin = global_ns();
   unsigned long long t_mark = t_begin;
   auto lap = [&](int phase) {
@@ -247,7 +298,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
   for (int j = 1; j < p.max_iter; ++j) {  // range(1, max_iter), :55
     const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
     // ---------------- P1
-    gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
+    if constexpr (TCBN > 0) gemm_phase_tc<TCBN>(p, sm.tc_tiles, pipe, pst, hdr->keys[slot]);
+    else gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
     if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
       if (t < 4) hdr->keys[next_slot][t] = 0u;
       for (int c = t; c < p.Nc; c += kThreads) p.cand[(size_t)next_slot * kMaxCandidates + c] = 0ull;
@@ -358,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(LoopParams p) {
   }
   rep.phase_ns[3] = global_ns() - t_begin;
   if (blockIdx.x == 0 && t == 0) *p.report = rep;
+  if constexpr (TCBN > 0) tc::pipe_teardown(pipe);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -465,8 +518,8 @@ static int check_loop_args(const char* who, const void* H, const void* U, const 
 }
 
 static int launch_loop(float* H, float* U, const float* F, const float* Minv, const float* rho, const int* inv_status,
-                       int I, int R, int max_iter, float eps, int bits, int qscheme, int num_attempts, int8_t* codes,
-                       admmq_loop_report* report, char* ws, int grid, cudaStream_t stream) {
+                       int I, int R, int max_iter, float eps, int bits, int qscheme, int num_attempts, int precision,
+                       int8_t* codes, admmq_loop_report* report, char* ws, int grid, cudaStream_t stream) {
   const LoopLayout l = loop_layout(I, R, grid);
   // header + candidate accumulators + RHS (its pad columns must be zero)
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, l.slots, stream));
@@ -497,10 +550,28 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   void* args[] = {&p};
   const void* fn = nullptr;
   size_t smem = 0;
-  switch (pick_tile(I, R, grid)) {
-    case 0: fn = (const void*)k_admm_loop<64, 64, 4, 4>; smem = sizeof(LoopSmem<64, 64>); break;
-    case 1: fn = (const void*)k_admm_loop<32, 32, 2, 2>; smem = sizeof(LoopSmem<32, 32>); break;
-    default: fn = (const void*)k_admm_loop<16, 32, 1, 2>; smem = sizeof(LoopSmem<16, 32>); break;
+  // tensor-core P1 only pays off when the factor has enough rows to fill a good part of a 128-row tile
+  const bool use_tc = precision == 1 && I >= 64 && R >= 32;
+  if (use_tc) {
+    const int tilesM = (I + tc::kTileM - 1) / tc::kTileM;
+    const int tcbn = ((long long)tilesM * ((R + 31) / 32) >= grid) ? 32 : 16;
+    if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
+    if (int e = tc::make_operand_tmap(&p.tm_minv, Minv, R, R, l.Rp, tcbn)) return e;
+    if (tcbn == 32) {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, 32>;
+      smem = sizeof(LoopSmem<16, 32, 32>);
+    } else {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, 16>;
+      smem = sizeof(LoopSmem<16, 32, 16>);
+    }
+  } else {
+    memset(&p.tm_rhs, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv, 0, sizeof(CUtensorMap));
+    switch (pick_tile(I, R, grid)) {
+      case 0: fn = (const void*)k_admm_loop<64, 64, 4, 4, 0>; smem = sizeof(LoopSmem<64, 64, 0>); break;
+      case 1: fn = (const void*)k_admm_loop<32, 32, 2, 2, 0>; smem = sizeof(LoopSmem<32, 32, 0>); break;
+      default: fn = (const void*)k_admm_loop<16, 32, 1, 2, 0>; smem = sizeof(LoopSmem<16, 32, 0>); break;
+    }
   }
   ADMMQ_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
@@ -545,10 +616,12 @@ extern "C" size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts
 
 extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
                                const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
-                               int num_attempts, int8_t* codes, admmq_loop_report* report, void* workspace,
-                               size_t workspace_bytes, void* stream_) {
+                               int num_attempts, int precision, int8_t* codes, admmq_loop_report* report,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
   if (int e = check_loop_args("admmq_admm_loop", H, U, F, Minv, report, I, R, bits, qscheme, num_attempts)) return e;
   if (rho == nullptr) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: rho is null");
+  if (precision != 0 && precision != 1) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: precision must be 0 or 1");
+  if (((uintptr_t)Minv & 15) != 0) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: Minv must be 16-byte aligned");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;
   if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
@@ -556,8 +629,8 @@ extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* 
       ((uintptr_t)workspace & 255) != 0)
     return fail(ADMMQ_E_WORKSPACE, "admmq_admm_loop: workspace needs %zu bytes, 256-byte aligned",
                 admmq_admm_loop_workspace_bytes(I, R, num_attempts));
-  return launch_loop(H, U, F, Minv, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, codes, report,
-                     (char*)workspace, coop_grid(dp), (cudaStream_t)stream_);
+  return launch_loop(H, U, F, Minv, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision, codes,
+                     report, (char*)workspace, coop_grid(dp), (cudaStream_t)stream_);
 }
 
 extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts) {
@@ -567,10 +640,11 @@ extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_att
 }
 
 extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R, int max_iter,
-                                    float eps, int bits, int qscheme, int num_attempts, int8_t* codes,
+                                    float eps, int bits, int qscheme, int num_attempts, int precision, int8_t* codes,
                                     admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_loop_args("admmq_admm_iteration", H, U, F, G, report, I, R, bits, qscheme, num_attempts)) return e;
+  if (precision != 0 && precision != 1) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: precision must be 0 or 1");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;
   if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
@@ -585,6 +659,6 @@ extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const fl
   if (int e = launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), &ih->rho, &ih->status, &ih->barrier_inv,
                                  (double*)(ws + l.inv_ws), (double*)(ws + l.inv_ws + spd_scratch_bytes(R) / 2), grid, stream))
     return e;
-  return launch_loop(H, U, F, Minv, &ih->rho, &ih->status, I, R, max_iter, eps, bits, qscheme, num_attempts, codes, report,
-                     ws + l.loop_ws, grid, stream);
+  return launch_loop(H, U, F, Minv, &ih->rho, &ih->status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision,
+                     codes, report, ws + l.loop_ws, grid, stream);
 }

@@ -21,7 +21,7 @@ int make_operand_tmap(CUtensorMap* out, const float* base, int rows, int cols, i
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)kAtomK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -37,11 +37,11 @@ struct GemmMaps {
 
 template <int BN>
 __global__ void __launch_bounds__(tc::kThreadsTC, 1)
-k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* __restrict__ C, int ldc) {
+k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* __restrict__ C, int ldc, float neg_zero) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ tc::Pipe pipe;
   tc::PipeState st;
-  tc::pipe_setup(pipe, st);
+  tc::pipe_setup(pipe, st, neg_zero);
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM, tilesN = (N + BN - 1) / BN;
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * BN;
@@ -74,25 +74,22 @@ extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int
   if (int e = device_props(&dp)) return e;
   if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "admmq_gemm_nt needs an sm_100 device (tcgen05)");
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM;
-  // widest tile that still gives every SM work
-  const int bn = ((long long)tilesM * ((N + 63) / 64) >= dp.sm_count) ? 64 : ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count ? 32 : 16);
+  // tile width: 32 unless 16 is needed to give every SM a tile
+  const int bn = ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count) ? 32 : 16;
   const int tiles = tilesM * ((N + bn - 1) / bn);
   const int grid = std::min(tiles, dp.sm_count);
   GemmMaps maps;
   if (int e = tc::make_operand_tmap(&maps.a, A, M, K, lda, tc::kTileM)) return e;
   if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
-  if (bn == 64) {
-    const int smem = tc::TileSmem<64>::kBytes;
-    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc);
+  if (false) {
   } else if (bn == 32) {
     const int smem = tc::TileSmem<32>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<32><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc);
+    k_gemm_nt_tc<32><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
   } else {
     const int smem = tc::TileSmem<16>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<16><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc);
+    k_gemm_nt_tc<16><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
   }
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);

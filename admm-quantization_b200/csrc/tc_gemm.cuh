@@ -36,21 +36,26 @@ namespace tc {
 
 constexpr int kThreadsTC = 512;
 constexpr int kMmaWarp = 15;     // its lane 0 also issues the MMAs
-constexpr int kBlockK = 32;      // floats per K-block (one 128-byte swizzle row)
+constexpr int kAtomK = 32;       // floats per 128-byte swizzle row
+constexpr int kAtoms = 2;        // swizzle atoms along K per K-block
+constexpr int kBlockK = kAtomK * kAtoms;  // 64: halves the per-block synchronisation cost of a 32-deep block
 constexpr int kUmmaK = 8;        // k per tcgen05.mma.kind::tf32
 constexpr int kStages = 3;       // operand stages (hi/lo, swizzled)
 constexpr int kTileM = 128;
 
-constexpr int kRawDepth = 4;     // K-blocks of raw float32 in flight (cp.async)
-constexpr int kAccStride = 64;   // TMEM columns between the three accumulators (BN <= 64)
-constexpr int kAccCols = 192;    // three accumulators: hi.hi at +0, hi.lo at +64, lo.hi at +128
-constexpr int kTmemCols = 512;   // accumulators + kStages x (A_hi 32 + A_lo 32 columns) = 384 -> next power of two
+constexpr int kRawDepth = 3;     // K-blocks of raw float32 in flight (TMA)
+constexpr int kAccStride = 32;   // TMEM columns between the three accumulators (BN <= 32)
+constexpr int kAccCols = 96;     // three accumulators: hi.hi at +0, hi.lo at +32, lo.hi at +64
+constexpr int kStageCols = 2 * kBlockK;  // TMEM columns of one A stage: hi [0, 64), lo [64, 128)
+constexpr int kTmemCols = 512;   // 96 + kStages x 128 = 480 -> next power of two
 
 template <int BN>
 struct TileSmem {
-  static_assert(BN == 16 || BN == 32 || BN == 64, "BN must be 16, 32 or 64");
-  static constexpr int kABytes = kTileM * 128;                   // one K-block of A as raw float32
-  static constexpr int kBBytes = BN * 128;
+  static_assert(BN == 16 || BN == 32, "BN must be 16 or 32");
+  static constexpr int kAAtomBytes = kTileM * 128;               // one 32-deep atom of A as raw float32
+  static constexpr int kBAtomBytes = BN * 128;
+  static constexpr int kABytes = kAtoms * kAAtomBytes;           // one K-block of A
+  static constexpr int kBBytes = kAtoms * kBAtomBytes;
   static constexpr int kStageBytes = 2 * kBBytes;                // B_hi, B_lo (A goes to tensor memory)
   static constexpr int kRawBytes = kABytes + kBBytes;            // one K-block of raw float32
   static constexpr int kBytes = kStages * kStageBytes + kRawDepth * kRawBytes + 1024;  // + slack for 1024-byte alignment
@@ -70,6 +75,7 @@ struct PipeState {  // per-thread copy, uniform across the CTA
   unsigned int raw_uses[kRawDepth];  // how often each raw slot has been filled so far
   unsigned int uses[kStages];  // how often each stage has been filled / consumed so far
   unsigned int tiles;          // commits issued so far on tile_done
+  unsigned long long nz2;      // (-0.0f, -0.0f) as a run-time value (see split2)
 #ifdef ADMMQ_TC_PROFILE
   long long cyc[6];            // producer: cp.async wait, stage_free wait, convert; mma: full wait, issue; all: tile_done wait
 #endif
@@ -188,25 +194,39 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned int smem_addr) 
          (1ull << 46) | (2ull << 61);
 }
 
-// round-to-nearest (ties away from zero) to the 10-bit tf32 mantissa with two integer operations: IEEE floats are
-// sign-magnitude, so adding half a tf32 ulp to the bit pattern and clearing the low 13 bits rounds the magnitude
-// (a carry into the exponent is the correct round-up to the next binade).  cvt.rna.tf32.f32 does the same but runs
-// on the quarter-rate conversion pipe, which made the producers the bottleneck of the tile pipeline.
-__device__ __forceinline__ float tf32_rn(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+// hi/lo split of two packed float32 values in four FMA-pipe instructions (the conversion is issue bound: the integer
+// form costs five half-rate ALU operations per element, cvt.rna.tf32 runs on the quarter-rate conversion pipe):
+//   Veltkamp/Dekker: t = x * (2^13 + 1); hi = t - (t - x) is x rounded to nearest to 11 significant bits, i.e.
+//   exactly a tf32 number; lo = x - hi is exact in float32 and |lo| <= 2^-11 |x|.
+// lo keeps up to 13 significant bits; the tensor core reads the upper 19 bits of each 32-bit operand, so lo enters the
+// product truncated to tf32 (error <= 2^-21 |x|, same order as the dropped lo.lo term).
+// ptxas contracts a packed multiply into each packed add/sub that consumes it (it even duplicates the multiply), which
+// turns hi = t - (t - x) into fma(x, c, -(fma(x, c, -x))) = x.  The product is therefore formed as fma(x, c, nz) with
+// nz = (-0.0f, -0.0f) taken from a kernel parameter, which cannot be folded away.
+__device__ __forceinline__ void split2(unsigned long long x, unsigned long long nz, unsigned long long& hi,
+                                       unsigned long long& lo) {
+  unsigned long long t, u;
+  const unsigned long long c = 0x4600040046000400ull;  // (8193.0f, 8193.0f)
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(x), "l"(c), "l"(nz));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(t), "l"(x));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(hi) : "l"(t), "l"(u));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(lo) : "l"(x), "l"(hi));
 }
-__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = tf32_rn(v.x); lo.x = tf32_rn(v.x - hi.x);
-  hi.y = tf32_rn(v.y); lo.y = tf32_rn(v.y - hi.y);
-  hi.z = tf32_rn(v.z); lo.z = tf32_rn(v.z - hi.z);
-  hi.w = tf32_rn(v.w); lo.w = tf32_rn(v.w - hi.w);
+__device__ __forceinline__ void split4(const float4 v, unsigned long long nz, float4& hi, float4& lo) {
+  const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(&v);
+  ulonglong2 h, l;
+  split2(x.x, nz, h.x, l.x);
+  split2(x.y, nz, h.y, l.y);
+  hi = *reinterpret_cast<const float4*>(&h);
+  lo = *reinterpret_cast<const float4*>(&l);
 }
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ unsigned int sw128(int r, int c) { return (unsigned int)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st) {
+__device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, float neg_zero) {
   const unsigned int tmem_cols = kTmemCols;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(st.nz2) : "f"(neg_zero));
   if (threadIdx.x == 0) {
     for (int d = 0; d < kRawDepth; ++d) mbar_init(&pipe.raw_full[d], 1);
     for (int s = 0; s < kStages; ++s) {
@@ -254,7 +274,8 @@ template <int BN>
 __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMap* tmB, int b_row0, int K,
                             unsigned char* smem_tiles, Pipe& pipe, PipeState& st) {
   using TS = TileSmem<BN>;
-  constexpr int kChunksB = BN * 8;  // 16-byte chunks of B per K-block
+  constexpr int kChunksB = BN * 8 * kAtoms;  // 16-byte chunks of B per K-block
+  constexpr int kRowChunks = 8 * kAtoms;     // 16-byte chunks per row per K-block
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const unsigned int tiles_base = (smem_u32(smem_tiles) + 1023u) & ~1023u;
   unsigned char* tiles_ptr = smem_tiles + (tiles_base - smem_u32(smem_tiles));
@@ -270,8 +291,12 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
       const int d = kb % kRawDepth;
       const unsigned int slot = raw_base + (unsigned int)(d * TS::kRawBytes);
       mbar_expect_tx(&pipe.raw_full[d], (unsigned int)TS::kRawBytes);
-      tma_load_2d(slot, tmA, kb * kBlockK, a_row0, &pipe.raw_full[d]);
-      tma_load_2d(slot + (unsigned int)TS::kABytes, tmB, kb * kBlockK, b_row0, &pipe.raw_full[d]);
+#pragma unroll
+      for (int a = 0; a < kAtoms; ++a) {
+        tma_load_2d(slot + (unsigned int)(a * TS::kAAtomBytes), tmA, kb * kBlockK + a * kAtomK, a_row0, &pipe.raw_full[d]);
+        tma_load_2d(slot + (unsigned int)(TS::kABytes + a * TS::kBAtomBytes), tmB, kb * kBlockK + a * kAtomK, b_row0,
+                    &pipe.raw_full[d]);
+      }
     };
     if (elect_one()) {
       for (int d = 0; d < kRawDepth; ++d)
@@ -284,24 +309,28 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
       st.uses[s] += 1u;
       tc_fence_after();
       TC_T0();
-      const unsigned int a_col = tmem + (unsigned int)(kAccCols + s * 64);
+      const unsigned int a_col = tmem + (unsigned int)(kAccCols + s * kStageCols);
       const unsigned int sb = tiles_base + (unsigned int)(s * TS::kStageBytes);
-      const unsigned long long b_hi = make_desc(sb), b_lo = make_desc(sb + TS::kBBytes);
       const unsigned int first = kb != 0 ? 1u : 0u;
       unsigned long long* free_bar = &pipe.stage_free[s];
       unsigned long long* done_bar = &pipe.tile_done;
       const bool last = kb + 1 == nkb;
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
-          const unsigned long long adv = (unsigned long long)((ks * kUmmaK * 4) >> 4);  // +32 bytes per k-step
-          const unsigned int a_hi = a_col + (unsigned int)(ks * kUmmaK), a_lo = a_hi + 32u;
-          // three independent accumulation chains (dependent MMAs on one accumulator serialise on the tensor
-          // pipe's latency when the tile is this narrow); the epilogue adds them, small terms first
-          const unsigned int acc = ks != 0 ? 1u : first;
-          umma_tf32_ts(tmem + 2u * kAccStride, a_lo, b_hi + adv, idesc, acc);
-          umma_tf32_ts(tmem + 1u * kAccStride, a_hi, b_lo + adv, idesc, acc);
-          umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
+        for (int a = 0; a < kAtoms; ++a) {
+          const unsigned long long b_hi = make_desc(sb + (unsigned int)(a * TS::kBAtomBytes));
+          const unsigned long long b_lo = make_desc(sb + (unsigned int)(TS::kBBytes + a * TS::kBAtomBytes));
+#pragma unroll
+          for (int ks = 0; ks < kAtomK / kUmmaK; ++ks) {
+            const unsigned long long adv = (unsigned long long)((ks * kUmmaK * 4) >> 4);  // +32 bytes per k-step
+            const unsigned int a_hi = a_col + (unsigned int)(a * kAtomK + ks * kUmmaK), a_lo = a_hi + (unsigned int)kBlockK;
+            // three independent accumulators, added small terms first by the epilogue: besides shortening the
+            // dependent chain this keeps the lo terms from being absorbed into the large hi.hi sums
+            const unsigned int acc = (a | ks) != 0 ? 1u : first;
+            umma_tf32_ts(tmem + 2u * kAccStride, a_lo, b_hi + adv, idesc, acc);
+            umma_tf32_ts(tmem + 1u * kAccStride, a_hi, b_lo + adv, idesc, acc);
+            umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
+          }
         }
         umma_commit(free_bar);
         if (last) umma_commit(done_bar);
@@ -314,9 +343,10 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
   } else {
     // ---------------- producers
     const int q = warp & 3, kgi = warp >> 2;
-    const int ar = q * 32 + lane;                       // tile row = TMEM lane of this thread
-    const int c_begin = (q == 3) ? kgi * 3 : kgi * 2;   // first chunk of the row this thread converts
-    const int c_count = (q == 3) ? (kgi == 2 ? 2 : 3) : 2;
+    const int ar = q * 32 + lane;  // tile row = TMEM lane of this thread
+    // chunks (4 k-columns each) of the row this thread converts: 4/4/4/4 in quarters 0-2, 6/5/5 over warps 3, 7, 11
+    const int c_begin = (q == 3) ? (kgi == 0 ? 0 : 1 + 5 * kgi) : kgi * (kRowChunks / 4);
+    const int c_count = (q == 3) ? (kgi == 0 ? 6 : 5) : kRowChunks / 4;
     const unsigned int lane_addr = tmem + ((unsigned int)(q * 32) << 16);
     // B chunk ids handled by this thread: bi0, bi0 + 384, ... (warps of quarters 0-2)
     const int bi0 = (q == 3) ? kChunksB : (kgi * 3 + q) * 32 + lane;
@@ -327,24 +357,25 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
       { TC_T0(); if (st.uses[s] > 0u) { mbar_wait(&pipe.stage_free[s], (st.uses[s] - 1u) & 1u); tc_fence_after(); } TC_ACC(1); }
       TC_T0();
       const unsigned char* raw = raw_ptr + (size_t)d * TS::kRawBytes;
-      const unsigned int col0 = lane_addr + (unsigned int)(kAccCols + s * 64);
+      const unsigned int col0 = lane_addr + (unsigned int)(kAccCols + s * kStageCols);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < 6; ++i) {
         if (i < c_count) {
-          const int c = c_begin + i;
-          const float4 v = *reinterpret_cast<const float4*>(raw + sw128(ar, c));
+          const int c = c_begin + i;  // chunk c of the row: atom c / 8, chunk c % 8 within the atom's 128-byte row
+          const float4 v = *reinterpret_cast<const float4*>(raw + (c >> 3) * TS::kAAtomBytes + sw128(ar, c & 7));
           float4 hi, lo;
-          split4(v, hi, lo);
+          split4(v, st.nz2, hi, lo);
           tmem_store4(col0 + (unsigned int)(c * 4), hi);
-          tmem_store4(col0 + 32u + (unsigned int)(c * 4), lo);
+          tmem_store4(col0 + (unsigned int)(kBlockK + c * 4), lo);
         }
       }
       unsigned char* stage = tiles_ptr + (size_t)s * TS::kStageBytes;
       for (int bi = bi0; bi < kChunksB; bi += 384) {
-        const unsigned int off = sw128(bi >> 3, bi & 7);
+        const int atom = bi / (BN * 8), lid = bi % (BN * 8);
+        const unsigned int off = (unsigned int)(atom * TS::kBAtomBytes) + sw128(lid >> 3, lid & 7);
         const float4 v = *reinterpret_cast<const float4*>(raw + TS::kABytes + off);
         float4 hi, lo;
-        split4(v, hi, lo);
+        split4(v, st.nz2, hi, lo);
         *reinterpret_cast<float4*>(stage + off) = hi;
         *reinterpret_cast<float4*>(stage + TS::kBBytes + off) = lo;
       }

@@ -49,7 +49,7 @@ def init_factors(tensor, rank, init='random', device=None, seed=None):
 last_report = None  # LoopReport of the most recent admm_iteration call (diagnostics)
 
 
-def admm_iteration(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, return_codes=False):
+def admm_iteration(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, return_codes=False, precision=0):
     """reference source/admm.py:51-67: `max_iter - 1` iterations of
     { H_ls = (G + rho I)^-1 (F + rho (H + U)); H = Q(H_ls - U); U += H - H_ls }, rho = trace(G)/R.
     Returns a NEW tensor H and the caller's U, which is updated in place (:60, :67)."""
@@ -59,7 +59,7 @@ def admm_iteration(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, r
     Uc = U if (U.dtype == torch.float32 and U.is_contiguous()) else _native.f32c(U).clone()
     codes = torch.empty(Hc.shape, dtype=torch.int8, device=Hc.device) if return_codes else None
     report = _native.admm_iteration_inplace(Hc, Uc, _native.f32c(F), _native.f32c(G), max_iter, eps, bits, qscheme,
-                                            num_attempts, codes)
+                                            num_attempts, codes, precision)
     last_report = _native.read_report(report)  # raises LinAlgError if G + rho I is not positive definite
     if Uc is not U:
         U.copy_(Uc)

@@ -20,7 +20,7 @@ def _bytes(n, device):
 
 class LayerSolver:
     def __init__(self, weight, factors, bits, qscheme, max_iter_admm=1000, eps=1e-8, tol=1e-5,
-                 num_attempts=200, mttkrp_precision=0, init_is_random=True, time_loops=False):
+                 num_attempts=200, mttkrp_precision=0, init_is_random=True, time_loops=False, solve_precision=0):
         _native.require_cuda(weight)
         assert weight.ndim in (2, 3), "Incorrect number of dimentions in weight tensor"
         self.W = _native.f32c(weight)
@@ -29,6 +29,7 @@ class LayerSolver:
         _native.qscheme_id(qscheme)
         self.max_iter_admm, self.eps, self.tol = int(max_iter_admm), float(eps), float(tol)
         self.num_attempts, self.mttkrp_precision = int(num_attempts), int(mttkrp_precision)
+        self.solve_precision = int(solve_precision)
         dev = self.W.device
         self.factors = [_native.f32c(f).to(dev).clone() for f in factors]
         self.duals = [torch.zeros_like(f) for f in self.factors]       # :209-212 / :272-273
@@ -94,7 +95,8 @@ class LayerSolver:
             ev0.record()
         _native.admm_loop_inplace(self.factors[mode], self.duals[mode], self.F[mode], self.Minv, self.rho,
                                   self.inv_status, self.max_iter_admm, self.eps, self.bits, self.qscheme,
-                                  self.num_attempts, codes, report=self.reports_dev[mode], ws=self.ws_loop)  # :218
+                                  self.num_attempts, codes, report=self.reports_dev[mode], ws=self.ws_loop,
+                                  precision=self.solve_precision)  # :218
         if self.time_loops:
             ev1.record()
             self.loop_events.append((mode, ev0, ev1))

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mttkrp-precision", type=int, default=0)
+    ap.add_argument("--solve-precision", type=int, default=1,
+                    help="ridge product inside the ADMM loop: 0 = float32 FFMA, 1 = 3xTF32 on tcgen05 (default)")
     return ap.parse_args()
 
 
@@ -66,7 +68,8 @@ def config_dict(args, desc, extra=None):
     cfg = {"workload": f"{desc}, ADMM {args.bits}-bit {QSCHEME}, reduction-rate {args.reduction_rate}, init=random, "
                        f"max_iter_admm={args.max_iter_admm}; one step = one outer sweep over every layer",
            "bits": args.bits, "qscheme": QSCHEME, "reduction_rate": args.reduction_rate,
-           "max_iter_admm": args.max_iter_admm, "num_attempts": 200}
+           "max_iter_admm": args.max_iter_admm, "num_attempts": 200,
+           "ridge_product": "3xTF32 tcgen05" if getattr(args, "solve_precision", 0) == 1 else "float32 FFMA"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -227,7 +230,7 @@ def run_native(args):
     for name, W, rnk, init in problems:
         solvers.append(LayerSolver(W.to(dev), [f.to(dev) for f in init], args.bits, QSCHEME,
                                    max_iter_admm=args.max_iter_admm, mttkrp_precision=args.mttkrp_precision,
-                                   time_loops=True))
+                                   solve_precision=args.solve_precision, time_loops=True))
         host.append({"W": W.pin_memory(), "factors": [f.clone().pin_memory() for f in init],
                      "duals": [torch.zeros_like(f).pin_memory() for f in init],
                      "factors_q": [torch.zeros_like(f).pin_memory() for f in init],

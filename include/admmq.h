@@ -144,18 +144,22 @@ typedef struct admmq_loop_report {
   uint64_t phase_ns[4];
 } admmq_loop_report;
 
-/* The loop alone, for callers that keep (Minv, rho) of a ridge system around (admmq_spd_inverse):
+/* precision (both entry points): how the per-iteration ridge product H_ls = (F + rho (H + U)) . Minv is formed
+ *   0  float32 FFMA tiles on the CUDA cores (parity mode: what the bit-level comparisons against the reference use)
+ *   1  3xTF32 on tcgen05 / tensor memory with TMA-fed operands (throughput mode; factors with < 64 rows fall back to 0)
+ *
+ * The loop alone, for callers that keep (Minv, rho) of a ridge system around (admmq_spd_inverse):
  *   Minv  R x admmq_padded_ld(R) float32, rho / inv_status device scalars written by admmq_spd_inverse
  *         (inv_status may be NULL; a non-zero value makes the loop return it in report->status untouched). */
 ADMMQ_API size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts);
 ADMMQ_API int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
                     const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
-                    int num_attempts, int8_t* codes, admmq_loop_report* report,
+                    int num_attempts, int precision, int8_t* codes, admmq_loop_report* report,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 ADMMQ_API size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts);
 ADMMQ_API int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R,
-                         int max_iter, float eps, int bits, int qscheme, int num_attempts,
+                         int max_iter, float eps, int bits, int qscheme, int num_attempts, int precision,
                          int8_t* codes, admmq_loop_report* report,
                          void* workspace, size_t workspace_bytes, void* stream);
 

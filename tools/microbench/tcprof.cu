@@ -5,11 +5,11 @@
 #include "../../admm-quantization_b200/csrc/tc_gemm.cu"
 namespace admmq { char* error_buffer() { static char b[8]; return b; } int fail(int c, const char*, ...) { return c; } void count_launches(int) {} int device_props(DeviceProps*) { return 0; } }
 template <int BN>
-__global__ void __launch_bounds__(512, 1) k(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* C, int ldc, long long* dbg) {
+__global__ void __launch_bounds__(512, 1) k(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* C, int ldc, long long* dbg, float nzv) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ tc::Pipe pipe;
   tc::PipeState st;
-  tc::pipe_setup(pipe, st);
+  tc::pipe_setup(pipe, st, nzv);
   const long long t_begin = clock64();
   const int tilesM = (M + 127) / 128, tilesN = (N + BN - 1) / BN;
   long long epi = 0;
@@ -41,12 +41,12 @@ template <int BN> void run(int M, int N, int K) {
   const int grid = tiles < 148 ? tiles : 148;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   GemmMaps maps; tc::make_operand_tmap(&maps.a, A, M, K, K, 128); tc::make_operand_tmap(&maps.b, B, N, K, K, BN);
-  for (int rep = 0; rep < 3; ++rep) { cudaEventRecord(e0); k<BN><<<grid, 512, smem>>>(maps, M, N, K, C, N, dbg); cudaEventRecord(e1); cudaDeviceSynchronize(); }
+  for (int rep = 0; rep < 3; ++rep) { cudaEventRecord(e0); k<BN><<<grid, 512, smem>>>(maps, M, N, K, C, N, dbg, -0.0f); cudaEventRecord(e1); cudaDeviceSynchronize(); }
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   long long h[16]; cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
-  const int nkb = (K + 31) / 32; const int tiles_cta0 = (tiles + grid - 1) / grid;
+  const int nkb = (K + 63) / 64; const int tiles_cta0 = (tiles + grid - 1) / grid;
   printf("BN=%d M=%d N=%d K=%d: %.1f us (%s), CTA0: %d tiles x %d K-blocks, total %lld cyc\n", BN, M, N, K, ms * 1e3, cudaGetErrorString(cudaGetLastError()), tiles_cta0, nkb, h[7]);
   printf("   producer(thread 0): cp.async wait %lld, stage_free wait %lld, convert+issue %lld, tile_done wait %lld, epilogue %lld\n", h[0], h[1], h[2], h[5], h[6]);
   printf("   mma warp (lane 0) : full wait %lld, issue %lld, tile_done wait %lld   => per K-block: full-wait %.0f issue %.0f\n", h[8 + 3], h[8 + 4], h[8 + 5], (double)h[11] / (tiles_cta0 * nkb), (double)h[12] / (tiles_cta0 * nkb));
 }
-int main() { run<32>(512, 1141, 1144); run<64>(4096, 4096, 4096); run<16>(256, 566, 568); return 0; }
+int main() { run<32>(512, 1141, 1144); run<32>(4096, 4096, 4096); run<16>(256, 566, 568); return 0; }

@@ -8,6 +8,7 @@ MSE = "tensor_mseminmax_symmetric"
 shapes = [(64, 134, 64, 9), (9, 134, 64, 64), (128, 278, 128, 9), (9, 278, 128, 128), (256, 566, 256, 9), (9, 566, 256, 256),
           (512, 759, 256, 9), (256, 759, 512, 9), (512, 1141, 512, 9), (9, 1141, 512, 512), (2048, 204, 512, 1), (4096, 1024, 4096, 1)]
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+prec = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 g = torch.Generator().manual_seed(0)
 for (I, R, n1, n2) in shapes:
     B = torch.randn(n1, R, generator=g).cuda(); C = torch.randn(n2, R, generator=g).cuda()
@@ -21,7 +22,7 @@ for (I, R, n1, n2) in shapes:
         e0.record()
         Minv, rho, st = nat.spd_inverse(G)
         e1.record()
-        r = nat.admm_iteration_inplace(Hc, Uc, F, G, iters + 1, 1e-8, 4, MSE)
+        r = nat.admm_iteration_inplace(Hc, Uc, F, G, iters + 1, 1e-8, 4, MSE, precision=prec)
         e2.record()
         torch.cuda.synchronize()
     rp = nat.read_report(r)
@@ -30,4 +31,5 @@ for (I, R, n1, n2) in shapes:
     evals = 200.0 * I * R / (per * 1e-6) / 1e12
     gflops = 2.0 * I * R * R / (per * 1e-6) / 1e12
     print(f"I={I:5d} R={R:5d}: inverse {t_inv:8.3f} ms; loop {per:8.2f} us/iter ({rp.iterations} its)  "
-          f"{evals:6.3f} T cand-evals/s  gemm-equiv {gflops:6.2f} TFLOP/s", flush=True)
+          f"{evals:6.3f} T cand-evals/s  gemm-equiv {gflops:6.2f} TFLOP/s  phases us/iter "
+          f"{[round(x / 1e3 / max(rp.iterations, 1), 1) for x in rp.phase_ns[:3]]}", flush=True)
