@@ -1,0 +1,178 @@
+"""ALS + EPC initialisation - drop-in for the reference's source/parafac_epc.py:12-82.
+
+The reference delegates the arithmetic to two third-party packages that are neither vendored nor
+installed here: `tensorly.decomposition.parafac` (0.4.5) and musco's `cp_anc` (1.0.6).  Both are
+restated from their published algorithms (PARITY UNPINNED - there is nothing to
+compare bit for bit): ALS with normal-equation solves and column normalisation, and error-preserving
+correction (Phan, Tichavsky, Cichocki, IEEE TSP 2019): minimise the sum of squared component norms
+subject to ||Y - Yhat|| <= delta.  Everything runs in float64 on the tensor's own device with torch
+dense ops (an R x R `eigh` / `solve` per mode update: init work, outside the timed ADMM hot path).
+The wrapper logic (float64 copy, ascending mode permutation, rounds, stop rules, original mode order)
+follows source/parafac_epc.py line by line.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .utils import unfold
+
+
+def _khatri_rao(mats):
+    out = mats[0]
+    for M in mats[1:]:
+        out = (out[:, None, :] * M[None, :, :]).reshape(-1, out.shape[1])
+    return out
+
+
+def _mttkrp(T, factors, mode):
+    return unfold(T, mode) @ _khatri_rao([f for k, f in enumerate(factors) if k != mode])
+
+
+def _reconstruct(weights, factors):
+    N = len(factors)
+    letters = "".join(chr(105 + k) for k in range(N))
+    spec = "r," + ",".join(f"{c}r" for c in letters) + "->" + letters
+    return torch.einsum(spec, weights, *factors)
+
+
+def parafac_als(tensor, rank, n_iter_max=100, tol=1e-8, random_state=None, normalize_factors=False,
+                dtype=None):
+    """`tensorly.decomposition.parafac(tensor, rank, init='random', ...)` as the reference calls it
+    (source/admm.py:38-39, source/parafac_epc.py:42-43, scripts/factorize.py:324-325).
+    Returns (weights, factors).  `random_state=None` draws from numpy's GLOBAL stream, like tensorly."""
+    if isinstance(random_state, np.random.RandomState):
+        rng = random_state
+    else:
+        rng = np.random.mtrand._rand if random_state is None else np.random.RandomState(random_state)
+    dtype = tensor.dtype if dtype is None else dtype
+    Y = tensor.to(dtype)
+    dev, N = Y.device, Y.ndim
+    factors = [torch.from_numpy(rng.random_sample((Y.shape[m], rank))).to(device=dev, dtype=dtype) for m in range(N)]
+    if normalize_factors:
+        factors = [f / (torch.linalg.norm(f, dim=0) + 1e-12) for f in factors]
+    weights = torch.ones(rank, dtype=dtype, device=dev)
+    norm_y = torch.linalg.norm(Y)
+    errs = []
+    for it in range(n_iter_max):
+        mt = None
+        for m in range(N):
+            gram = torch.ones(rank, rank, dtype=dtype, device=dev)
+            for k in range(N):
+                if k != m:
+                    gram = gram * (factors[k].T @ factors[k])
+            mt = _mttkrp(Y, factors, m)
+            f = torch.linalg.solve(gram.T, mt.T).T
+            if normalize_factors:
+                weights = torch.linalg.norm(f, dim=0)
+                weights = torch.where(weights <= torch.finfo(dtype).eps, torch.ones_like(weights), weights)
+                f = f / weights
+            factors[m] = f
+        if tol:
+            gram_all = torch.ones(rank, rank, dtype=dtype, device=dev)
+            for k in range(N):
+                gram_all = gram_all * (factors[k].T @ factors[k])
+            norm_rec2 = (weights[:, None] * weights[None, :] * gram_all).sum()
+            inner = (weights * (mt * factors[N - 1]).sum(dim=0)).sum()
+            err = math.sqrt(abs(float(norm_y ** 2 + norm_rec2 - 2 * inner))) / float(norm_y)
+            errs.append(err)
+            if it >= 1 and abs(errs[-2] - errs[-1]) < tol:
+                break
+    return weights, factors
+
+
+def epc_sweep(Y, factors, delta, norm_y2=None):
+    """One error-preserving-correction pass over all modes (the body of musco's `cp_anc`)."""
+    N = Y.ndim
+    rank = factors[0].shape[1]
+    norm_y2 = float(torch.sum(Y * Y)) if norm_y2 is None else norm_y2
+    target = delta * delta
+    for m in range(N):
+        scale = torch.ones(rank, dtype=Y.dtype, device=Y.device)
+        for k in range(N):
+            if k != m:
+                nk = torch.linalg.norm(factors[k], dim=0)
+                nk = torch.where(nk == 0, torch.ones_like(nk), nk)
+                factors[k] = factors[k] / nk
+                scale = scale * nk
+        factors[m] = factors[m] * scale
+        gamma = torch.ones(rank, rank, dtype=Y.dtype, device=Y.device)
+        for k in range(N):
+            if k != m:
+                gamma = gamma * (factors[k].T @ factors[k])
+        T = _mttkrp(Y, factors, m)
+        sig, V = torch.linalg.eigh(gamma)
+        sig = torch.clamp(sig, min=0.0)
+        Tt = T @ V
+        s = (Tt * Tt).sum(dim=0)
+        # residual(mu) = ||Y||^2 - sum_i s_i (sig_i + 2 mu) / (sig_i + mu)^2, increasing in mu: bisection on the host
+        sig_c, s_c = sig.cpu(), s.cpu()
+
+        def resid(mu):
+            return norm_y2 - float((s_c * (sig_c + 2 * mu) / (sig_c + mu) ** 2).sum())
+
+        floor = float(sig_c.max()) * 1e-14
+        mu = 0.0
+        if resid(floor) < target:
+            lo, hi = floor, max(float(sig_c.max()), 1e-300)
+            while resid(hi) < target and hi < 1e300:
+                hi *= 2.0
+            for _ in range(200):
+                mid = 0.5 * (lo + hi)
+                if resid(mid) < target:
+                    lo = mid
+                else:
+                    hi = mid
+                if hi - lo <= 1e-15 * hi:
+                    break
+            mu = 0.5 * (lo + hi)
+        factors[m] = (Tt / (sig + max(mu, floor))) @ V.T
+    return factors
+
+
+def _intensities(factors):
+    lam = torch.ones(factors[0].shape[1], dtype=factors[0].dtype, device=factors[0].device)
+    for f in factors:
+        lam = lam * torch.linalg.norm(f, dim=0)
+    return lam
+
+
+def parafac_epc(tensor, rank, als_maxiter=5000, als_tol=1e-5, num_threads=4, init="random",
+                epc_maxiter=5000, epc_rounds=50, epc_tol=1e-5, stop_tol=1e-4, ratio_tol=1e-3,
+                ratio_max_iters=10):
+    """reference source/parafac_epc.py:12-82.  Returns (lmbda, Us) with Us in the ORIGINAL mode order,
+    float64, on the device of `tensor`.  `num_threads` is accepted for signature compatibility; the
+    reference's `torch.set_num_threads` (:33) is a CPU-side global side effect that has no GPU meaning."""
+    if init != "random":
+        raise NotImplementedError(init)
+    Y = tensor.detach().to(torch.float64)                                   # :36
+    order = np.argsort(Y.shape)                                             # :38
+    Yp = Y.permute(tuple(int(o) for o in order)).contiguous()               # :40
+    weights, factors = parafac_als(Yp, rank, n_iter_max=als_maxiter, tol=als_tol, random_state=None,
+                                   normalize_factors=True)                  # :42-43
+    delta = float(torch.linalg.norm(Yp - _reconstruct(weights, factors)))   # :51
+    lam_prev_norm = float(torch.linalg.norm(weights))                       # :52
+    factors[-1] = factors[-1] * weights                                     # :53
+    alpha_prev = float(weights.max() / weights.min())                       # :57
+    norm_y2 = float(torch.sum(Yp * Yp))
+    stopflag = 0
+    lam = _intensities(factors)
+    for _ in range(epc_rounds):                                             # :61
+        prev = None
+        for _it in range(epc_maxiter):                                      # cp_anc(maxiter, tol)  :63
+            factors = epc_sweep(Yp, factors, delta, norm_y2)
+            cur = float((_intensities(factors) ** 2).sum())
+            if prev is not None and abs(prev - cur) < epc_tol * prev:
+                break
+            prev = cur
+        lam = _intensities(factors)
+        lam_norm = float(torch.linalg.norm(lam))
+        alpha = float(lam.max() / lam.min())
+        if abs(lam_prev_norm - lam_norm) < stop_tol * lam_prev_norm:        # :67
+            break
+        stopflag = stopflag + 1 if abs(alpha_prev - alpha) < ratio_tol else 0   # :69
+        lam_prev_norm, alpha_prev = lam_norm, alpha
+        if stopflag >= ratio_max_iters:                                     # :74
+            break
+    inv = np.argsort(order)
+    return lam, [factors[int(i)] for i in inv]                              # :77-82

@@ -1,0 +1,145 @@
+"""CPU-only tests of the host-side logic: rank / reshape rules against the reference's tables, the LPT sharding,
+the ALS + EPC initialisation (property tests - parity unpinned), the CLI argument contract, and the
+N > 1 gather path on the gloo backend with two processes."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "admm-quantization_b200")
+torch.set_num_threads(1)
+
+
+def test_rank_rule_reproduces_the_reference_rank_tables():
+    from source import workloads as wl
+    from source.solver import layer_weight_as_tensor, rank_from_reduction_rate
+    table = json.load(open(os.path.join(REPO, "tests", "golden", "rank_table.json")))["table"]
+    layers = {n: (co, ci, kh, kw) for n, co, ci, kh, kw in wl.resnet18_conv_layers()}
+    assert len(layers) == 16
+    checked = 0
+    for rate, ranks in table.items():
+        for name, ref_rank in ranks.items():
+            if name not in layers:
+                continue
+            co, ci, kh, kw = layers[name]
+            W = layer_weight_as_tensor(torch.empty(co, ci, kh, kw))
+            assert W.shape == (co, ci, kh * kw)
+            assert rank_from_reduction_rate(W, float(rate)) == ref_rank, (rate, name)
+            checked += 1
+    assert checked >= 60
+    assert layer_weight_as_tensor(torch.empty(8, 4, 1, 1)).shape == (8, 4)
+
+
+def test_lpt_sharding_is_balanced_and_complete():
+    from source import workloads as wl
+    from source.distributed import shard_units
+    units = [{"shape": (co, ci, kh * kw), "rank": int(co * ci * kh * kw / (co + ci + kh * kw) / 2)}
+             for _, co, ci, kh, kw in wl.resnet18_conv_layers()]
+    costs = [wl.solve_cost(u["shape"], u["rank"]) for u in units]
+    for ws in (1, 2, 4, 8):
+        owner = shard_units(units, ws)
+        assert sorted(set(owner)) == list(range(ws))
+        load = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(ws)]
+        # the largest unit bounds what any schedule can do (~4.2x on 8 GPUs for one ResNet-18)
+        assert max(load) <= max(sum(costs) / ws, max(costs)) * 1.34
+    assert sum(costs) / max(costs) == pytest.approx(4.2, abs=0.4)
+
+
+def test_parafac_epc_properties():
+    from source.parafac_epc import _intensities, _reconstruct, epc_sweep, parafac_als, parafac_epc
+    np.random.seed(3)
+    g = torch.Generator().manual_seed(3)
+    W = torch.randn(14, 10, 6, generator=g)
+    Y = W.double()
+    w, fac = parafac_als(Y, 12, n_iter_max=40, tol=1e-7, random_state=5, normalize_factors=True)
+    delta = float(torch.linalg.norm(Y - _reconstruct(w, fac)))
+    assert delta / float(torch.linalg.norm(Y)) < 0.75          # ALS does reduce the error
+    fac[-1] = fac[-1] * w
+    prev = float((_intensities(fac) ** 2).sum())
+    for _ in range(8):
+        fac = epc_sweep(Y, fac, delta)
+        err = float(torch.linalg.norm(Y - torch.einsum("ir,jr,kr->ijk", *fac)))
+        cur = float((_intensities(fac) ** 2).sum())
+        assert err <= delta * (1 + 1e-6)                       # the error bound is preserved
+        assert cur <= prev * (1 + 1e-9)                        # the intensity never grows
+        prev = cur
+    lam, Us = parafac_epc(W, 12, als_maxiter=15, epc_maxiter=4, epc_rounds=2)
+    assert [u.shape for u in Us] == [(14, 12), (10, 12), (6, 12)] and Us[0].dtype == torch.float64
+    rel = float(torch.linalg.norm(Y - torch.einsum("ir,jr,kr->ijk", *Us)) / torch.linalg.norm(Y))
+    assert rel < 0.8 and lam.shape == (12,)
+    with pytest.raises(NotImplementedError):
+        parafac_epc(W, 4, init="svd")
+
+
+def test_init_factors_random_matches_reference_generator_semantics():
+    from source.admm import init_factors
+    W = torch.zeros(5, 4, 3)
+    a = init_factors(W, 7, init="random", device=None, seed=42)
+    gen = torch.Generator().manual_seed(42)
+    ref = [torch.randn(d, 7, generator=gen) for d in W.shape]   # source/admm.py:22-28: one generator, modes in order
+    assert all(torch.equal(x, y) for x, y in zip(a, ref))
+    with pytest.raises(NotImplementedError):
+        init_factors(W, 7, init="bogus", seed=1)
+
+
+def test_cli_argument_contract():
+    sys.path.insert(0, os.path.join(PKG, "scripts"))
+    import importlib
+    fz = importlib.import_module("factorize")
+    base = ["--model-name", "resnet18", "--method", "admm", "--layer", "layer1.0.conv1", "--bits", "4", "--seed", "42",
+            "--qscheme", "tensor_mseminmax_symmetric"]
+    with pytest.raises(ValueError):
+        fz.parse_args(base)                                     # neither --rank nor --reduction-rate (:98-99)
+    with pytest.raises(ValueError):
+        fz.parse_args([a if a != "admm" else "bogus" for a in base] + ["--rank", "3"])   # (:100-101)
+    a = fz.parse_args(base + ["--reduction-rate", "2"])
+    assert (a.max_iter_als, a.max_iter_admm, a.max_iter_epc, a.init) == (5000, 1000, 5000, "random")
+    assert fz.run_name(fz.parse_args(base + ["--rank", "134"])) == "admm_l=layer1.0.conv1_r=134_b=4_s=42_i=random_tensor_mseminmax_symmetric"
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [REPO, PKG]
+    from source.distributed import gather_results, shard_units
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    units = [{"key": f"u{i}", "seed": 100 + i, "shape": (8 + i, 6, 3), "rank": 5 + i} for i in range(5)]
+    owner = shard_units(units, world)
+    local = {}
+    for u, o in zip(units, owner):
+        if o == rank:
+            g = torch.Generator().manual_seed(u["seed"])
+            local[u["key"]] = {"factors": [torch.randn(d, u["rank"], generator=g) for d in u["shape"]],
+                               "loss": [0.5, 0.4], "loss_quant": [0.6]}
+    merged = gather_results(local)
+    if rank == 0:
+        ok = sorted(merged) == [u["key"] for u in units]
+        for u in units:
+            g = torch.Generator().manual_seed(u["seed"])
+            ref = [torch.randn(d, u["rank"], generator=g) for d in u["shape"]]
+            ok = ok and all(torch.equal(a, b) for a, b in zip(merged[u["key"]]["factors"], ref))
+            ok = ok and merged[u["key"]]["loss"] == [0.5, 0.4]
+        out.put(ok)
+    else:
+        assert merged is None
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_on_gloo_is_bitwise_identical():
+    """world_size 2 on CPU: units sharded by LPT, results gathered once; the merged factors equal what a single
+    process computes (no arithmetic crosses a shard boundary)."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() is True
