@@ -465,7 +465,9 @@ static IterationLayout iteration_layout(int I, int R, int grid) {
 
 constexpr int kMaxGrid = 1024;  // workspaces are sized for any cooperative grid up to this many CTAs
 
-static int coop_grid(const DeviceProps& dp) { return dp.sm_count; }
+static int coop_grid(const DeviceProps& dp, int max_ctas) {
+  return (max_ctas > 0 && max_ctas < dp.sm_count) ? max_ctas : dp.sm_count;
+}
 
 static int launch_spd_inverse(const float* G, int R, float* Minv, int ldm, float* rho_out, int* status,
                               unsigned int* barrier, double* Lw, double* Xw, int grid, cudaStream_t stream) {
@@ -590,8 +592,8 @@ extern "C" size_t admmq_spd_inverse_workspace_bytes(int R) {
   return 256 + spd_scratch_bytes(R);
 }
 
-extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, void* workspace,
-                                 size_t workspace_bytes, void* stream_) {
+extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, int max_ctas,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (G == nullptr || Minv == nullptr || rho_out == nullptr || status == nullptr || R <= 0)
     return fail(ADMMQ_E_BADARG, "admmq_spd_inverse: bad argument");
@@ -605,7 +607,7 @@ extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_
   ADMMQ_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), stream));
   double* Lw = (double*)(ws + 256);
   double* Xw = (double*)(ws + 256 + spd_scratch_bytes(R) / 2);
-  return launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp), stream);
+  return launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp, max_ctas), stream);
 }
 
 extern "C" size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts) {
@@ -616,7 +618,7 @@ extern "C" size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts
 
 extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
                                const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
-                               int num_attempts, int precision, int8_t* codes, admmq_loop_report* report,
+                               int num_attempts, int precision, int max_ctas, int8_t* codes, admmq_loop_report* report,
                                void* workspace, size_t workspace_bytes, void* stream_) {
   if (int e = check_loop_args("admmq_admm_loop", H, U, F, Minv, report, I, R, bits, qscheme, num_attempts)) return e;
   if (rho == nullptr) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: rho is null");
@@ -630,7 +632,7 @@ extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* 
     return fail(ADMMQ_E_WORKSPACE, "admmq_admm_loop: workspace needs %zu bytes, 256-byte aligned",
                 admmq_admm_loop_workspace_bytes(I, R, num_attempts));
   return launch_loop(H, U, F, Minv, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision, codes,
-                     report, (char*)workspace, coop_grid(dp), (cudaStream_t)stream_);
+                     report, (char*)workspace, coop_grid(dp, max_ctas), (cudaStream_t)stream_);
 }
 
 extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts) {
@@ -640,15 +642,16 @@ extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_att
 }
 
 extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R, int max_iter,
-                                    float eps, int bits, int qscheme, int num_attempts, int precision, int8_t* codes,
-                                    admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream_) {
+                                    float eps, int bits, int qscheme, int num_attempts, int precision, int max_ctas,
+                                    int8_t* codes, admmq_loop_report* report, void* workspace, size_t workspace_bytes,
+                                    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_loop_args("admmq_admm_iteration", H, U, F, G, report, I, R, bits, qscheme, num_attempts)) return e;
   if (precision != 0 && precision != 1) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: precision must be 0 or 1");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;
   if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
-  const int grid = coop_grid(dp);
+  const int grid = coop_grid(dp, max_ctas);
   const IterationLayout l = iteration_layout(I, R, kMaxGrid);
   if (workspace == nullptr || workspace_bytes < l.total || ((uintptr_t)workspace & 255) != 0)
     return fail(ADMMQ_E_WORKSPACE, "admmq_admm_iteration: workspace needs %zu bytes, 256-byte aligned", l.total);

@@ -49,13 +49,13 @@ def _load():
         "admmq_gemm_nt": (c_int, [vp, c_int, c_int, vp, c_int, c_int, c_int, vp, c_int, vp]),
         "admmq_padded_ld": (c_int, [c_int]),
         "admmq_spd_inverse_workspace_bytes": (c_sz, [c_int]),
-        "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, vp, c_sz, vp]),
+        "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, c_int, vp, c_sz, vp]),
         "admmq_admm_loop_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
-        "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, vp,
-                                    vp, vp, c_sz, vp]),
+        "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
+                                    vp, vp, vp, c_sz, vp]),
         "admmq_admm_iteration_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
-        "admmq_admm_iteration": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, vp,
-                                         vp, vp, c_sz, vp]),
+        "admmq_admm_iteration": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
+                                         vp, vp, vp, c_sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -238,7 +238,7 @@ def spd_inverse_workspace_bytes(R):
     return int(lib.admmq_spd_inverse_workspace_bytes(int(R)))
 
 
-def spd_inverse(G, out=None, ws=None):
+def spd_inverse(G, out=None, ws=None, max_ctas=0):
     """(Minv [R, ld], rho [1], status [1]) of G + trace(G)/R * I.  `out` = preallocated (Minv, rho, status)."""
     require_cuda(G)
     G = f32c(G)
@@ -251,11 +251,13 @@ def spd_inverse(G, out=None, ws=None):
     else:
         Minv, rho, status = out
     ws = _ws(spd_inverse_workspace_bytes(R), G.device, ws)
-    check(lib.admmq_spd_inverse(ptr(G), R, ptr(Minv), ptr(rho), ptr(status), ptr(ws), ws.numel(), stream_ptr(G.device)))
+    check(lib.admmq_spd_inverse(ptr(G), R, ptr(Minv), ptr(rho), ptr(status), int(max_ctas), ptr(ws), ws.numel(),
+                                stream_ptr(G.device)))
     return Minv, rho, status
 
 
-def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, codes=None, precision=0):
+def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, codes=None, precision=0,
+                           max_ctas=0):
     """Runs the persistent loop on contiguous float32 CUDA tensors, updating H and U in place.
     Returns the device report (uint8[32]); decode with `read_report` (synchronises)."""
     require_cuda(H, U, F, G)
@@ -267,8 +269,8 @@ def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempt
     nbytes = lib.admmq_admm_iteration_workspace_bytes(I, R, int(num_attempts))
     ws = workspace(nbytes, H.device)
     check(lib.admmq_admm_iteration(ptr(H), ptr(U), ptr(F), ptr(G), I, R, int(max_iter), float(eps), int(bits),
-                                   qscheme_id(qscheme), int(num_attempts), int(precision), ptr(codes), ptr(report),
-                                   ptr(ws), ws.numel(), stream_ptr(H.device)))
+                                   qscheme_id(qscheme), int(num_attempts), int(precision), int(max_ctas), ptr(codes),
+                                   ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
     return report
 
 
@@ -281,7 +283,7 @@ def new_report(device):
 
 
 def admm_loop_inplace(H, U, F, Minv, rho, inv_status, max_iter, eps, bits, qscheme, num_attempts=200, codes=None,
-                      report=None, ws=None, precision=0):
+                      report=None, ws=None, precision=0, max_ctas=0):
     """The persistent loop alone, given (Minv, rho, status) from `spd_inverse`; H and U are updated in place."""
     require_cuda(H, U, F, Minv, rho)
     for t in (H, U, F, Minv):
@@ -291,8 +293,8 @@ def admm_loop_inplace(H, U, F, Minv, rho, inv_status, max_iter, eps, bits, qsche
     report = new_report(H.device) if report is None else report
     ws = _ws(admm_loop_workspace_bytes(I, R, num_attempts), H.device, ws)
     check(lib.admmq_admm_loop(ptr(H), ptr(U), ptr(F), ptr(Minv), ptr(rho), ptr(inv_status), I, R, int(max_iter),
-                              float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), int(precision), ptr(codes),
-                              ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
+                              float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), int(precision),
+                              int(max_ctas), ptr(codes), ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
     return report
 
 

@@ -20,7 +20,8 @@ def _bytes(n, device):
 
 class LayerSolver:
     def __init__(self, weight, factors, bits, qscheme, max_iter_admm=1000, eps=1e-8, tol=1e-5,
-                 num_attempts=200, mttkrp_precision=0, init_is_random=True, time_loops=False, solve_precision=0):
+                 num_attempts=200, mttkrp_precision=0, init_is_random=True, time_loops=False, solve_precision=0,
+                 max_ctas=0):
         _native.require_cuda(weight)
         assert weight.ndim in (2, 3), "Incorrect number of dimentions in weight tensor"
         self.W = _native.f32c(weight)
@@ -30,6 +31,7 @@ class LayerSolver:
         self.max_iter_admm, self.eps, self.tol = int(max_iter_admm), float(eps), float(tol)
         self.num_attempts, self.mttkrp_precision = int(num_attempts), int(mttkrp_precision)
         self.solve_precision = int(solve_precision)
+        self.max_ctas = int(max_ctas)   # cooperative-grid budget of this solver (0 = every SM), see include/admmq.h
         dev = self.W.device
         self.factors = [_native.f32c(f).to(dev).clone() for f in factors]
         self.duals = [torch.zeros_like(f) for f in self.factors]       # :209-212 / :272-273
@@ -62,6 +64,7 @@ class LayerSolver:
         self.ws_err = _bytes(_native.recon_error_workspace_bytes(dims[0], nxny[0][0], nxny[0][1]), dev)
         self.time_loops = bool(time_loops)
         self.loop_events = []      # (mode, start, stop) CUDA events around the persistent kernel
+        self.part_events = None    # set to [] to record an event after every kernel group of a sweep (diagnostics)
         self.last_reports = []
         self._pending = False
         if not init_is_random:                                          # :192-201
@@ -87,28 +90,49 @@ class LayerSolver:
         o = self._others[mode]
         X = self.factors[o[0]]
         Y = self.factors[o[1]] if self.N == 3 else None
+        self._mark(f"m{mode}:start")
         _native.gram_hadamard(X, Y, out=self.G)                                          # :215
+        self._mark(f"m{mode}:gram")
         _native.mttkrp(self.unfoldings[mode], X, Y, self.mttkrp_precision, out=self.F[mode], ws=self.ws_mttkrp)  # :217
-        _native.spd_inverse(self.G, out=(self.Minv, self.rho, self.inv_status), ws=self.ws_inv)  # source/admm.py:52-54
+        self._mark(f"m{mode}:mttkrp")
+        _native.spd_inverse(self.G, out=(self.Minv, self.rho, self.inv_status), ws=self.ws_inv,
+                            max_ctas=self.max_ctas)  # source/admm.py:52-54
+        self._mark(f"m{mode}:inverse")
         if self.time_loops:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         _native.admm_loop_inplace(self.factors[mode], self.duals[mode], self.F[mode], self.Minv, self.rho,
                                   self.inv_status, self.max_iter_admm, self.eps, self.bits, self.qscheme,
                                   self.num_attempts, codes, report=self.reports_dev[mode], ws=self.ws_loop,
-                                  precision=self.solve_precision)  # :218
+                                  precision=self.solve_precision, max_ctas=self.max_ctas)  # :218
         if self.time_loops:
             ev1.record()
             self.loop_events.append((mode, ev0, ev1))
+        self._mark(f"m{mode}:loop")
         _native.project(self.factors[mode], self.bits, self.qscheme, self.num_attempts,
                         out=self.factors_q[mode], ws=self.ws_proj)                       # :222
+        self._mark(f"m{mode}:project")
+
+    def _mark(self, label):
+        if self.part_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.part_events.append((label, ev))
+
+    def part_times_ms(self):
+        """[(label, ms since the previous mark)] of the last recorded sweep (after a synchronise)."""
+        ev = self.part_events or []
+        return [(ev[i][0], ev[i - 1][1].elapsed_time(ev[i][1])) for i in range(1, len(ev))]
 
     def enqueue_sweep(self):
         """One outer iteration (:214-255) on the current stream; no allocation, no host sync."""
+        if self.part_events is not None:
+            self.part_events.clear()
         for mode in range(self.N):
             self.update_mode(mode)
         self._error_sums(self.factors, out=self.err_sums[0])           # :246-248
         self._error_sums(self.factors_q, out=self.err_sums[1])         # :249-253
+        self._mark("errors")
         self._pending = True
 
     def collect(self):

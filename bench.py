@@ -23,6 +23,10 @@ import sys
 import threading
 import time
 
+# One hardware work queue per layer stream: with the default of 8 connections, streams that share a queue falsely
+# serialise behind each other's long-running persistent kernels (measured: the last-launched layers started 0.4 s late).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(REPO, "admm-quantization_b200")
 for p in (REPO, PKG):
@@ -48,6 +52,14 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mttkrp-precision", type=int, default=0)
+    ap.add_argument("--concurrency", default="prop", choices=["off", "prop"],
+                    help="off: layers run one after the other on every SM; prop: every layer gets a share of the SMs "
+                         "proportional to its cost and all layers run concurrently on their own streams")
+    ap.add_argument("--min-ctas", type=int, default=2)
+    ap.add_argument("--trace-layer", default=None, help="print the per-kernel-group times of this layer's last sweep")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="SMs kept out of the cooperative-grid budgets so that the ordinary kernels between the loops "
+                         "(Gram, MTTKRP, projection, errors) never wait for a persistent kernel to finish")
     ap.add_argument("--solve-precision", type=int, default=1,
                     help="ridge product inside the ADMM loop: 0 = float32 FFMA, 1 = 3xTF32 on tcgen05 (default)")
     return ap.parse_args()
@@ -207,6 +219,22 @@ def run_reference(args):
     return 0
 
 
+def allocate_ctas(costs, sm_count, min_ctas):
+    """Share of the SMs for every independent solve, proportional to its estimated cost (largest-remainder rounding,
+    at least `min_ctas` each, sum == sm_count when there are enough SMs)."""
+    n = len(costs)
+    total = float(sum(costs))
+    if n * min_ctas >= sm_count:
+        return [max(1, sm_count // n)] * n
+    spare = sm_count - n * min_ctas
+    raw = [c / total * spare for c in costs]
+    out = [min_ctas + int(r) for r in raw]
+    rest = sm_count - sum(out)
+    for i in sorted(range(n), key=lambda k: raw[k] - int(raw[k]), reverse=True)[:rest]:
+        out[i] += 1
+    return out
+
+
 # ------------------------------------------------------------------------------------------ native arm
 def run_native(args):
     import torch
@@ -227,14 +255,22 @@ def run_native(args):
     problems = wl.build_problems(layers, args.reduction_rate, weight_seed=42, init_seed=42 + rank)
     host = []   # pinned host state for the end-to-end leg
     solvers = []
-    for name, W, rnk, init in problems:
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    budgets = allocate_ctas([wl.solve_cost(W.shape, rnk) for _, W, rnk, _ in problems], sm_count - args.reserve_sms,
+                            args.min_ctas) \
+        if args.concurrency == "prop" else [0] * len(problems)
+    streams = [torch.cuda.Stream(device=dev) for _ in problems] if args.concurrency == "prop" else None
+    for (name, W, rnk, init), g in zip(problems, budgets):
         solvers.append(LayerSolver(W.to(dev), [f.to(dev) for f in init], args.bits, QSCHEME,
                                    max_iter_admm=args.max_iter_admm, mttkrp_precision=args.mttkrp_precision,
-                                   solve_precision=args.solve_precision, time_loops=True))
+                                   solve_precision=args.solve_precision, time_loops=True, max_ctas=g))
         host.append({"W": W.pin_memory(), "factors": [f.clone().pin_memory() for f in init],
                      "duals": [torch.zeros_like(f).pin_memory() for f in init],
                      "factors_q": [torch.zeros_like(f).pin_memory() for f in init],
                      "err": torch.zeros(2, 2, dtype=torch.float64).pin_memory()})
+    for (name, _, _, _), s in zip(problems, solvers):
+        if args.trace_layer and name == args.trace_layer:
+            s.part_events = []
     inner_per_step = sum(s.inner_iterations_per_sweep() for s in solvers)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -243,25 +279,60 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sweep_events = []
+
+    def enqueue_all(prepare=None):
+        """One sweep of every layer.  Concurrent mode: every layer on its own stream (fork from / join into the
+        current stream with events, so CUDA events recorded on the current stream bracket all of the work)."""
+        if streams is None:
+            for k, s in enumerate(solvers):
+                if prepare is not None:
+                    prepare(k)
+                s.enqueue_sweep()
+            return
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event(enable_timing=True)
+        fork.record(main)
+        sweep_events.clear()
+        for k, (s, st) in enumerate(zip(solvers, streams)):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                if prepare is not None:
+                    prepare(k)
+                s.enqueue_sweep()
+                join = torch.cuda.Event(enable_timing=True)
+                join.record(st)
+            main.wait_event(join)
+            sweep_events.append((fork, join))
+
     def step():
-        for s in solvers:
-            s.enqueue_sweep()
+        enqueue_all()
         return [s.collect() for s in solvers]
 
     def step_e2e():
         """The same sweep through the public solver API starting from HOST buffers: weights, factors and
         duals go host->device (pinned), results (factors, duals, re-projected factors, error sums) come back."""
-        h2d = d2h = 0
-        for s, h in zip(solvers, host):
-            h2d += s.load_from_host(h["W"], h["factors"], h["duals"])
-            s.enqueue_sweep()
-            d2h += s.store_to_host(h["factors"], h["duals"], h["factors_q"], h["err"])
-        torch.cuda.synchronize()
-        return h2d, d2h
+        moved = [0, 0]
 
-    for _ in range(args.warmup):
+        def h2d_copy(k):
+            moved[0] += solvers[k].load_from_host(host[k]["W"], host[k]["factors"], host[k]["duals"])
+
+        enqueue_all(prepare=h2d_copy)
+        for s, h in zip(solvers, host):   # results come back on the (joined) current stream
+            moved[1] += s.store_to_host(h["factors"], h["duals"], h["factors_q"], h["err"])
+        torch.cuda.synchronize()
+        return moved[0], moved[1]
+
+    for w in range(args.warmup):
         flush.fill_(1)
         step()
+        if streams is not None and w < min(2, args.warmup - 1):
+            # re-balance the SM shares from what was just measured: a layer's work is (sweep time) x (its CTAs)
+            torch.cuda.synchronize()
+            work = [a.elapsed_time(b) * max(s.max_ctas, 1) for (a, b), s in zip(sweep_events, solvers)]
+            for s, g in zip(solvers, allocate_ctas(work, sm_count - args.reserve_sms, 1)):
+                s.max_ctas = g
+            budgets[:] = [s.max_ctas for s in solvers]
     for s in solvers:
         s.loop_events.clear()
     sampler = ClockSampler(local)
@@ -356,15 +427,22 @@ def run_native(args):
         v, sample, threads, spent = cpu_reference_sample(args, layers, args.cpu_budget_s)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                "host_cores": os.cpu_count(), "seconds": round(spent, 1)}
+    if rank == 0 and args.trace_layer:
+        for (name, _, _, _), s in zip(problems, solvers):
+            if s.part_events:
+                sys.stderr.write(f"[trace {name}] " + ", ".join(f"{k} {v:.1f}" for k, v in s.part_times_ms()) + "\n")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, desc, {"l2": "flushed between timed steps (256 MiB write)",
+                                                   "concurrency": args.concurrency,
+                                                   "ctas_per_layer": dict(zip([p[0] for p in problems], budgets)),
                                                    "parallelism": f"{world} independent seeds, one per GPU; no data-path collective",
                                                    "inner_iterations_per_step_per_gpu": inner_per_step}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "per_layer_inner_iter_per_s": per_layer,
+                "per_layer_sweep_ms_last_step": {p[0]: round(a.elapsed_time(b), 1) for p, (a, b) in zip(problems, sweep_events)},
                 "rec_error_last_step": {n[0]: round(e[0], 6) for n, e in zip(problems, errs)},
                 "factor_gather_ms": gather_ms}
         print(json.dumps(line), flush=True)

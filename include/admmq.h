@@ -118,7 +118,7 @@ ADMMQ_API int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int 
  * status (device int): 0 or ADMMQ_E_NOT_PD.  rho_out: device float. */
 ADMMQ_API int admmq_padded_ld(int R);
 ADMMQ_API size_t admmq_spd_inverse_workspace_bytes(int R);
-ADMMQ_API int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status,
+ADMMQ_API int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, int max_ctas,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ ADMM inner loop
@@ -144,7 +144,12 @@ typedef struct admmq_loop_report {
   uint64_t phase_ns[4];
 } admmq_loop_report;
 
-/* precision (both entry points): how the per-iteration ridge product H_ls = (F + rho (H + U)) . Minv is formed
+/* max_ctas (admmq_spd_inverse and both loop entry points): size of the cooperative grid, 0 = one CTA per SM.
+ *   Independent solves are latency bound on small factors (three device-wide barriers per iteration), so a caller
+ *   with several solves gives each a share of the SMs and runs them concurrently on different streams: cooperative
+ *   launches are gang scheduled, a grid that does not fit yet simply waits for SMs to free up.
+ *
+ * precision (both loop entry points): how the per-iteration ridge product H_ls = (F + rho (H + U)) . Minv is formed
  *   0  float32 FFMA tiles on the CUDA cores (parity mode: what the bit-level comparisons against the reference use)
  *   1  3xTF32 on tcgen05 / tensor memory with TMA-fed operands (throughput mode; factors with < 64 rows fall back to 0)
  *
@@ -154,13 +159,13 @@ typedef struct admmq_loop_report {
 ADMMQ_API size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts);
 ADMMQ_API int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
                     const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
-                    int num_attempts, int precision, int8_t* codes, admmq_loop_report* report,
+                    int num_attempts, int precision, int max_ctas, int8_t* codes, admmq_loop_report* report,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 ADMMQ_API size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts);
 ADMMQ_API int admmq_admm_iteration(float* H, float* U, const float* F, const float* G, int I, int R,
                          int max_iter, float eps, int bits, int qscheme, int num_attempts, int precision,
-                         int8_t* codes, admmq_loop_report* report,
+                         int max_ctas, int8_t* codes, admmq_loop_report* report,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
