@@ -286,7 +286,7 @@ extern "C" int admmq_unfold3(const float* W, int I, int J, int K, int mode, floa
 
 namespace admmq {
 size_t mttkrp_tc_workspace_bytes(int M, int nx, int ny, int R);
-int mttkrp_tc(const float* Wn, int M, const float* X, int nx, const float* Y, int ny, int R, float* F,
+int mttkrp_tc(const float* V, int M, const float* X, int nx, const float* Y, int ny, int R, float* F,
               void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace admmq
 
@@ -305,7 +305,13 @@ extern "C" int admmq_mttkrp(const float* Wn, int M, const float* X, int nx, cons
   if (Wn == nullptr || X == nullptr || F == nullptr || M <= 0 || nx <= 0 || R <= 0 || (Y != nullptr && ny <= 0))
     return fail(ADMMQ_E_BADARG, "admmq_mttkrp: bad argument");
   if (Y == nullptr) ny = 1;
-  if (precision == 1) return mttkrp_tc(Wn, M, X, nx, Y, ny, R, F, workspace, workspace_bytes, stream);
+  if (precision == 1) {
+    // the tensor-core form contracts the large index first and needs the (m, y, x) permutation of the tensor; for a
+    // matrix (ny == 1, nx % 4 == 0) the unfolding itself is that operand
+    if (ny == 1 && (nx & 3) == 0) return mttkrp_tc(Wn, M, X, nx, nullptr, 1, R, F, workspace, workspace_bytes, stream);
+    return fail(ADMMQ_E_UNSUPPORTED, "admmq_mttkrp: precision 1 on a 3-way tensor takes the permuted operand: use "
+                                     "admmq_permute_myx once per layer and admmq_mttkrp_tc");
+  }
   if (precision != 0) return fail(ADMMQ_E_BADARG, "admmq_mttkrp: precision must be 0 (f64 accumulate) or 1 (3xTF32)");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;

@@ -44,6 +44,9 @@ def _load():
         "admmq_unfold3": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
         "admmq_mttkrp_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
         "admmq_mttkrp": (c_int, [vp, c_int, vp, c_int, vp, c_int, c_int, vp, c_int, vp, c_sz, vp]),
+        "admmq_permute_myx": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
+        "admmq_mttkrp_tc_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+        "admmq_mttkrp_tc": (c_int, [vp, c_int, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
         "admmq_recon_error_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_recon_error": (c_int, [vp, c_int, vp, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
         "admmq_gemm_nt": (c_int, [vp, c_int, c_int, vp, c_int, c_int, c_int, vp, c_int, vp]),
@@ -67,7 +70,8 @@ def _load():
 lib = _load()
 EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count admmq_project_workspace_bytes "
            "admmq_project admmq_admm_loop_workspace_bytes admmq_admm_loop admmq_gemm_nt "
-           "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp "
+           "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp admmq_permute_myx "
+           "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
            "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration").split()
 
@@ -200,6 +204,36 @@ def mttkrp(Wn, X, Y=None, precision=0, out=None, ws=None):
     ws = _ws(mttkrp_workspace_bytes(M, nx, ny, R, precision), Wn.device, ws)
     check(lib.admmq_mttkrp(ptr(Wn), M, ptr(X), nx, ptr(Y), ny, R, ptr(F), int(precision), ptr(ws), ws.numel(),
                            stream_ptr(Wn.device)))
+    return F
+
+
+def permute_myx(Wn, nx, ny):
+    """V[(m, y), x] = Wn[m, x*ny + y] as an (M*ny, ldv) tensor, ldv = nx rounded up to 4 (operand of mttkrp_tc)."""
+    require_cuda(Wn)
+    Wn = f32c(Wn)
+    M = Wn.shape[0]
+    assert Wn.shape[1] == nx * ny
+    ldv = (nx + 3) // 4 * 4
+    V = torch.empty(M * ny, ldv, dtype=torch.float32, device=Wn.device)
+    check(lib.admmq_permute_myx(ptr(Wn), M, int(nx), int(ny), ptr(V), stream_ptr(Wn.device)))
+    return V
+
+
+def mttkrp_tc_workspace_bytes(M, nx, ny, R):
+    return int(lib.admmq_mttkrp_tc_workspace_bytes(int(M), int(nx), int(ny), int(R)))
+
+
+def mttkrp_tc(V, M, X, Y=None, out=None, ws=None):
+    """F = MTTKRP in 3xTF32 on the tensor cores; V from `permute_myx` (or the (M, nx) matrix itself when Y is None)."""
+    require_cuda(V, X, Y)
+    X = f32c(X)
+    Y = None if Y is None else f32c(Y)
+    nx, R = X.shape
+    ny = 1 if Y is None else Y.shape[0]
+    assert V.dtype == torch.float32 and V.is_contiguous() and V.shape == (M * ny, (nx + 3) // 4 * 4)
+    F = torch.empty(M, R, dtype=torch.float32, device=V.device) if out is None else out
+    ws = _ws(mttkrp_tc_workspace_bytes(M, nx, ny, R), V.device, ws)
+    check(lib.admmq_mttkrp_tc(ptr(V), int(M), ptr(X), nx, ptr(Y), ny, R, ptr(F), ptr(ws), ws.numel(), stream_ptr(V.device)))
     return F
 
 

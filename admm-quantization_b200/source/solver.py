@@ -59,8 +59,15 @@ class LayerSolver:
         self.ws_inv = _bytes(_native.spd_inverse_workspace_bytes(R), dev)
         self.ws_loop = _bytes(max(_native.admm_loop_workspace_bytes(d, R, self.num_attempts) for d in dims), dev)
         self.ws_proj = _bytes(_native.project_workspace_bytes(max(dims) * R, self.num_attempts), dev)
-        self.ws_mttkrp = _bytes(max(_native.mttkrp_workspace_bytes(dims[m], nxny[m][0], nxny[m][1], R,
-                                                                   self.mttkrp_precision) for m in range(self.N)), dev)
+        if self.mttkrp_precision == 1:
+            # tensor-core MTTKRP: the (m, y, x) permutations of W are constant, make them once (include/admmq.h)
+            self.permuted = [_native.permute_myx(self.unfoldings[m], nxny[m][0], nxny[m][1]) for m in range(self.N)]
+            self.ws_mttkrp = _bytes(max(_native.mttkrp_tc_workspace_bytes(dims[m], nxny[m][0], nxny[m][1], R)
+                                        for m in range(self.N)), dev)
+        else:
+            self.permuted = None
+            self.ws_mttkrp = _bytes(max(_native.mttkrp_workspace_bytes(dims[m], nxny[m][0], nxny[m][1], R, 0)
+                                        for m in range(self.N)), dev)
         self.ws_err = _bytes(_native.recon_error_workspace_bytes(dims[0], nxny[0][0], nxny[0][1]), dev)
         self.time_loops = bool(time_loops)
         self.loop_events = []      # (mode, start, stop) CUDA events around the persistent kernel
@@ -93,7 +100,10 @@ class LayerSolver:
         self._mark(f"m{mode}:start")
         _native.gram_hadamard(X, Y, out=self.G)                                          # :215
         self._mark(f"m{mode}:gram")
-        _native.mttkrp(self.unfoldings[mode], X, Y, self.mttkrp_precision, out=self.F[mode], ws=self.ws_mttkrp)  # :217
+        if self.permuted is not None:
+            _native.mttkrp_tc(self.permuted[mode], self.F[mode].shape[0], X, Y, out=self.F[mode], ws=self.ws_mttkrp)
+        else:
+            _native.mttkrp(self.unfoldings[mode], X, Y, 0, out=self.F[mode], ws=self.ws_mttkrp)  # :217
         self._mark(f"m{mode}:mttkrp")
         _native.spd_inverse(self.G, out=(self.Minv, self.rho, self.inv_status), ws=self.ws_inv,
                             max_ctas=self.max_ctas)  # source/admm.py:52-54
@@ -162,6 +172,14 @@ class LayerSolver:
             _native.unfold3(self.W, 2, out=self.unfoldings[2])
         else:
             self.unfoldings[1].copy_(self.W.t())
+        if self.permuted is not None:
+            dims = [f.shape[0] for f in self.factors]
+            for m in range(self.N):
+                o = self._others[m]
+                _native.check(_native.lib.admmq_permute_myx(_native.ptr(self.unfoldings[m]), dims[m], dims[o[0]],
+                                                            dims[o[1]] if self.N == 3 else 1,
+                                                            _native.ptr(self.permuted[m]),
+                                                            _native.stream_ptr(self.W.device)))
         for dst, src in zip(self.factors + self.duals, list(factors) + list(duals)):
             dst.copy_(src, non_blocking=True)
             n += dst.numel() * 4

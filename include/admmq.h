@@ -90,10 +90,22 @@ ADMMQ_API int admmq_unfold3(const float* W, int I, int J, int K, int mode, float
  *   Wn  (M x P) row-major unfolding, P = nx*ny;  X (nx x R), Y (ny x R) or NULL (ny = 1, matrix case);
  *   KR row p = x*ny + y is X[x,:] * Y[y,:];  F (M x R).
  *   precision 0: float64 accumulation on CUDA cores (parity mode)
- *   precision 1: 3xTF32 tcgen05 tensor-core path (throughput mode)  */
+ *   precision 1: 3xTF32 tcgen05 tensor-core path; matrices only (ny = 1, nx % 4 == 0) - 3-way tensors use
+ *                admmq_permute_myx + admmq_mttkrp_tc below, which need the permuted operand  */
 ADMMQ_API size_t admmq_mttkrp_workspace_bytes(int M, int nx, int ny, int R, int precision);
 ADMMQ_API int admmq_mttkrp(const float* Wn, int M, const float* X, int nx, const float* Y, int ny, int R,
                  float* F, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tensor-core MTTKRP (3xTF32 on tcgen05): the contraction over the large index x runs as a GEMM against X alone,
+ * T[(m,y), r] = sum_x V[(m,y), x] X[x, r], the small index y is folded afterwards, F[m, r] = sum_y Y[y, r] T[(m,y), r]
+ * (float64 accumulation) - no Khatri-Rao operand is ever formed.
+ *   admmq_permute_myx   V[(m, y), x] = Wn[m, x*ny + y]; V is (M*ny) x ldv with ldv = nx rounded up to 4 (pad columns
+ *                       zeroed).  W is constant, so this runs once per layer and mode.
+ *   admmq_mttkrp_tc     V as above, X (nx x R), Y (ny x R) or NULL (matrix case: V = Wn, T = F). */
+ADMMQ_API int admmq_permute_myx(const float* Wn, int M, int nx, int ny, float* V, void* stream);
+ADMMQ_API size_t admmq_mttkrp_tc_workspace_bytes(int M, int nx, int ny, int R);
+ADMMQ_API int admmq_mttkrp_tc(const float* V, int M, const float* X, int nx, const float* Y, int ny, int R, float* F,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Reconstruction error pieces for squared_relative_diff  source/admm.py:14-15 with the einsum of
  * scripts/factorize.py:246-253 (3-D) / :296-297 (2-D):  out2 (device double[2]) = { sum (W - [[A,X,Y]])^2, sum W^2 }.

@@ -161,6 +161,41 @@ def test_contractions_against_reference_and_float64(nat, golden_contractions):
         assert abs(err - float(gc[n + "/err"][0])) <= 1e-5 * err
 
 
+def test_tensor_core_mttkrp_and_gemm(nat, golden_contractions):
+    """3xTF32 tcgen05 paths against float64: admmq_gemm_nt and the permuted-operand MTTKRP, incl. ragged shapes.
+    Tolerance 4e-6 of the largest output (measured 3e-6 at K = 1141; cuBLAS float32 gives 1.5e-6)."""
+    g = torch.Generator().manual_seed(77)
+    for (M, N, K) in [(128, 32, 64), (100, 50, 72), (512, 300, 1144), (9, 1141, 512), (64, 134, 136)]:
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+        C = nat.gemm_nt(A.cuda(), B.cuda()).cpu().double()
+        ref = A.double() @ B.double().T
+        assert (C - ref).abs().max() <= 4e-6 * ref.abs().max(), (M, N, K)
+    gc = golden_contractions
+    for m in gc.meta:
+        n = m["name"]
+        W = gc[n + "/W"]
+        fac = [gc[n + "/" + k] for k in "ABC"[: m["ndim"]]]
+        fd = [dev(f) for f in fac]
+        f64 = [f.astype(np.float64) for f in fac]
+        if m["ndim"] == 3:
+            I, J, K = m["dims"]
+            unf = [dev(W.reshape(I, J * K)), nat.unfold3(dev(W), 1), nat.unfold3(dev(W), 2)]
+            subs = ["abc,br,cr->ar", "abc,ar,cr->br", "abc,ar,br->cr"]
+        else:
+            unf = [dev(W), dev(W.T.copy())]
+        for mode in range(m["ndim"]):
+            others = [k for k in range(m["ndim"]) if k != mode]
+            X = fd[others[0]]
+            Y = fd[others[1]] if m["ndim"] == 3 else None
+            V = nat.permute_myx(unf[mode], X.shape[0], 1 if Y is None else Y.shape[0])
+            F = nat.mttkrp_tc(V, unf[mode].shape[0], X, Y).cpu().numpy()
+            if m["ndim"] == 3:
+                F64 = np.einsum(subs[mode], W.astype(np.float64), f64[others[0]], f64[others[1]])
+            else:
+                F64 = W.astype(np.float64) @ f64[1] if mode == 0 else W.astype(np.float64).T @ f64[0]
+            assert np.abs(F - F64).max() <= 4e-6 * np.abs(F64).max(), (n, mode)
+
+
 def test_spd_inverse(nat):
     g = torch.Generator().manual_seed(11)
     for R, n in ((5, 9), (32, 40), (33, 64), (134, 64), (300, 128)):
@@ -348,6 +383,20 @@ def test_outer_loop_against_reference_history(golden_outer, capsys, precision):
         s2.sweep()
     rel2 = np.abs(np.array(s2.loss_hist) - go["mat/loss"]) / go["mat/loss"]
     assert rel2[0] <= 1e-3 and rel2.max() <= 2e-2
+
+
+def test_outer_loop_with_tensor_core_mttkrp(golden_outer):
+    """Throughput configuration (3xTF32 MTTKRP + 3xTF32 ridge product): first sweeps track the reference history."""
+    from source.solver import LayerSolver
+    go = golden_outer
+    m = go.case("config1_short")
+    W = dev(go["config1/W"])
+    init = [dev(go[f"config1_short/init{k}"]) for k in range(3)]
+    s = LayerSolver(W, init, m["bits"], m["qscheme"], max_iter_admm=m["max_iter_admm"], solve_precision=1, mttkrp_precision=1)
+    for _ in range(3):
+        s.sweep()
+    rel = np.abs(np.array(s.loss_hist) - go["config1_short/loss"][:3]) / go["config1_short/loss"][:3]
+    assert rel[0] <= 1e-3 and rel.max() <= 2e-2, rel
 
 
 @pytest.mark.parametrize("precision", [0, 1])

@@ -1,0 +1,29 @@
+"""Dev tool: MTTKRP timings (float64 CUDA-core vs 3xTF32 tensor-core) on the largest ResNet-18 layer."""
+import os, sys, torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [REPO, os.path.join(REPO, "admm-quantization_b200")]
+from source import _native as nat
+I, J, K, R = 512, 512, 9, 1141
+g = torch.Generator().manual_seed(0)
+W = (torch.randn(I, J, K, generator=g) * 0.02).cuda()
+fac = [torch.randn(d, R, generator=g).cuda() for d in (I, J, K)]
+unf = [W.reshape(I, J * K), nat.unfold3(W, 1), nat.unfold3(W, 2)]
+dims = [I, J, K]
+def T(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
+flop = 2.0 * I * J * K * R
+for mode in range(3):
+    o = [k for k in range(3) if k != mode]
+    X, Y = fac[o[0]], fac[o[1]]
+    V = nat.permute_myx(unf[mode], X.shape[0], Y.shape[0])
+    ws = torch.empty(nat.mttkrp_tc_workspace_bytes(dims[mode], X.shape[0], Y.shape[0], R), dtype=torch.uint8, device="cuda")
+    F1 = torch.empty(dims[mode], R, device="cuda")
+    t1 = T(lambda: nat.mttkrp_tc(V, dims[mode], X, Y, out=F1, ws=ws))
+    t0 = T(lambda: nat.mttkrp(unf[mode], X, Y, 0))
+    F0 = nat.mttkrp(unf[mode], X, Y, 0)
+    err = ((F1 - F0).abs().max() / F0.abs().max()).item()
+    print(f"mode {mode}: f64 CUDA-core {t0 * 1e3:8.1f} us ({flop / t0 / 1e9:6.1f} TFLOP/s)   3xTF32 tcgen05 {t1 * 1e3:8.1f} us ({flop / t1 / 1e9:6.1f} TFLOP/s fp32-equivalent)   max rel diff {err:.2e}")
