@@ -55,6 +55,7 @@ struct LoopParams {
   unsigned long long* cand;  // [kKeySlots][kMaxCandidates]
   double* slots;             // [gridDim.x][4]
   float* Hls;                // I x Rp
+  float* V;                  // I x R flat: H_ls - U, the projection input of this iteration (source/admm.py:59)
   float* RHS;                // I x Rp (pad columns stay zero)
   const float* Minv;         // R x Rp
 };
@@ -145,6 +146,7 @@ __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned i
             const float h = add_rn(acc[m][n], gs.red[(ty * TM + m) * BN + tx * TN + n]);
             p.Hls[(size_t)i * Rp + c] = h;
             const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
+            p.V[(size_t)i * R + c] = v;
             const unsigned int k = float_key(v);
             kmax = max(kmax, k);
             kinv = max(kinv, ~k);
@@ -184,6 +186,7 @@ __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc
         if (n < R) {
           p.Hls[(size_t)i * Rp + n] = v[c];
           const float d = sub_rn(v[c], __ldcg(p.U + (size_t)i * R + n));  // V = H_ls - U (:59)
+          p.V[(size_t)i * R + n] = d;
           const unsigned int k = float_key(d);
           kmax = max(kmax, k);
           kinv = max(kinv, ~k);
@@ -324,14 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
       degenerate = !(absmax > 0.0f) || isinf(absmax);
       if (!degenerate) {
         unsigned long long* cand = p.cand + (size_t)slot * kMaxCandidates;
-        const float* Hls = p.Hls;
-        const float* U = p.U;
-        cta_candidate_sums(
-            [Hls, U, R, Rp](long long e) {
-              const int ei = (int)e, i = ei / R, n = ei - i * R;  // I*R < 2^31 is checked on the host
-              return sub_rn(__ldcg(Hls + (size_t)i * Rp + n), __ldcg(U + e));
-            },
-            e0, e1, absmax, p.Nc, L, (double)N, cand, sm.search, p.neg_zero);
+        cta_candidate_sums(p.V, e0, e1, absmax, p.Nc, L, (double)N, cand, sm.search, p.neg_zero);
         bar.sync();
         lap(1);
         // ---------------- P3
@@ -346,37 +342,60 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f, f3 = 0.0f;
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     {
+      // batches of 4 elements per thread: all 16 loads of a batch are issued before the first dependent use, so the
+      // phase runs at L2 bandwidth instead of one L2 round trip per element
+      constexpr int kBatch = 4;
       int i = row0, n = col0, cnt = 0;
-      for (long long e = e0 + t; e < e1; e += kThreads) {
-        const float hls = __ldcg(p.Hls + (size_t)i * Rp + n);
-        const float u = __ldcg(p.U + e);
-        const float v = sub_rn(hls, u);
-        float code = 0.0f;
-        const float hq = degenerate ? qnan : quantize_value(v, qp, L, code);   // H = Q(H_ls - U)   (:59)
-        const float d1 = sub_rn(hq, hls);
-        const float un = add_rn(u, d1);                                        // U += H - H_ls     (:60)
-        const float d2 = sub_rn(hq, p.H[e]);
-        f0 = fmaf(d1, d1, f0);  // sum (H - H_ls)^2     (:62)
-        f1 = fmaf(hq, hq, f1);  // sum H^2
-        f2 = fmaf(d2, d2, f2);  // sum (H - H_prev)^2   (:63)
-        f3 = fmaf(un, un, f3);  // sum U^2
-        p.H[e] = hq;
-        p.U[e] = un;
-        p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(hq, un)));
-        if (p.codes != nullptr) p.codes[e] = (int8_t)code;
-        i += drow;
-        n += dcol;
-        if (n >= R) {
-          n -= R;
-          ++i;
+      long long e = e0 + t;
+      while (e < e1) {
+        long long ee[kBatch];
+        int ii[kBatch], nn[kBatch];
+        float hls[kBatch], u[kBatch], hp[kBatch], fv[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          ee[b] = e;
+          ii[b] = i;
+          nn[b] = n;
+          if (e < e1) {
+            hls[b] = __ldcg(p.Hls + (size_t)i * Rp + n);
+            u[b] = __ldcg(p.U + e);
+            hp[b] = p.H[e];
+            fv[b] = p.F[e];
+          }
+          e += kThreads;
+          i += drow;
+          n += dcol;
+          if (n >= R) {
+            n -= R;
+            ++i;
+          }
         }
-        if (++cnt == 16) {  // float32 partial sums over at most 16 elements, float64 beyond
-          sums[0] += (double)f0;
-          sums[1] += (double)f1;
-          sums[2] += (double)f2;
-          sums[3] += (double)f3;
-          f0 = f1 = f2 = f3 = 0.0f;
-          cnt = 0;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (ee[b] < e1) {
+            const float v = sub_rn(hls[b], u[b]);
+            float code = 0.0f;
+            const float hq = degenerate ? qnan : quantize_value(v, qp, L, code);   // H = Q(H_ls - U)   (:59)
+            const float d1 = sub_rn(hq, hls[b]);
+            const float un = add_rn(u[b], d1);                                     // U += H - H_ls     (:60)
+            const float d2 = sub_rn(hq, hp[b]);
+            f0 = fmaf(d1, d1, f0);  // sum (H - H_ls)^2     (:62)
+            f1 = fmaf(hq, hq, f1);  // sum H^2
+            f2 = fmaf(d2, d2, f2);  // sum (H - H_prev)^2   (:63)
+            f3 = fmaf(un, un, f3);  // sum U^2
+            p.H[ee[b]] = hq;
+            p.U[ee[b]] = un;
+            p.RHS[(size_t)ii[b] * Rp + nn[b]] = add_rn(fv[b], mul_rn(rho, add_rn(hq, un)));
+            if (p.codes != nullptr) p.codes[ee[b]] = (int8_t)code;
+            if (++cnt == 16) {  // float32 partial sums over at most 16 elements, float64 beyond
+              sums[0] += (double)f0;
+              sums[1] += (double)f1;
+              sums[2] += (double)f2;
+              sums[3] += (double)f3;
+              f0 = f1 = f2 = f3 = 0.0f;
+              cnt = 0;
+            }
+          }
         }
       }
       sums[0] += (double)f0;
@@ -415,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
 
 // ------------------------------------------------------------------------------------ host side
 struct LoopLayout {  // workspace of admmq_admm_loop
-  size_t header, cand, slots, hls, rhs, total;
+  size_t header, cand, slots, hls, rhs, v, total;
   int Rp;
 };
 
@@ -433,6 +452,7 @@ static LoopLayout loop_layout(int I, int R, int grid) {
   l.slots = take((size_t)grid * 4 * sizeof(double));
   l.rhs = take((size_t)I * l.Rp * sizeof(float));
   l.hls = take((size_t)I * l.Rp * sizeof(float));
+  l.v = take((size_t)I * R * sizeof(float));
   l.total = off;
   return l;
 }
@@ -547,6 +567,7 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.cand = (unsigned long long*)(ws + l.cand);
   p.slots = (double*)(ws + l.slots);
   p.Hls = (float*)(ws + l.hls);
+  p.V = (float*)(ws + l.v);
   p.RHS = (float*)(ws + l.rhs);
   p.Minv = Minv;
   void* args[] = {&p};
@@ -556,10 +577,13 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   const bool use_tc = precision == 1 && I >= 64 && R >= 32;
   if (use_tc) {
     const int tilesM = (I + tc::kTileM - 1) / tc::kTileM;
-    const int tcbn = ((long long)tilesM * ((R + 31) / 32) >= grid) ? 32 : 16;
+    const int tcbn = ((long long)tilesM * ((R + 63) / 64) >= grid) ? 64 : (((long long)tilesM * ((R + 31) / 32) >= grid) ? 32 : 16);
     if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
     if (int e = tc::make_operand_tmap(&p.tm_minv, Minv, R, R, l.Rp, tcbn)) return e;
-    if (tcbn == 32) {
+    if (tcbn == 64) {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, 64>;
+      smem = sizeof(LoopSmem<16, 32, 64>);
+    } else if (tcbn == 32) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, 32>;
       smem = sizeof(LoopSmem<16, 32, 32>);
     } else {

@@ -43,21 +43,22 @@ __device__ __forceinline__ void read_minmax(const ProjectHeader* hdr, float& tmi
 __global__ void __launch_bounds__(kThreads) k_mse_sums(const float* x, long long n, int bits, int Nc,
                                                       const ProjectHeader* hdr, unsigned long long* cand_sums,
                                                       float neg_zero) {
-  __shared__ SearchSmem sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SearchSmem& sm = *reinterpret_cast<SearchSmem*>(smem_raw);
   float tmin, tmax, absmax;
   read_minmax(hdr, tmin, tmax, absmax);
   if (!(absmax > 0.0f) || isinf(absmax)) return;  // all-zero / non-finite input: output is NaN (k_apply)
   const Levels L = make_levels(bits);
   const long long cs = chunk_size(n, gridDim.x);
   const long long e0 = min(n, (long long)blockIdx.x * cs), e1 = min(n, e0 + cs);
-  cta_candidate_sums([x](long long e) { return x[e]; }, e0, e1, absmax, Nc, L, (double)n, cand_sums, sm, neg_zero);
+  cta_candidate_sums(x, e0, e1, absmax, Nc, L, (double)n, cand_sums, sm, neg_zero);
 }
 
 __global__ void __launch_bounds__(kThreads) k_apply(const float* x, long long n, int bits, int scheme, int Nc,
                                                    const ProjectHeader* hdr, const unsigned long long* cand_sums,
                                                    const float* tmin_in, const float* tmax_in, float* xq,
                                                    int8_t* codes, float* info) {
-  __shared__ SearchSmem sm;
+  __shared__ BestSmem sm;
   float tmin, tmax, absmax;
   read_minmax(hdr, tmin, tmax, absmax);
   const Levels L = make_levels(bits);
@@ -136,7 +137,8 @@ extern "C" int admmq_project(const float* x, int64_t n, int bits, int qscheme, i
     // one chunk of >= 512 elements (4 groups of 8 per warp) per CTA, at most one CTA per SM
     const long long want = (n + 511) / 512;
     const int g = (int)std::max<long long>(1, std::min<long long>((long long)dp.sm_count, want));
-    k_mse_sums<<<g, kThreads, 0, stream>>>(x, n, bits, num_attempts, hdr, cand, -0.0f);
+    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mse_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem)));
+    k_mse_sums<<<g, kThreads, sizeof(SearchSmem), stream>>>(x, n, bits, num_attempts, hdr, cand, -0.0f);
   }
   k_apply<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, bits, qscheme, num_attempts, hdr, cand, tmin, tmax,
                                                             xq, codes, info);

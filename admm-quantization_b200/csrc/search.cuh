@@ -2,7 +2,7 @@
 // (quantize_tensor_mse, source/quantization.py:118-144), shared by the standalone
 // projection kernels (project.cu) and the persistent ADMM loop (admm_loop.cu).
 //
-// Work split: the CTA's elements are staged through shared memory; every warp walks its
+// Work split: the CTA's elements are staged through shared memory (cp.async, double buffered); every warp walks its
 // slice of the stage in aligned groups of 8 elements read as warp-wide broadcasts (2 x LDS.128),
 // and each LANE owns kCPL candidates (scale and 1/scale in registers, duplicated into both
 // halves of a packed f32x2 register) -> no per-candidate warp reduction.  One candidate
@@ -27,7 +27,7 @@ constexpr int kMaxCandidates = 1024;        // num_attempts limit (custom_benchm
 constexpr int kChunkAlign = 64;             // CTA chunks are multiples of this many elements
 
 struct SearchSmem {
-  __align__(16) float stage[kStage];
+  __align__(16) float stage[2][kStage];  // double buffered: cp.async fills one while the warps evaluate the other
   double red[kWarps * kCandPerPass];
   unsigned long long key[kWarps];
 };
@@ -99,17 +99,37 @@ __device__ __forceinline__ void eval_pair(f32x2 x, f32x2 s, f32x2 rc, const Leve
 }
 
 // Adds this CTA's share of sum_e (x_e - Q_c(x_e))^2 for every candidate c < Nc into
-// cand_sums[c] (fixed point, see numerics.cuh).  loadv(e) returns element e.
-template <class LoadV>
-__device__ void cta_candidate_sums(LoadV loadv, long long e0, long long e1, float absmax, int Nc,
-                                   const Levels L, double n_total, unsigned long long* cand_sums,
-                                   SearchSmem& sm, float opaque_neg_zero) {
+// cand_sums[c] (fixed point, see numerics.cuh).  The CTA's elements are v[e0 .. e1) (contiguous).
+__device__ inline void cta_candidate_sums(const float* __restrict__ v, long long e0, long long e1, float absmax, int Nc,
+                                          const Levels L, double n_total, unsigned long long* cand_sums,
+                                          SearchSmem& sm, float opaque_neg_zero) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (e0 >= e1) return;  // uniform per CTA
   const ClipGrid g = make_clip_grid(absmax, Nc);
   const double unit_inv = fixed_point_unit_inv(n_total, absmax);
   const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
   const f32x2 nzero = pack2(opaque_neg_zero, opaque_neg_zero);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(v + e0) & 15) == 0);  // e0 and kStage are multiples of 64
+  const int nstage = (int)((e1 - e0 + kStage - 1) / kStage);
+  // asynchronous fill of one stage buffer (16-byte copies when the source is aligned, 4-byte otherwise)
+  auto fill = [&](int st) {
+    const long long base = e0 + (long long)st * kStage;
+    const int cnt = (int)min((long long)kStage, e1 - base);
+    float* dst = sm.stage[st & 1];
+    if (vec_ok) {
+      for (int i = threadIdx.x * 4; i + 3 < cnt; i += kThreads * 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst + i)),
+                     "l"(v + base + i) : "memory");
+      for (int i = (cnt & ~3) + threadIdx.x; i < cnt; i += kThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(dst + i)),
+                     "l"(v + base + i) : "memory");
+    } else {
+      for (int i = threadIdx.x; i < cnt; i += kThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(dst + i)),
+                     "l"(v + base + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   for (int c0 = 0; c0 < Nc; c0 += kCandPerPass) {
     f32x2 sc[kCPL], rc[kCPL];
     double dacc[kCPL];
@@ -122,19 +142,28 @@ __device__ void cta_candidate_sums(LoadV loadv, long long e0, long long e1, floa
       rc[j] = pack2(r, r);
       dacc[j] = 0.0;
     }
-    for (long long base = e0; base < e1; base += kStage) {
+    __syncthreads();  // the previous pass / phase is done with both stage buffers
+    fill(0);
+    for (int st = 0; st < nstage; ++st) {
+      const long long base = e0 + (long long)st * kStage;
       const int cnt = (int)min((long long)kStage, e1 - base);
       const int cnt8 = (cnt + kGroup - 1) / kGroup * kGroup;  // zero padding contributes exactly 0
-      __syncthreads();
-      for (int i = threadIdx.x; i < cnt8; i += kThreads) sm.stage[i] = (i < cnt) ? loadv(base + i) : 0.0f;
+      float* stage = sm.stage[st & 1];
+      if (st + 1 < nstage) {
+        fill(st + 1);  // buffer (st+1)&1 was released by the barrier at the end of iteration st-1
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      if (threadIdx.x < cnt8 - cnt) stage[cnt + threadIdx.x] = 0.0f;
       __syncthreads();
       // warp slice, multiple of kGroup (base and e0 are multiples of kChunkAlign)
       int per = (cnt8 + kWarps - 1) / kWarps;
       per = (per + kGroup - 1) / kGroup * kGroup;
       const int wb = min(warp * per, cnt8), we = min(wb + per, cnt8);
       for (int gb = wb; gb < we; gb += kGroup) {
-        const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&sm.stage[gb]);
-        const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&sm.stage[gb + 4]);
+        const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&stage[gb]);
+        const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&stage[gb + 4]);
         const f32x2 xs[4] = {va.x, va.y, vb.x, vb.y};
         f32x2 acc[kCPL];
         float worst = 0.0f;
@@ -167,9 +196,9 @@ __device__ void cta_candidate_sums(LoadV loadv, long long e0, long long e1, floa
           dacc[j] += (double)add_rn(even, odd);
         }
       }
+      __syncthreads();  // everyone is done with this buffer: it may be refilled two stages from now
     }
     // fixed-order reduction over the CTA's warps, then one integer atomic per candidate
-    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kCPL; ++j) sm.red[warp * kCandPerPass + j * 32 + lane] = dacc[j];
     __syncthreads();
@@ -185,8 +214,12 @@ __device__ void cta_candidate_sums(LoadV loadv, long long e0, long long e1, floa
 
 // First index of the smallest MSE (torch.argmin, source/quantization.py:141), evaluated
 // redundantly by every CTA from the global fixed-point sums.  Returns the index to all threads.
+struct BestSmem {
+  unsigned long long key[kWarps];
+};
+template <class Smem>
 __device__ inline int cta_best_candidate(const unsigned long long* cand_sums, int Nc, float absmax,
-                                         double n_total, SearchSmem& sm) {
+                                         double n_total, Smem& sm) {
   const double unit = fixed_point_unit(n_total, absmax);
   const float nf = (float)n_total;
   unsigned long long best = ~0ull;

@@ -74,14 +74,18 @@ extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int
   if (int e = device_props(&dp)) return e;
   if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "admmq_gemm_nt needs an sm_100 device (tcgen05)");
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM;
-  // tile width: 32 unless 16 is needed to give every SM a tile
-  const int bn = ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count) ? 32 : 16;
+  // widest tile that still gives every SM one: a wider MMA costs the issuing thread the same ~28 cycles
+  const int bn = ((long long)tilesM * ((N + 63) / 64) >= dp.sm_count) ? 64
+                                                                       : ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count ? 32 : 16);
   const int tiles = tilesM * ((N + bn - 1) / bn);
   const int grid = std::min(tiles, dp.sm_count);
   GemmMaps maps;
   if (int e = tc::make_operand_tmap(&maps.a, A, M, K, lda, tc::kTileM)) return e;
   if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
-  if (false) {
+  if (bn == 64) {
+    const int smem = tc::TileSmem<64>::kBytes;
+    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_gemm_nt_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
   } else if (bn == 32) {
     const int smem = tc::TileSmem<32>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -40,18 +40,20 @@ constexpr int kAtomK = 32;       // floats per 128-byte swizzle row
 constexpr int kAtoms = 2;        // swizzle atoms along K per K-block
 constexpr int kBlockK = kAtomK * kAtoms;  // 64: halves the per-block synchronisation cost of a 32-deep block
 constexpr int kUmmaK = 8;        // k per tcgen05.mma.kind::tf32
-constexpr int kStages = 3;       // operand stages (hi/lo, swizzled)
+constexpr int kMaxStages = 3;    // operand stages (hi/lo, swizzled): 3 for BN <= 32, 2 for BN = 64 (TMEM budget)
 constexpr int kTileM = 128;
 
 constexpr int kRawDepth = 3;     // K-blocks of raw float32 in flight (TMA)
-constexpr int kAccStride = 32;   // TMEM columns between the three accumulators (BN <= 32)
-constexpr int kAccCols = 96;     // three accumulators: hi.hi at +0, hi.lo at +32, lo.hi at +64
 constexpr int kStageCols = 2 * kBlockK;  // TMEM columns of one A stage: hi [0, 64), lo [64, 128)
-constexpr int kTmemCols = 512;   // 96 + kStages x 128 = 480 -> next power of two
+constexpr int kTmemCols = 512;   // 3 accumulators + stages x 128: 96 + 3 x 128 = 480 (BN <= 32), 192 + 2 x 128 = 448 (BN = 64)
 
 template <int BN>
 struct TileSmem {
-  static_assert(BN == 16 || BN == 32, "BN must be 16 or 32");
+  static_assert(BN == 16 || BN == 32 || BN == 64, "BN must be 16, 32 or 64");
+  static constexpr int kStages = (BN == 64) ? 2 : 3;
+  static constexpr int kAccStride = (BN == 64) ? 64 : 32;        // TMEM columns between the three accumulators
+  static constexpr int kAccCols = 3 * kAccStride;                // hi.hi at +0, hi.lo at +stride, lo.hi at +2 stride
+  static_assert(kAccCols + kStages * kStageCols <= kTmemCols, "tensor memory budget");
   static constexpr int kAAtomBytes = kTileM * 128;               // one 32-deep atom of A as raw float32
   static constexpr int kBAtomBytes = BN * 128;
   static constexpr int kABytes = kAtoms * kAAtomBytes;           // one K-block of A
@@ -64,8 +66,8 @@ struct TileSmem {
 
 struct Pipe {  // lives in shared memory (static), one per CTA
   unsigned long long raw_full[kRawDepth];  // cp.async data of a K-block has landed (one arrival per thread)
-  unsigned long long stage_full[kStages];
-  unsigned long long stage_free[kStages];
+  unsigned long long stage_full[kMaxStages];
+  unsigned long long stage_free[kMaxStages];
   unsigned long long tile_done;
   unsigned int tmem_base;
   unsigned int pad;
@@ -73,7 +75,7 @@ struct Pipe {  // lives in shared memory (static), one per CTA
 
 struct PipeState {  // per-thread copy, uniform across the CTA
   unsigned int raw_uses[kRawDepth];  // how often each raw slot has been filled so far
-  unsigned int uses[kStages];  // how often each stage has been filled / consumed so far
+  unsigned int uses[kMaxStages];  // how often each stage has been filled / consumed so far
   unsigned int tiles;          // commits issued so far on tile_done
   unsigned long long nz2;      // (-0.0f, -0.0f) as a run-time value (see split2)
 #ifdef ADMMQ_TC_PROFILE
@@ -229,7 +231,7 @@ __device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, float neg_
   asm("mov.b64 %0, {%1, %1};" : "=l"(st.nz2) : "f"(neg_zero));
   if (threadIdx.x == 0) {
     for (int d = 0; d < kRawDepth; ++d) mbar_init(&pipe.raw_full[d], 1);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&pipe.stage_full[s], kThreadsTC / 32 - 1);
       mbar_init(&pipe.stage_free[s], 1);
     }
@@ -240,7 +242,7 @@ __device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, float neg_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  for (int s = 0; s < kStages; ++s) st.uses[s] = 0u;
+  for (int s = 0; s < kMaxStages; ++s) st.uses[s] = 0u;
   for (int d = 0; d < kRawDepth; ++d) st.raw_uses[d] = 0u;
   st.tiles = 0u;
 #ifdef ADMMQ_TC_PROFILE
@@ -279,8 +281,8 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const unsigned int tiles_base = (smem_u32(smem_tiles) + 1023u) & ~1023u;
   unsigned char* tiles_ptr = smem_tiles + (tiles_base - smem_u32(smem_tiles));
-  const unsigned int raw_base = tiles_base + (unsigned int)(kStages * TS::kStageBytes);
-  unsigned char* raw_ptr = tiles_ptr + (size_t)kStages * TS::kStageBytes;
+  const unsigned int raw_base = tiles_base + (unsigned int)(TS::kStages * TS::kStageBytes);
+  unsigned char* raw_ptr = tiles_ptr + (size_t)TS::kStages * TS::kStageBytes;
   const int nkb = (K + kBlockK - 1) / kBlockK;
   const unsigned int tmem = pipe.tmem_base;  // keep in a register: the asm memory clobbers would re-read it
 
@@ -304,12 +306,12 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
     }
     __syncwarp();
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kStages;
+      const int s = kb % TS::kStages;
       { TC_T0(); mbar_wait(&pipe.stage_full[s], st.uses[s] & 1u); TC_ACC(3); }
       st.uses[s] += 1u;
       tc_fence_after();
       TC_T0();
-      const unsigned int a_col = tmem + (unsigned int)(kAccCols + s * kStageCols);
+      const unsigned int a_col = tmem + (unsigned int)(TS::kAccCols + s * kStageCols);
       const unsigned int sb = tiles_base + (unsigned int)(s * TS::kStageBytes);
       const unsigned int first = kb != 0 ? 1u : 0u;
       unsigned long long* free_bar = &pipe.stage_free[s];
@@ -327,8 +329,8 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
             // three independent accumulators, added small terms first by the epilogue: besides shortening the
             // dependent chain this keeps the lo terms from being absorbed into the large hi.hi sums
             const unsigned int acc = (a | ks) != 0 ? 1u : first;
-            umma_tf32_ts(tmem + 2u * kAccStride, a_lo, b_hi + adv, idesc, acc);
-            umma_tf32_ts(tmem + 1u * kAccStride, a_hi, b_lo + adv, idesc, acc);
+            umma_tf32_ts(tmem + 2u * TS::kAccStride, a_lo, b_hi + adv, idesc, acc);
+            umma_tf32_ts(tmem + 1u * TS::kAccStride, a_hi, b_lo + adv, idesc, acc);
             umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
           }
         }
@@ -353,11 +355,11 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
     for (int kb = 0; kb < nkb; ++kb) {
       const int d = kb % kRawDepth;
       { TC_T0(); mbar_wait(&pipe.raw_full[d], (st.raw_uses[d] + (unsigned int)(kb / kRawDepth)) & 1u); TC_ACC(0); }  // K-block kb has landed
-      const int s = kb % kStages;
+      const int s = kb % TS::kStages;
       { TC_T0(); if (st.uses[s] > 0u) { mbar_wait(&pipe.stage_free[s], (st.uses[s] - 1u) & 1u); tc_fence_after(); } TC_ACC(1); }
       TC_T0();
       const unsigned char* raw = raw_ptr + (size_t)d * TS::kRawBytes;
-      const unsigned int col0 = lane_addr + (unsigned int)(kAccCols + s * kStageCols);
+      const unsigned int col0 = lane_addr + (unsigned int)(TS::kAccCols + s * kStageCols);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         if (i < c_count) {
@@ -427,8 +429,8 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
   const unsigned int taddr = pipe.tmem_base + ((unsigned int)(q * 32) << 16) + (unsigned int)col0;
   unsigned int hh[BN / 4], hl[BN / 4], lh[BN / 4];
   tmem_load<BN / 4>(taddr, hh);
-  tmem_load<BN / 4>(taddr + 1u * kAccStride, hl);
-  tmem_load<BN / 4>(taddr + 2u * kAccStride, lh);
+  tmem_load<BN / 4>(taddr + 1u * TileSmem<BN>::kAccStride, hl);
+  tmem_load<BN / 4>(taddr + 2u * TileSmem<BN>::kAccStride, lh);
 #pragma unroll
   for (int i = 0; i < BN / 4; ++i) v[i] = (__uint_as_float(lh[i]) + __uint_as_float(hl[i])) + __uint_as_float(hh[i]);
 }

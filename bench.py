@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-budget-s", type=float, default=15.0, help="CPU seconds for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mttkrp-precision", type=int, default=0)
+    ap.add_argument("--mttkrp-precision", type=int, default=1,
+                    help="0 = float64-accumulating CUDA-core MTTKRP, 1 = 3xTF32 tcgen05 MTTKRP (default)")
     ap.add_argument("--concurrency", default="prop", choices=["off", "prop"],
                     help="off: layers run one after the other on every SM; prop: every layer gets a share of the SMs "
                          "proportional to its cost and all layers run concurrently on their own streams")
@@ -358,11 +359,14 @@ def run_native(args):
     total_ms = float(total_ms.item())
     value = world * inner_per_step * args.steps / (total_ms / 1e3)
 
-    # ---- the dominant kernel (persistent ADMM loop), timed with CUDA events on its own stream
-    loop_ms, per_layer = 0.0, {}
+    # ---- the dominant kernel (persistent ADMM loop), timed with CUDA events on its own stream.  In concurrent mode a
+    # launch holds only its share g of the SMs, so its duration is weighted by g / SMs: the sum is the time the whole
+    # GPU would have been busy with these launches (equals the plain sum when every launch uses every SM).
+    loop_ms, loop_gpu_ms, per_layer = 0.0, 0.0, {}
     for (name, _, _, _), s in zip(problems, solvers):
         ms = sum(a.elapsed_time(b) for _, a, b in s.loop_events)
         loop_ms += ms
+        loop_gpu_ms += ms * ((s.max_ctas or sm_count) / sm_count)
         per_layer[name] = round(s.inner_iterations_per_sweep() * args.steps / (ms / 1e3), 1)
     n_loop = sum(len(s.loop_events) for s in solvers)
     alg_bytes = sum(s.loop_algorithmic_bytes_per_sweep() for s in solvers) * args.steps
@@ -373,21 +377,28 @@ def run_native(args):
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))
+    except OSError:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (loop_ms / 1e3) / 1e9
+    achieved = alg_bytes / (loop_gpu_ms / 1e3) / 1e9
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    alu_peak = 148 * 128 * sm_max * 1e6   # fp32 lane-instructions / s
+    fma_lane_peak = sm_count * 128 * sm_max * 1e6          # FP32 lane-ops / s on the FMA pipe (measured: tools/microbench)
+    eval_peak = sm_count * 18.3 * sm_max * 1e6             # packed evaluation: 7 FMA-pipe + 2.5 ALU lane-ops
     roofline = {"kernel": "k_admm_loop (persistent ADMM inner loop)", "bound": "hbm", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None, "launches": n_loop, "avg_launch_ms": loop_ms / max(n_loop, 1),
-                "share_of_step": loop_ms / sum(step_ms),
+                "traffic": traffic, "launches": n_loop, "avg_launch_ms": loop_ms / max(n_loop, 1),
+                "gpu_share_weighted_ms": loop_gpu_ms, "share_of_step": loop_gpu_ms / sum(step_ms),
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_loop, 1),
-                "note": "state is L2-resident by design, so HBM is not the binding resource; the kernel is fp32-ALU bound "
-                        "(200 clip candidates per element per iteration), see 'alu'",
-                "alu": {"candidate_evals_per_s": evals / (loop_ms / 1e3), "fp32_lane_instr_peak_per_s": alu_peak,
-                        "evals_per_lane_cycle": evals / (loop_ms / 1e3) / alu_peak,
-                        "solve_tflops_fp32": flops / (loop_ms / 1e3) / 1e12}}
+                "note": "state is L2-resident by design, so HBM is not the binding resource; the kernel is bound by the FP32 "
+                        "pipes (200 clip candidates per element per iteration), see 'alu'",
+                "alu": {"candidate_evals_per_s": evals / (loop_gpu_ms / 1e3), "candidate_evals_per_s_pipe_bound": eval_peak,
+                        "frac_of_pipe_bound": evals / (loop_gpu_ms / 1e3) / eval_peak,
+                        "fp32_fma_pipe_lane_ops_per_s": fma_lane_peak,
+                        "ridge_product_tflops_fp32_equiv": flops / (loop_gpu_ms / 1e3) / 1e12}}
 
     # ---- end to end through the public API with host buffers
     e2e = None
