@@ -82,8 +82,9 @@ ADMMQ_HD Levels make_levels(int bits) {
   L.fast_lo = -q - 0.25f;
   L.fast_hi = q - 0.75f;
   // |x*rcp(s) - x/s| <= |t| * 2^-23 (two roundings) and |fl(x/s) - x/s| <= |t| * 2^-24;
-  // q * 2^-21 leaves a >2.5x margin for |t| <= q + 0.25.
-  L.fast_thr = 0.5f - q * 4.76837158203125e-07f;
+  // (q + 2) * 2^-21 leaves a >2.5x margin for every quotient |t| <= q + 1.5 whose rounding can matter (larger ones
+  // clamp to the same code either way).
+  L.fast_thr = 0.5f - (q + 2.0f) * 4.76837158203125e-07f;
   return L;
 }
 
@@ -141,6 +142,17 @@ ADMMQ_HD float dev_fast(float x, float scale, float rcp_scale, const Levels& L, 
   frac = fabsf(sub_rn(t, k));
   return sub_rn(x, mul_rn(k, scale));
 }
+// An alternative form (not used by the kernels, see search.cuh eval_pair; kept pinned by the host tests): round the EXACT product x * rcp_scale (one FMA with the magic
+// constant), take its rounding residual r with a second FMA, clamp the integer afterwards.  rint(x / scale) can differ
+// from the rounded product only when the quotient lies within |x/s| * 2^-23 of a half integer, and only matters while
+// the integer is inside [-q - 1, q]; |r| <= fast_thr = 0.5 - q * 2^-21 excludes both, everything else is redone exactly.
+ADMMQ_HD float dev_fast2(float x, float scale, float rcp_scale, const Levels& L, float& frac) {
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23
+  const float ku = sub_rn(fma_rn(x, rcp_scale, MAGIC), MAGIC);
+  frac = fabsf(fma_rn(x, rcp_scale, -ku));
+  const float k = fminf(fmaxf(ku, L.lo), L.hi);
+  return sub_rn(x, mul_rn(k, scale));
+}
 ADMMQ_HD float sqerr_fast(float x, float scale, float rcp_scale, const Levels& L, float& frac) {
   const float d = dev_fast(x, scale, rcp_scale, L, frac);
   return mul_rn(d, d);
@@ -154,8 +166,14 @@ ADMMQ_HD float sqerr_fast(float x, float scale, float rcp_scale, const Levels& L
 //     which contributes exactly 0;
 //   * within a group two float32 FMA chains accumulate d*d, one over the even and one over the odd
 //     positions (the two lanes of a packed f32x2 FMA), and are added in float32;
-//   * group sums are added in float64 in element order, the CTA/chunk totals in 64-bit fixed point.
+//   * the 8 group sums of an aligned block of 64 elements (kSumBlock) are added in float32 in order (the float32 ->
+//     float64 conversion runs on the quarter-rate conversion pipe: once per 64 elements instead of once per 8 it
+//     costs ~2 % instead of ~14 % of the search);
+//   * block sums are added in float64 in element order, the CTA/chunk totals in 64-bit fixed point.
+// Blocks are aligned to the ABSOLUTE element index (chunk starts, stage sizes and warp slices are multiples of 64), so
+// the result does not depend on the grid size or on how the elements are split over CTAs and warps.
 constexpr int kSumGroup = 8;
+constexpr int kSumBlock = 64;
 ADMMQ_HD float group_sum8(const float d[kSumGroup]) {
   float even = 0.0f, odd = 0.0f;
   for (int i = 0; i < kSumGroup; i += 2) {

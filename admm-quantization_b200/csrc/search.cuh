@@ -8,7 +8,7 @@
 // halves of a packed f32x2 register) -> no per-candidate warp reduction.  One candidate
 // evaluation is ~6 issue slots: the multiplies/adds run as packed FFMA2/FADD2/FMUL2 on two
 // elements at a time, only the clamp (FMNMX) and the boundary check (FMNMX3) are scalar.
-// Group sums follow the group_sum8 recipe of numerics.cuh, go into float64 per lane, and the
+// Group sums follow the group_sum8 / 64-element block recipe of numerics.cuh, go into float64 per lane, and the
 // CTA total is converted to fixed point and added to the global per-candidate accumulators
 // with integer atomics (order independent => deterministic for any grid size).
 #pragma once
@@ -82,6 +82,9 @@ __host__ __device__ inline long long chunk_size(long long n, int ctas) {
 // One candidate (scale s, 1/s duplicated in both halves) on two elements x = (x0, x1):
 // acc += d*d per half with d = x - k*s, k = clamp(rint(x/s)) via the reciprocal + magic-number
 // shortcut (numerics.cuh dev_fast); `worst` collects the distance of the quotient from its rounded value.
+// 7 FMA-pipe (FMUL2, 4 x FADD2, 2 x FFMA2) + 2.5 ALU-pipe instructions per two evaluations.  (A 6-instruction variant
+// that rounds the product with an FMA and takes the residual with a second FMA measured 13 % SLOWER on B200: four
+// three-operand FFMA2 per pair lose more to register-bank conflicts than the saved FADD2 gains.)
 __device__ __forceinline__ void eval_pair(f32x2 x, f32x2 s, f32x2 rc, const Levels& L, f32x2 magic, f32x2 nmagic,
                                           f32x2 nzero, f32x2& acc, float& worst) {
   const f32x2 t = mul2(x, rc);
@@ -132,7 +135,10 @@ __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long
   };
   for (int c0 = 0; c0 < Nc; c0 += kCandPerPass) {
     f32x2 sc[kCPL], rc[kCPL];
-    double dacc[kCPL];
+    // per-lane float64 accumulators live in shared memory (sm.red[warp][candidate slot]): they are touched once per
+    // 64-element block, and keeping them out of the register file keeps the 512-thread CTA under 128 registers
+    double* dacc = &sm.red[warp * kCandPerPass + lane];
+    __syncthreads();  // the previous pass / phase is done with both stage buffers and with sm.red
 #pragma unroll
     for (int j = 0; j < kCPL; ++j) {
       const int c = c0 + j * 32 + lane;
@@ -140,9 +146,8 @@ __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long
       const float r = (c < Nc) ? div_rn(1.0f, s) : 0.0f;
       sc[j] = pack2(s, s);
       rc[j] = pack2(r, r);
-      dacc[j] = 0.0;
+      dacc[j * 32] = 0.0;
     }
-    __syncthreads();  // the previous pass / phase is done with both stage buffers
     fill(0);
     for (int st = 0; st < nstage; ++st) {
       const long long base = e0 + (long long)st * kStage;
@@ -157,10 +162,13 @@ __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long
       }
       if (threadIdx.x < cnt8 - cnt) stage[cnt + threadIdx.x] = 0.0f;
       __syncthreads();
-      // warp slice, multiple of kGroup (base and e0 are multiples of kChunkAlign)
+      // warp slice, multiple of kSumBlock (base and e0 are multiples of kChunkAlign = kSumBlock)
       int per = (cnt8 + kWarps - 1) / kWarps;
-      per = (per + kGroup - 1) / kGroup * kGroup;
+      per = (per + kSumBlock - 1) / kSumBlock * kSumBlock;
       const int wb = min(warp * per, cnt8), we = min(wb + per, cnt8);
+      float bacc[kCPL];
+#pragma unroll
+      for (int j = 0; j < kCPL; ++j) bacc[j] = 0.0f;
       for (int gb = wb; gb < we; gb += kGroup) {
         const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&stage[gb]);
         const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&stage[gb + 4]);
@@ -193,15 +201,19 @@ __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long
         for (int j = 0; j < kCPL; ++j) {
           float even, odd;
           unpack2(acc[j], even, odd);
-          dacc[j] += (double)add_rn(even, odd);
+          bacc[j] = add_rn(bacc[j], add_rn(even, odd));
+        }
+        if (((gb + kGroup) & (kSumBlock - 1)) == 0 || gb + kGroup >= we) {  // end of an aligned 64-element block
+#pragma unroll
+          for (int j = 0; j < kCPL; ++j) {
+            dacc[j * 32] += (double)bacc[j];
+            bacc[j] = 0.0f;
+          }
         }
       }
       __syncthreads();  // everyone is done with this buffer: it may be refilled two stages from now
     }
-    // fixed-order reduction over the CTA's warps, then one integer atomic per candidate
-#pragma unroll
-    for (int j = 0; j < kCPL; ++j) sm.red[warp * kCandPerPass + j * 32 + lane] = dacc[j];
-    __syncthreads();
+    // fixed-order reduction over the CTA's warps (the last stage ended with a barrier), one integer atomic per candidate
     if (threadIdx.x < kCandPerPass && c0 + (int)threadIdx.x < Nc) {
       double tot = 0.0;
 #pragma unroll

@@ -21,7 +21,8 @@ void hc_candidates(float absmax, int n, int bits, float* clip, float* scale) {
 }
 
 // per-candidate MSE exactly as the kernels form it: fast path with exact fallback per group of 8,
-// the group_sum8 recipe of numerics.cuh, float64 across groups, fixed point, float32 mean.
+// the group_sum8 recipe of numerics.cuh, float32 over the 8 groups of a 64-element block, float64 across blocks,
+// fixed point, float32 mean.
 // Returns the number of groups that needed the exact-division fallback.
 long long hc_mse(const float* x, long long n, float absmax, int bits, int nc, float* mse, int* best, int force_exact) {
   const Levels L = make_levels(bits);
@@ -33,6 +34,7 @@ long long hc_mse(const float* x, long long n, float absmax, int bits, int nc, fl
     const float s = scale_of(clip_candidate(g, c), L);
     const float r = div_rn(1.0f, s);
     double tot = 0.0;
+    float block = 0.0f;
     for (long long b = 0; b < n; b += kSumGroup) {
       float d[kSumGroup];
       float worst = 0.0f;
@@ -46,7 +48,11 @@ long long hc_mse(const float* x, long long n, float absmax, int bits, int nc, fl
         for (int i = 0; i < kSumGroup; ++i) d[i] = dev_exact((b + i < n) ? x[b + i] : 0.0f, s, L);
         ++slow;
       }
-      tot += (double)group_sum8(d);
+      block = add_rn(block, group_sum8(d));
+      if ((b + kSumGroup) % kSumBlock == 0 || b + kSumGroup >= n) {
+        tot += (double)block;
+        block = 0.0f;
+      }
     }
     const long long fx = llrint(tot * unit_inv);
     mse[c] = mse_from_fixed(fx, unit, (float)n);
@@ -65,6 +71,9 @@ long long hc_fastpath_violations(const float* x, long long n, float scale, int b
     float frac;
     const float f = sqerr_fast(x[i], scale, r, L, frac);
     if (frac <= L.fast_thr && f != sqerr_exact(x[i], scale, L)) ++bad;
+    float frac2;
+    const float d2 = dev_fast2(x[i], scale, r, L, frac2);
+    if (frac2 <= L.fast_thr && d2 != dev_exact(x[i], scale, L)) ++bad;
   }
   return bad;
 }
