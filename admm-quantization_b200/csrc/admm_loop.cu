@@ -327,11 +327,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
       degenerate = !(absmax > 0.0f) || isinf(absmax);
       if (!degenerate) {
         unsigned long long* cand = p.cand + (size_t)slot * kMaxCandidates;
-        cta_candidate_sums(p.V, e0, e1, absmax, p.Nc, L, (double)N, cand, sm.search, p.neg_zero);
+        cta_candidate_sums(p.V, e0, e1, absmax, p.Nc, L, p.bits, (double)N, cand, sm.search, p.neg_zero);
         bar.sync();
         lap(1);
         // ---------------- P3
-        rep.best_index = cta_best_candidate(cand, p.Nc, absmax, (double)N, sm.search);
+        rep.best_index = cta_best_candidate(cand, p.Nc, absmax, (double)N, sm.search.direct);
         qp.scale = scale_of(clip_candidate(make_clip_grid(absmax, p.Nc), rep.best_index), L);
       }
     } else {
@@ -577,7 +577,20 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   const bool use_tc = precision == 1 && I >= 64 && R >= 32;
   if (use_tc) {
     const int tilesM = (I + tc::kTileM - 1) / tc::kTileM;
-    const int tcbn = ((long long)tilesM * ((R + 63) / 64) >= grid) ? 64 : (((long long)tilesM * ((R + 31) / 32) >= grid) ? 32 : 16);
+    // tile width: the cost of a tile is dominated by staging its 128 rows of A (independent of the width) plus the
+    // BN rows of B, so minimise waves * (128 + BN); ties go to the wider tile
+    int tcbn = 64;
+    {
+      long long best = -1;
+      for (int bn = 64; bn >= 16; bn >>= 1) {
+        const long long tiles = (long long)tilesM * ((R + bn - 1) / bn);
+        const long long cost = ((tiles + grid - 1) / grid) * (128 + bn);
+        if (best < 0 || cost < best) {
+          best = cost;
+          tcbn = bn;
+        }
+      }
+    }
     if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
     if (int e = tc::make_operand_tmap(&p.tm_minv, Minv, R, R, l.Rp, tcbn)) return e;
     if (tcbn == 64) {

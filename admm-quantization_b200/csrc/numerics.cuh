@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define ADMMQ_HD __host__ __device__ __forceinline__
@@ -201,6 +202,112 @@ ADMMQ_HD double fixed_point_unit(double n_elems, float absmax) {
 ADMMQ_HD float mse_from_fixed(long long fixed_sum, double unit, float n_elems_f) {
   const float total = (float)((double)fixed_sum * unit);
   return div_rn(total, n_elems_f);
+}
+
+// --- the threshold ("binned") form of the clip search ----------------------------------------
+// For one candidate scale s the quantizer k(x) = clamp(rint(x / s), -q, q-1) is a monotone step function of x, so
+// it is fully described by its 2q-1 thresholds: theta_j = the SMALLEST float32 x with rint(fl(x / s)) >= -q + j + 1
+// (found by stepping through neighbouring floats with the exact division, so ties-to-even and the rounding of the
+// quotient are captured exactly).  With C_j = #{x < theta_j}, P_j = sum{x < theta_j} x, the grid values
+// y_j = fl32((-q + j) * s) (source/quantization.py:127 rounds `codes * scale` to float32) and summation by parts,
+//     sum_e (x_e - y_k(e))^2 = sum_e x_e^2 + sum_{j=0}^{2q-2} [ C_j (y_j^2 - y_{j+1}^2) - 2 P_j (y_j - y_{j+1}) ]
+//                                           + n y_top^2 - 2 P_tot y_top,
+// which needs C and P at (2q-1) * num_attempts thresholds instead of num_attempts evaluations per element.  C is an
+// integer, P is accumulated in 64-bit fixed point (x rounded to 2^-41 of the power of two above absmax), the bracket is
+// evaluated in float64 and converted to the fixed-point unit of the per-candidate accumulators, so the result is
+// independent of grid size, chunking and arrival order.  It is the exact real-number value of the reference's
+// sum((x - xq)**2) up to ~1e-12 relative; the reference's own float32 evaluation of that sum carries ~1e-7.
+ADMMQ_HD unsigned int f32_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  unsigned int u;
+  std::memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+ADMMQ_HD float bits_f32(unsigned int u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+// order-preserving map float -> uint32 (larger float <=> larger key); NaN maps above +inf
+ADMMQ_HD unsigned int ordered_key(float f) {
+  const unsigned int b = f32_bits(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+ADMMQ_HD float ordered_float(unsigned int k) { return bits_f32((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// smallest float32 x with rint(fl(x / scale)) >= level + 1   (level = -q .. q-2)
+ADMMQ_HD float code_threshold(float scale, float level) {
+  const float target = level + 1.0f;
+  unsigned int key = ordered_key(mul_rn(level + 0.5f, scale));
+  if (rint_rn(div_rn(ordered_float(key), scale)) >= target) {
+    for (int it = 0; it < 64 && rint_rn(div_rn(ordered_float(key - 1u), scale)) >= target; ++it) --key;
+  } else {
+    for (int it = 0; it < 64; ++it) {
+      ++key;
+      if (rint_rn(div_rn(ordered_float(key), scale)) >= target) break;
+    }
+  }
+  return ordered_float(key);
+}
+
+// 64-bit fixed point of the elements: unit = 2^-41 of the power of two above absmax.  The threshold form is used for
+// absmax in [2^-40, 2^40] (float32 squares neither overflow nor vanish); outside, the kernels fall back to the direct
+// per-element evaluation.
+struct FixX {
+  float p2a;     // 2^a with 2^20 <= absmax * 2^a < 2^21
+  double unit;   // value of one fixed-point step = 2^-(a + 20)
+};
+constexpr float kBinnedMinAbs = 9.094947017729282e-13f;  // 2^-40
+constexpr float kBinnedMaxAbs = 1099511627776.0f;        // 2^40
+ADMMQ_HD bool binned_range_ok(float absmax) { return absmax >= kBinnedMinAbs && absmax <= kBinnedMaxAbs; }
+ADMMQ_HD FixX make_fix_x(float absmax) {
+  const int e = (int)((f32_bits(absmax) >> 23) & 0xffu) - 127;  // absmax = 1.m * 2^e
+  FixX f;
+  f.p2a = bits_f32((unsigned int)(20 - e + 127) << 23);
+  // 2^-(a + 20) = 2^(e - 40) as a double
+  unsigned long long db = (unsigned long long)(e - 40 + 1023) << 52;
+#if defined(__CUDA_ARCH__)
+  f.unit = __longlong_as_double((long long)db);
+#else
+  std::memcpy(&f.unit, &db, 8);
+#endif
+  return f;
+}
+// x -> rne(x * 2^(a + 20)) without the conversion pipe: two magic-number roundings (|x * 2^a| < 2^21)
+ADMMQ_HD long long fix_x(float x, const FixX& f) {
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23, bits 0x4B400000
+  const float xs = mul_rn(x, f.p2a);                 // exact (power of two)
+  const float hb = add_rn(xs, MAGIC);                // integer part (rne) in the low mantissa bits
+  const float r = sub_rn(xs, sub_rn(hb, MAGIC));     // exact, |r| <= 0.5
+  const float lb = fma_rn(r, 1048576.0f, MAGIC);     // rne(r * 2^20)
+  const long long th = (long long)((int)f32_bits(hb) - 0x4B400000);
+  const long long tl = (long long)((int)f32_bits(lb) - 0x4B400000);
+  return th * 1048576ll + tl;
+}
+
+// sum of squares of four consecutive elements as the kernels form it (float32 FMA chain, then float64)
+ADMMQ_HD float sumsq4(float a, float b, float c, float d) {
+  return fma_rn(d, d, fma_rn(c, c, fma_rn(b, b, mul_rn(a, a))));
+}
+
+// contribution of threshold j of one candidate to the per-candidate sum, in float64:
+//   C (y_lo^2 - y_hi^2) - 2 P unit (y_lo - y_hi),   y_lo = fl32(level * s), y_hi = fl32((level + 1) * s)
+ADMMQ_HD double threshold_term(float scale, float level, long long count, long long psum, double xunit) {
+  const double ylo = (double)mul_rn(level, scale), yhi = (double)mul_rn(level + 1.0f, scale);
+  const double d1 = ylo - yhi;
+  return (double)count * (d1 * (ylo + yhi)) - 2.0 * ((double)psum * xunit) * d1;
+}
+// closing term n y_top^2 - 2 P_tot unit y_top, y_top = fl32((q - 1) * s)
+ADMMQ_HD double closing_term(float scale, float top_level, long long n, long long ptot, double xunit) {
+  const double y = (double)mul_rn(top_level, scale);
+  return (double)n * (y * y) - 2.0 * ((double)ptot * xunit) * y;
 }
 
 // --- the other tensor_* schemes ---------------------------------------------------------

@@ -26,10 +26,31 @@ constexpr int kGroup = kSumGroup;           // accumulation group (aligned, see 
 constexpr int kMaxCandidates = 1024;        // num_attempts limit (custom_benchmark.py uses 1000)
 constexpr int kChunkAlign = 64;             // CTA chunks are multiples of this many elements
 
-struct SearchSmem {
+struct DirectSmem {
   __align__(16) float stage[2][kStage];  // double buffered: cp.async fills one while the warps evaluate the other
   double red[kWarps * kCandPerPass];
   unsigned long long key[kWarps];
+};
+
+// threshold ("binned") form of the search, see numerics.cuh
+constexpr int kBins = 8192;        // linear bins over [-absmax, absmax]
+constexpr int kStageCap = 20480;   // elements sorted by bin in shared memory at a time (40 per thread)
+constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
+struct BinnedSmem {
+  __align__(16) float sorted[kStageCap];   // the stage's elements grouped by bin
+  __align__(16) unsigned int cnt[kBins];   // per-bin counts -> start offsets -> end offsets
+  __align__(16) unsigned int slo[kBins];   // per-bin fixed-point sums (low / high word) -> exclusive prefix sums
+  __align__(16) unsigned int shi[kBins];
+  unsigned long long acc[kMaxCandidates];  // per-candidate fixed-point totals of this CTA
+  float scale[kMaxCandidates];
+  unsigned long long wsum[kWarps];
+  unsigned int wcnt[kWarps];
+  double red[kWarps];
+};
+
+union SearchSmem {
+  DirectSmem direct;
+  BinnedSmem binned;
 };
 
 // ---- packed pairs of float32 (two independent IEEE round-to-nearest operations per instruction).
@@ -103,9 +124,9 @@ __device__ __forceinline__ void eval_pair(f32x2 x, f32x2 s, f32x2 rc, const Leve
 
 // Adds this CTA's share of sum_e (x_e - Q_c(x_e))^2 for every candidate c < Nc into
 // cand_sums[c] (fixed point, see numerics.cuh).  The CTA's elements are v[e0 .. e1) (contiguous).
-__device__ inline void cta_candidate_sums(const float* __restrict__ v, long long e0, long long e1, float absmax, int Nc,
-                                          const Levels L, double n_total, unsigned long long* cand_sums,
-                                          SearchSmem& sm, float opaque_neg_zero) {
+__device__ inline void cta_candidate_sums_direct(const float* __restrict__ v, long long e0, long long e1, float absmax,
+                                                 int Nc, const Levels L, double n_total, unsigned long long* cand_sums,
+                                                 DirectSmem& sm, float opaque_neg_zero) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (e0 >= e1) return;  // uniform per CTA
   const ClipGrid g = make_clip_grid(absmax, Nc);
@@ -222,6 +243,242 @@ __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long
       atomicAdd(cand_sums + c0 + threadIdx.x, (unsigned long long)fx);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Threshold form (numerics.cuh): per stage of <= kStageCap elements
+//   pass 1  histogram over kBins linear bins: count + 64-bit fixed-point sum per bin (shared-memory atomics; the 64-bit
+//           sum as two 32-bit atomics with carry), sum of squares in float64
+//   scan    exclusive prefix over the bins
+//   pass 2  counting-sort scatter of the elements into `sorted` (grouped by bin)
+//   pass 3  one (candidate, threshold) pair per thread: exact threshold, its bin, prefix + the bin's elements compared
+//           one by one -> C, P -> float64 term -> fixed point -> per-candidate shared accumulator
+// bin(x) is monotone in x, so every element in a lower bin is below the threshold and every element in a higher bin
+// is not; only the threshold's own bin (kStageCap / kBins = 5 elements on average) is inspected.
+__device__ __forceinline__ int bin_of(float x, float bmul) {
+  const float t = fma_rn(x, bmul, 12582912.0f + (float)(kBins / 2));  // rne(x * bmul) + kBins / 2 in the low mantissa bits
+  const int b = (int)__float_as_uint(t) - 0x4B400000;
+  return min(max(b, 0), kBins - 1);
+}
+
+__device__ __forceinline__ float4 load_group4(const float* __restrict__ p, int gi, int ngroups, int cnt, bool vec_ok) {
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gi < ngroups) {
+    const int i = gi * 4;
+    if (vec_ok && i + 3 < cnt) {
+      x = __ldcg(reinterpret_cast<const float4*>(p + i));
+    } else {
+      x.x = __ldcg(p + i);
+      if (i + 1 < cnt) x.y = __ldcg(p + i + 1);
+      if (i + 2 < cnt) x.z = __ldcg(p + i + 2);
+      if (i + 3 < cnt) x.w = __ldcg(p + i + 3);
+    }
+  }
+  return x;
+}
+
+__device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, long long e0, long long e1, float absmax,
+                                                 int Nc, const Levels L, int bits, double n_total,
+                                                 unsigned long long* cand_sums, BinnedSmem& sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (e0 >= e1) return;  // uniform per CTA
+  const ClipGrid g = make_clip_grid(absmax, Nc);
+  const double unit_inv = fixed_point_unit_inv(n_total, absmax);
+  const FixX fx = make_fix_x(absmax);
+  const float bmul = div_rn((float)(kBins / 2), absmax);
+  const int nthr = (1 << bits) - 1;  // thresholds per candidate
+  const int npairs = Nc * nthr;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(v + e0) & 15) == 0);
+  __syncthreads();  // the previous phase is done with the shared memory
+  for (int c = tid; c < Nc; c += kThreads) {
+    sm.scale[c] = scale_of(clip_candidate(g, c), L);
+    sm.acc[c] = 0ull;
+  }
+  double x2 = 0.0;
+  for (long long base = e0; base < e1; base += kStageCap) {
+    const int cnt = (int)min((long long)kStageCap, e1 - base);
+    const int ngroups = (cnt + 3) >> 2;
+    const float* __restrict__ src = v + base;
+    for (int b = tid * 4; b < kBins; b += kThreads * 4) {
+      *reinterpret_cast<uint4*>(&sm.cnt[b]) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(&sm.slo[b]) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(&sm.shi[b]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    // ---- pass 1: histogram
+    for (int g0 = tid; g0 < ngroups; g0 += kThreads * kLoadBatch) {
+      float4 xs[kLoadBatch];
+#pragma unroll
+      for (int u = 0; u < kLoadBatch; ++u) xs[u] = load_group4(src, g0 + u * kThreads, ngroups, cnt, vec_ok);
+#pragma unroll
+      for (int u = 0; u < kLoadBatch; ++u) {
+        const int gi = g0 + u * kThreads;
+        if (gi < ngroups) {
+          const float xe[4] = {xs[u].x, xs[u].y, xs[u].z, xs[u].w};
+          const int nv = min(4, cnt - gi * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < nv) {
+              const int b = bin_of(xe[q], bmul);
+              atomicAdd(&sm.cnt[b], 1u);
+              const long long f = fix_x(xe[q], fx);
+              const unsigned int lo = (unsigned int)f, hi = (unsigned int)((unsigned long long)f >> 32);
+              const unsigned int old = atomicAdd(&sm.slo[b], lo);
+              atomicAdd(&sm.shi[b], hi + ((old + lo < old) ? 1u : 0u));
+              const double xd = (double)xe[q];
+              x2 = fma(xd, xd, x2);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- exclusive scan over the bins: thread t owns kBins / kThreads consecutive bins
+    {
+      constexpr int kPer = kBins / kThreads;
+      static_assert(kPer % 4 == 0 && kPer * kThreads == kBins, "bins per thread");
+      const int b0 = tid * kPer;
+      unsigned int c[kPer], lo[kPer], hi[kPer];
+#pragma unroll
+      for (int i = 0; i < kPer; i += 4) {
+        *reinterpret_cast<uint4*>(&c[i]) = *reinterpret_cast<const uint4*>(&sm.cnt[b0 + i]);
+        *reinterpret_cast<uint4*>(&lo[i]) = *reinterpret_cast<const uint4*>(&sm.slo[b0 + i]);
+        *reinterpret_cast<uint4*>(&hi[i]) = *reinterpret_cast<const uint4*>(&sm.shi[b0 + i]);
+      }
+      unsigned int ct = 0u;
+      unsigned long long st = 0ull;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        ct += c[i];
+        st += ((unsigned long long)hi[i] << 32) | lo[i];
+      }
+      unsigned int ci = ct;
+      unsigned long long si = st;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int nc = __shfl_up_sync(0xffffffffu, ci, o);
+        const unsigned long long ns = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) {
+          ci += nc;
+          si += ns;
+        }
+      }
+      if (lane == 31) {
+        sm.wcnt[warp] = ci;
+        sm.wsum[warp] = si;
+      }
+      __syncthreads();
+      unsigned int rc = ci - ct;
+      unsigned long long rs = si - st;
+      for (int w = 0; w < warp; ++w) {
+        rc += sm.wcnt[w];
+        rs += sm.wsum[w];
+      }
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const unsigned int cc = c[i];
+        const unsigned long long ss = ((unsigned long long)hi[i] << 32) | lo[i];
+        c[i] = rc;
+        lo[i] = (unsigned int)rs;
+        hi[i] = (unsigned int)(rs >> 32);
+        rc += cc;
+        rs += ss;
+      }
+#pragma unroll
+      for (int i = 0; i < kPer; i += 4) {
+        *reinterpret_cast<uint4*>(&sm.cnt[b0 + i]) = *reinterpret_cast<const uint4*>(&c[i]);
+        *reinterpret_cast<uint4*>(&sm.slo[b0 + i]) = *reinterpret_cast<const uint4*>(&lo[i]);
+        *reinterpret_cast<uint4*>(&sm.shi[b0 + i]) = *reinterpret_cast<const uint4*>(&hi[i]);
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: scatter (cnt[b] runs from the start to the end of bin b)
+    for (int g0 = tid; g0 < ngroups; g0 += kThreads * kLoadBatch) {
+      float4 xs[kLoadBatch];
+#pragma unroll
+      for (int u = 0; u < kLoadBatch; ++u) xs[u] = load_group4(src, g0 + u * kThreads, ngroups, cnt, vec_ok);
+#pragma unroll
+      for (int u = 0; u < kLoadBatch; ++u) {
+        const int gi = g0 + u * kThreads;
+        if (gi < ngroups) {
+          const float xe[4] = {xs[u].x, xs[u].y, xs[u].z, xs[u].w};
+          const int nv = min(4, cnt - gi * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < nv) {
+              const unsigned int pos = atomicAdd(&sm.cnt[bin_of(xe[q], bmul)], 1u);
+              sm.sorted[pos] = xe[q];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass 3: thresholds.  pair p = j * Nc + c: neighbouring threads take neighbouring candidates of the same
+    // level, whose thresholds fall into neighbouring bins and whose accumulators are distinct
+    {
+      long long ptot = 0ll;
+      for (int w = 0; w < kWarps; ++w) ptot += (long long)sm.wsum[w];
+      int j = tid / Nc, c = tid - j * Nc;
+      const int dj = kThreads / Nc, dc = kThreads - dj * Nc;
+      for (int p = tid; p < npairs; p += kThreads) {
+        const float s = sm.scale[c];
+        const float level = L.lo + (float)j;
+        const float theta = code_threshold(s, level);
+        const int b = bin_of(theta, bmul);
+        const unsigned int beg = b ? sm.cnt[b - 1] : 0u, end = sm.cnt[b];
+        long long ps = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);
+        long long cn = (long long)beg;
+        // fix_x() split into its two integer parts, accumulated separately (int32 is enough for 512 elements at a time)
+        for (unsigned int i0 = beg; i0 < end; i0 += 512u) {
+          const unsigned int i1 = min(end, i0 + 512u);
+          int sth = 0, stl = 0, below = 0;
+          for (unsigned int i = i0; i < i1; ++i) {
+            const float x = sm.sorted[i];
+            const float hb = fma_rn(x, fx.p2a, 12582912.0f);
+            const float r = fma_rn(x, fx.p2a, -sub_rn(hb, 12582912.0f));
+            const float lb = fma_rn(r, 1048576.0f, 12582912.0f);
+            const bool in = x < theta;
+            sth += in ? (int)__float_as_uint(hb) - 0x4B400000 : 0;
+            stl += in ? (int)__float_as_uint(lb) - 0x4B400000 : 0;
+            below += in ? 1 : 0;
+          }
+          cn += below;
+          ps += (long long)sth * 1048576ll + (long long)stl;
+        }
+        double term = threshold_term(s, level, cn, ps, fx.unit);
+        if (j == nthr - 1) term += closing_term(s, L.hi, (long long)cnt, ptot, fx.unit);
+        atomicAdd(&sm.acc[c], (unsigned long long)__double2ll_rn(term * unit_inv));
+        j += dj;
+        c += dc;
+        if (c >= Nc) {
+          c -= Nc;
+          ++j;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- sum of squares: fixed-order reduction over the CTA, then one integer atomic per candidate
+  x2 = warp_sum(x2);
+  if (lane == 0) sm.red[warp] = x2;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) tot += sm.red[w];
+  const long long x2f = __double2ll_rn(tot * unit_inv);
+  for (int c = tid; c < Nc; c += kThreads) {
+    const long long f = (long long)sm.acc[c] + x2f;  // >= 0 up to rounding
+    atomicAdd(cand_sums + c, (unsigned long long)max(f, 0ll));
+  }
+}
+
+// Dispatch: threshold form whenever absmax is in its supported range, direct evaluation otherwise (and on request)
+__device__ inline void cta_candidate_sums(const float* __restrict__ v, long long e0, long long e1, float absmax, int Nc,
+                                          const Levels L, int bits, double n_total, unsigned long long* cand_sums,
+                                          SearchSmem& sm, float opaque_neg_zero, bool force_direct = false) {
+  if (!force_direct && binned_range_ok(absmax)) cta_candidate_sums_binned(v, e0, e1, absmax, Nc, L, bits, n_total, cand_sums, sm.binned);
+  else cta_candidate_sums_direct(v, e0, e1, absmax, Nc, L, n_total, cand_sums, sm.direct, opaque_neg_zero);
 }
 
 // First index of the smallest MSE (torch.argmin, source/quantization.py:141), evaluated

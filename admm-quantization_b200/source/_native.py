@@ -40,6 +40,7 @@ def _load():
         "admmq_launch_count": (ctypes.c_uint64, []),
         "admmq_project_workspace_bytes": (c_sz, [c_i64, c_int]),
         "admmq_project": (c_int, [vp, c_i64, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, c_sz, vp]),
+        "admmq_clip_search_sums": (c_int, [vp, c_i64, c_int, c_int, c_int, c_int, vp, vp, c_sz, vp]),
         "admmq_gram_hadamard": (c_int, [vp, c_int, vp, c_int, c_int, vp, vp]),
         "admmq_unfold3": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
         "admmq_mttkrp_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
@@ -69,7 +70,7 @@ def _load():
 
 lib = _load()
 EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count admmq_project_workspace_bytes "
-           "admmq_project admmq_admm_loop_workspace_bytes admmq_admm_loop admmq_gemm_nt "
+           "admmq_project admmq_clip_search_sums admmq_admm_loop_workspace_bytes admmq_admm_loop admmq_gemm_nt "
            "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp admmq_permute_myx "
            "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
@@ -165,6 +166,18 @@ def project(x, bits, qscheme, num_attempts=200, tmin=None, tmax=None, want_codes
     check(lib.admmq_project(ptr(xc), n, int(bits), qscheme_id(qscheme), int(num_attempts), ptr(tmin_t), ptr(tmax_t),
                             ptr(out), ptr(codes), ptr(info), ptr(ws), ws.numel(), stream_ptr(xc.device)))
     return out, codes, info
+
+
+def clip_search_sums(x, bits, num_attempts=200, method=1, max_ctas=0):
+    """Per-candidate sum((x - Q_c(x))**2) as float64: method 0 = direct evaluation, 1 = threshold form (parity tests)."""
+    require_cuda(x)
+    xc = f32c(x)
+    n = xc.numel()
+    sums = torch.empty(int(num_attempts), dtype=torch.float64, device=xc.device)
+    ws = _ws(project_workspace_bytes(n, num_attempts), xc.device, None)
+    check(lib.admmq_clip_search_sums(ptr(xc), n, int(bits), int(num_attempts), int(method), int(max_ctas), ptr(sums),
+                                     ptr(ws), ws.numel(), stream_ptr(xc.device)))
+    return sums
 
 
 def gram_hadamard(U1, U2=None, out=None):

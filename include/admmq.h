@@ -76,6 +76,12 @@ ADMMQ_API size_t admmq_project_workspace_bytes(int64_t n, int num_attempts);
 ADMMQ_API int admmq_project(const float* x, int64_t n, int bits, int qscheme, int num_attempts,
                   const float* tmin, const float* tmax, float* xq, int8_t* codes, float* info,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* The per-candidate sums behind the argmin of source/quantization.py:136-141, sums[c] = sum((x - Q_c(x))**2) as
+ * float64, for the parity tests: method 0 = direct evaluation of every (element, candidate) pair with the
+ * reference's float32 operations, method 1 = the threshold form the product uses (csrc/numerics.cuh).  max_ctas > 0
+ * limits the grid (the result must not depend on it).  Workspace: admmq_project_workspace_bytes(n, num_attempts). */
+ADMMQ_API int admmq_clip_search_sums(const float* x, int64_t n, int bits, int num_attempts, int method, int max_ctas,
+                  double* sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ per-sweep contractions
  * Gram-Hadamard  G = (U1^T U1) * (U2^T U2)   scripts/factorize.py:215,226,236 (3-D), :276,286 (2-D, U2 = NULL)

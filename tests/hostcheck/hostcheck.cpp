@@ -5,6 +5,8 @@
 // Build: g++ -O2 -ffp-contract=off -shared -fPIC (tests/test_host_numerics.py does it).
 #include <cstdint>
 #include <cmath>
+#include <algorithm>
+#include <vector>
 #include "../../admm-quantization_b200/csrc/numerics.cuh"
 
 using namespace admmq;
@@ -60,6 +62,56 @@ long long hc_mse(const float* x, long long n, float absmax, int bits, int nc, fl
   }
   *best = arg;
   return slow;
+}
+
+// per-candidate MSE in the THRESHOLD form the kernels use (numerics.cuh): exact thresholds, counts and fixed-point
+// prefix sums below each threshold (here from a sorted copy), float64 terms converted one by one to the accumulator's
+// fixed point, float32 mean.  Also returns, through `sums`, the float64 value of each sum.
+void hc_mse_thresholds(const float* x, long long n, float absmax, int bits, int nc, float* mse, double* sums, int* best) {
+  const Levels L = make_levels(bits);
+  const ClipGrid g = make_clip_grid(absmax, nc);
+  const double unit_inv = fixed_point_unit_inv((double)n, absmax), unit = fixed_point_unit((double)n, absmax);
+  const FixX fx = make_fix_x(absmax);
+  std::vector<float> xs(x, x + n);
+  std::sort(xs.begin(), xs.end());
+  std::vector<long long> pre(n + 1, 0);
+  for (long long i = 0; i < n; ++i) pre[i + 1] = pre[i] + fix_x(xs[i], fx);
+  double x2 = 0.0;
+  for (long long i = 0; i < n; ++i) x2 += (double)x[i] * (double)x[i];
+  const long long x2f = llrint(x2 * unit_inv);
+  const int nthr = (1 << bits) - 1;
+  int arg = 0;
+  for (int c = 0; c < nc; ++c) {
+    const float s = scale_of(clip_candidate(g, c), L);
+    long long acc = 0;
+    for (int j = 0; j < nthr; ++j) {
+      const float level = L.lo + (float)j;
+      const float theta = code_threshold(s, level);
+      const long long cnt = std::lower_bound(xs.begin(), xs.end(), theta) - xs.begin();  // #{x < theta}
+      double term = threshold_term(s, level, cnt, pre[cnt], fx.unit);
+      if (j == nthr - 1) term += closing_term(s, L.hi, n, pre[n], fx.unit);
+      acc += llrint(term * unit_inv);
+    }
+    const long long f = std::max(acc + x2f, 0ll);
+    sums[c] = (double)f * unit;
+    mse[c] = mse_from_fixed(f, unit, (float)n);
+    if (mse[c] < mse[arg]) arg = c;
+  }
+  *best = arg;
+}
+
+// code_threshold(): theta is the smallest float whose code reaches level + 1.  Returns the number of violations among
+// the thresholds of every level for this scale (checks theta itself and its predecessor with the exact division).
+long long hc_threshold_violations(float scale, int bits) {
+  const Levels L = make_levels(bits);
+  long long bad = 0;
+  for (float level = L.lo; level < L.hi; level += 1.0f) {
+    const float theta = code_threshold(scale, level);
+    const float below = ordered_float(ordered_key(theta) - 1u);
+    if (!(rint_rn(div_rn(theta, scale)) >= level + 1.0f)) ++bad;
+    if (rint_rn(div_rn(below, scale)) >= level + 1.0f) ++bad;
+  }
+  return bad;
 }
 
 // fast path alone vs exact path: count of elements where they disagree although the fast path was accepted

@@ -103,6 +103,42 @@ def test_projection_full_size_layer4(nat):
     torch.set_num_threads(1)
 
 
+def test_threshold_search_against_direct_evaluation(nat):
+    """The product's threshold form of the clip search (csrc/numerics.cuh) against the direct evaluation of every
+    (element, candidate) pair with the reference's float32 operations, incl. BASELINE full sizes, skewed / grid-valued
+    / outlier inputs and every bit-width: sums agree to float32 summation noise, the argmin is the same (or a near
+    tie), the result does not depend on the grid beyond fixed-point rounding and is bit-reproducible run to run."""
+    g = torch.Generator().manual_seed(99)
+    cases = []
+    for shape, bits, nc in [((512, 1141), 4, 200), ((4096, 1024), 4, 200), ((64, 134), 4, 200), ((9, 1141), 4, 200),
+                            ((256, 566), 3, 200), ((128, 278), 8, 200), ((64, 134), 8, 1000), ((300, 77), 2, 200),
+                            ((37, 41), 1, 200), ((1, 5), 4, 200), ((2048, 204), 6, 200), ((1, 1), 4, 7)]:
+        cases.append((torch.randn(*shape, generator=g) * 0.07, bits, nc, "randn"))
+    x = torch.randn(256, 566, generator=g)
+    x[17, 3] = 250.0
+    cases.append((x, 4, 200, "outlier"))
+    cases.append((torch.randn(200, 300, generator=g).abs() + 5.0, 4, 200, "offset"))
+    cases.append((torch.randint(-8, 8, (128, 278), generator=g).float() * 0.013, 4, 200, "grid-valued"))
+    cases.append((torch.full((64, 64), 0.37), 4, 200, "constant"))
+    cases.append((torch.randn(128, 128, generator=g) * 1e-9, 4, 200, "small"))
+    cases.append((torch.randn(128, 128, generator=g) * 1e9, 4, 200, "large"))
+    for x, bits, nc, tag in cases:
+        xd = x.cuda()
+        direct = nat.clip_search_sums(xd, bits, nc, method=0).cpu().numpy()
+        thr = nat.clip_search_sums(xd, bits, nc, method=1).cpu().numpy()
+        n = x.numel()
+        floor = 1e-13 * float((x.double() ** 2).sum()) + 1e-300
+        assert np.all(np.abs(thr - direct) <= 3e-6 * np.abs(direct) + floor), (tag, tuple(x.shape), bits, nc)
+        mse_d, mse_t = (direct / n).astype(np.float32), (thr / n).astype(np.float32)
+        bd, bt = int(np.argmin(mse_d)), int(np.argmin(mse_t))
+        if bd != bt:
+            assert abs(float(mse_d[bd]) - float(mse_d[bt])) <= 3e-7 * float(mse_d[bd]), (tag, bd, bt)
+        again = nat.clip_search_sums(xd, bits, nc, method=1).cpu().numpy()
+        assert np.array_equal(thr, again), tag
+        few = nat.clip_search_sums(xd, bits, nc, method=1, max_ctas=3).cpu().numpy()
+        assert np.all(np.abs(few - thr) <= 1e-11 * np.abs(thr) + floor), tag
+
+
 def test_projection_in_place_and_repeatable(nat):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(300, 77, generator=g).cuda()

@@ -71,6 +71,64 @@ def test_kernel_mse_recipe_selects_reference_candidate(hc, golden_projection):
         assert np.array_equal(codes, gp[m["name"] + "/codes"].reshape(-1))
 
 
+def test_threshold_form_selects_reference_candidate(hc, golden_projection):
+    """The threshold form of the clip search (what the kernels run) picks the reference's candidate on every golden
+    vector, and its sums agree with the direct float32 evaluation to float32 summation noise."""
+    gp = golden_projection
+    checked = 0
+    for m in gp.meta:
+        if "scheme" in m or m["name"] == "all_zero_b4":
+            continue
+        x = np.ascontiguousarray(gp[m["name"] + "/x"]).reshape(-1)
+        mx = np.float32(max(abs(x.min()), abs(x.max())))
+        if not (2.0 ** -40 <= mx <= 2.0 ** 40):
+            continue  # outside the threshold form's range the kernels use the direct form
+        nc = m["num_attempts"]
+        mse, sums, best = np.empty(nc, np.float32), np.empty(nc, np.float64), ctypes.c_int()
+        hc.hc_mse_thresholds(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(mx), m["bits"], nc, fp(mse), fp(sums), ctypes.byref(best))
+        idx, scale = gp[m["name"] + "/idx_scale"]
+        assert best.value == int(idx), m["name"]
+        direct = np.empty(nc, np.float32)
+        hc.hc_mse(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(mx), m["bits"], nc, fp(direct), ctypes.byref(best), 0)
+        ok = direct > 0
+        assert np.all(np.abs(mse[ok] - direct[ok]) <= 3e-6 * direct[ok]), m["name"]
+        checked += 1
+    assert checked >= 10
+
+
+def test_code_thresholds_are_exact(hc):
+    g = torch.Generator().manual_seed(11)
+    for bits in (1, 2, 3, 4, 6, 8):
+        for trial in range(200):
+            scale = np.float32(float(torch.rand(1, generator=g) + 0.01) * 10 ** float(torch.randint(-9, 9, (1,), generator=g)))
+            assert hc.hc_threshold_violations(ctypes.c_float(scale), bits) == 0, (bits, scale)
+
+
+def test_threshold_form_matches_oracle_argmin_on_random_tensors(hc):
+    g = torch.Generator().manual_seed(77)
+    for shape, bits, nc in [((64, 134), 4, 200), ((9, 134), 4, 200), ((33, 57), 3, 200), ((128, 97), 8, 200),
+                            ((7, 5), 2, 33), ((40, 40), 6, 1000), ((1, 1), 4, 200), ((2, 3), 1, 50)]:
+        for trial in range(3):
+            xt = torch.randn(*shape, generator=g) * float(10 ** torch.randint(-3, 3, (1,), generator=g).item())
+            _, _, _, ref_best, mses = orc.project_mse(xt, bits, nc, "aten")
+            x = np.ascontiguousarray(xt.numpy()).reshape(-1)
+            mx = np.float32(np.abs(x).max())
+            mse, sums, best = np.empty(nc, np.float32), np.empty(nc, np.float64), ctypes.c_int()
+            hc.hc_mse_thresholds(fp(x), ctypes.c_longlong(x.size), ctypes.c_float(mx), bits, nc, fp(mse), fp(sums), ctypes.byref(best))
+            if best.value != ref_best:
+                gap = abs(float(mses[best.value]) - float(mses[ref_best])) / float(mses[ref_best])
+                assert gap < 3e-7, (shape, bits, nc, best.value, ref_best, gap)
+            # the sums themselves against a float64 evaluation of the reference's expression
+            clip, scale = np.empty(nc, np.float32), np.empty(nc, np.float32)
+            hc.hc_candidates(ctypes.c_float(mx), nc, bits, fp(clip), fp(scale))
+            q = 2 ** (bits - 1)
+            for c in (0, nc // 3, nc - 1):
+                codes = np.clip(np.rint((x / scale[c]).astype(np.float32)), -q, q - 1).astype(np.float32)
+                y = (codes * scale[c]).astype(np.float32)
+                exact = float(((x.astype(np.float64) - y.astype(np.float64)) ** 2).sum())
+                assert abs(sums[c] - exact) <= 1e-9 * exact + 1e-300, (shape, bits, c, sums[c], exact)
+
+
 def test_fast_path_equals_exact_division(hc):
     """x*(1/s) + magic-number rounding agrees with rint(x/s) whenever the fast path accepts, incl.
     values placed right at the rounding boundaries (k + 0.5) * s."""

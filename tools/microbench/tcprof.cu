@@ -31,14 +31,14 @@ __global__ void __launch_bounds__(512, 1) k(const __grid_constant__ GemmMaps map
   }
   tc::pipe_teardown(pipe);
 }
-template <int BN> void run(int M, int N, int K) {
+template <int BN> void run(int M, int N, int K, int gmax = 148) {
   float *A, *B, *C; long long* dbg;
   cudaMalloc(&A, (size_t)M * K * 4); cudaMalloc(&B, (size_t)N * K * 4); cudaMalloc(&C, (size_t)M * N * 4); cudaMalloc(&dbg, 128);
   cudaMemset(A, 0, (size_t)M * K * 4); cudaMemset(B, 0, (size_t)N * K * 4);
   const int smem = tc::TileSmem<BN>::kBytes;
   cudaFuncSetAttribute(k<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
-  const int grid = tiles < 148 ? tiles : 148;
+  const int grid = tiles < gmax ? tiles : gmax;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   GemmMaps maps; tc::make_operand_tmap(&maps.a, A, M, K, K, 128); tc::make_operand_tmap(&maps.b, B, N, K, K, BN);
   for (int rep = 0; rep < 3; ++rep) { cudaEventRecord(e0); k<BN><<<grid, 512, smem>>>(maps, M, N, K, C, N, dbg, -0.0f); cudaEventRecord(e1); cudaDeviceSynchronize(); }
@@ -49,4 +49,4 @@ template <int BN> void run(int M, int N, int K) {
   printf("   producer(thread 0): cp.async wait %lld, stage_free wait %lld, convert+issue %lld, tile_done wait %lld, epilogue %lld\n", h[0], h[1], h[2], h[5], h[6]);
   printf("   mma warp (lane 0) : full wait %lld, issue %lld, tile_done wait %lld   => per K-block: full-wait %.0f issue %.0f\n", h[8 + 3], h[8 + 4], h[8 + 5], (double)h[11] / (tiles_cta0 * nkb), (double)h[12] / (tiles_cta0 * nkb));
 }
-int main() { run<32>(512, 1141, 1144); run<32>(4096, 4096, 4096); run<16>(256, 566, 568); return 0; }
+int main() { run<16>(512, 1141, 1144); run<32>(512, 1141, 1144); run<64>(512, 1141, 1144); run<64>(512, 1141, 1144, 31); run<32>(512, 1141, 1144, 31); run<64>(4096, 4096, 4096); run<16>(256, 566, 568); run<64>(256, 566, 568, 8); return 0; }

@@ -22,10 +22,12 @@ def launches(csv_path, out_path, title):
             f.write(f"| `{k}` | {n} | {t:.2f} | {100 * t / tot:.1f} % | {', '.join(sorted(g))[:60]} |\n")
 
 
-def full(rep_path, out_path, title, top=25):
+def full(rep_path, out_path, title, top=25, kernel=""):
     raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    i_kn = hdr.index("Kernel Name")
+    vals = [r for r in rows[2:] if kernel in r[i_kn]][-1]  # last launch of the wanted kernel
     want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
             "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed",
@@ -35,7 +37,12 @@ def full(rep_path, out_path, title, top=25):
             "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg.per_second",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
     src = subprocess.run(["ncu", "-i", rep_path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    srows = list(csv.reader(src.splitlines()))
+    srows_all = list(csv.reader(src.splitlines()))
+    # the source page has one section per profiled launch, each introduced by a "Kernel Name" row
+    starts = [i for i, r in enumerate(srows_all) if r and r[0] == "Kernel Name"]
+    pick = [i for i in starts if kernel in srows_all[i][1]][-1] if starts else 0
+    end = min([i for i in starts if i > pick] + [len(srows_all)])
+    srows = srows_all[pick:end]
     with open(out_path, "w") as f:
         f.write(f"# {title}\n\n| metric | unit | value |\n|---|---|---|\n")
         for h, u, v in zip(hdr, units, vals):
@@ -58,4 +65,7 @@ def full(rep_path, out_path, title, top=25):
 
 if __name__ == "__main__":
     kind = sys.argv[1]
-    (launches if kind == "launches" else full)(sys.argv[2], sys.argv[3], sys.argv[4])
+    if kind == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        full(sys.argv[2], sys.argv[3], sys.argv[4], kernel=sys.argv[5] if len(sys.argv) > 5 else "")
