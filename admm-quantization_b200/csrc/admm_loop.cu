@@ -162,6 +162,81 @@ __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned i
   }
 }
 
+// P1 for factors with very few rows (the 3 x 3 tap factor of a convolution: I = 9): a 128-row tensor-core tile or a
+// 16 x 32 FFMA tile would idle on padding, and the product is really I matrix-vector products that stream Minv once.
+// Every CTA owns a strip of output columns; inside the CTA thread (c, s) accumulates columns 4c .. 4c+3 of the strip
+// over the k-slice {s, s + ks, ...} (Minv rows read as float4 from L2, the staged RHS from shared memory), and the
+// k-slices are summed in fixed order through shared memory.
+template <int MI>
+struct __align__(16) SkinnySmem {
+  static constexpr int kRhsFloats = 16384;  // I * Rp must fit (launch_loop checks)
+  float rhs[kRhsFloats];
+  float red[512 * MI * 4];
+};
+
+template <int MI>
+__device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsigned int* keys) {
+  const int I = p.I, R = p.R, Rp = p.Rp, t = threadIdx.x;
+  const int cps = ((R + (int)gridDim.x - 1) / (int)gridDim.x + 3) / 4 * 4;
+  const int n_begin = blockIdx.x * cps, n_end = min(R, n_begin + cps);
+  unsigned int kmax = 0u, kinv = 0u;
+  if (n_begin < R) {  // uniform per CTA
+    __syncthreads();
+    for (int e = t * 4; e < I * Rp; e += kThreads * 4) *reinterpret_cast<float4*>(&ss.rhs[e]) = ldcg4(p.RHS + e);
+    __syncthreads();
+    for (int s0 = n_begin; s0 < n_end; s0 += 128) {
+      const int w = min(128, n_end - s0);
+      const int cg = (w + 3) >> 2;     // float4 column groups; s0 + 4 cg <= Rp, the pad columns of Minv are zero
+      const int ks = kThreads / cg;    // k-slices
+      const int s = t / cg, c = t - s * cg;
+      float acc[MI][4];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+      if (s < ks) {
+        const float* mp = p.Minv + s0 + 4 * c;
+#pragma unroll 4
+        for (int k = s; k < R; k += ks) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(mp + (size_t)k * Rp));
+#pragma unroll
+          for (int i = 0; i < MI; ++i) {
+            if (i < I) {
+              const float r = ss.rhs[i * Rp + k];
+              acc[i][0] = fmaf(r, m.x, acc[i][0]);
+              acc[i][1] = fmaf(r, m.y, acc[i][1]);
+              acc[i][2] = fmaf(r, m.z, acc[i][2]);
+              acc[i][3] = fmaf(r, m.w, acc[i][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+          *reinterpret_cast<float4*>(&ss.red[(size_t)t * (MI * 4) + i * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      }
+      __syncthreads();
+      for (int o = t; o < I * w; o += kThreads) {
+        const int i = o / w, nn = o - i * w;
+        const int cc = nn >> 2, q = nn & 3;
+        float h = 0.0f;
+        for (int sl = 0; sl < ks; ++sl) h = add_rn(h, ss.red[(size_t)(sl * cg + cc) * (MI * 4) + i * 4 + q]);
+        const int n = s0 + nn;
+        p.Hls[(size_t)i * Rp + n] = h;
+        const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + n));  // V = H_ls - U (:59)
+        p.V[(size_t)i * R + n] = v;
+        const unsigned int k = float_key(v);
+        kmax = max(kmax, k);
+        kinv = max(kinv, ~k);
+      }
+      __syncthreads();
+    }
+  }
+  kmax = warp_max_u32(kmax);
+  kinv = warp_max_u32(kinv);
+  if ((threadIdx.x & 31) == 0 && (kmax | kinv) != 0u) {
+    atomicMax(&keys[0], kmax);
+    atomicMax(&keys[1], kinv);
+  }
+}
+
 // P1 on the tensor cores: 128 x TCBN tiles of H_ls = RHS . Minv^T (Minv is symmetric) in 3xTF32.
 template <int TCBN>
 __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc::Pipe& pipe, tc::PipeState& st,
@@ -175,25 +250,35 @@ __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * TCBN;
     tc::tile_3xtf32<TCBN>(&p.tm_rhs, i0, &p.tm_minv, n0, R, smem_tiles, pipe, st);
-    float v[TCBN / 4];
-    int row, col0;
-    tc::load_acc<TCBN>(pipe, v, row, col0);
-    const int i = i0 + row;
-    if (i < I) {
+    // epilogue over row-contiguous float4 groups of the tile parked in shared memory (coalesced global traffic)
+    const float* tile_h = tc::acc_to_smem<TCBN>(pipe, smem_tiles);
+    using ET = tc::EpiTile<TCBN>;
 #pragma unroll
-      for (int c = 0; c < TCBN / 4; ++c) {
-        const int n = n0 + col0 + c;
-        if (n < R) {
-          p.Hls[(size_t)i * Rp + n] = v[c];
-          const float d = sub_rn(v[c], __ldcg(p.U + (size_t)i * R + n));  // V = H_ls - U (:59)
-          p.V[(size_t)i * R + n] = d;
-          const unsigned int k = float_key(d);
-          kmax = max(kmax, k);
-          kinv = max(kinv, ~k);
+    for (int g0 = 0; g0 < ET::kGroups; g0 += kThreads) {
+      const int g = g0 + (int)threadIdx.x;
+      const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
+      const int i = i0 + row, n = n0 + c4;
+      if (g < ET::kGroups && i < I && n < R) {
+        const float4 h4 = *reinterpret_cast<const float4*>(tile_h + row * ET::kLd + c4);
+        const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+        *reinterpret_cast<float4*>(p.Hls + (size_t)i * Rp + n) = h4;  // n + 3 < Rp: pad columns hold the zero-filled product
+        const size_t e = (size_t)i * R + n;
+        float u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = (n + q < R) ? __ldcg(p.U + e + q) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (n + q < R) {
+            const float d = sub_rn(h[q], u[q]);  // V = H_ls - U (:59)
+            p.V[e + q] = d;
+            const unsigned int k = float_key(d);
+            kmax = max(kmax, k);
+            kinv = max(kinv, ~k);
+          }
         }
       }
     }
-    tc::release_acc();
+    __syncthreads();  // the staging tile lives in the operand stages the next tile's producers write
   }
   kmax = warp_max_u32(kmax);
   kinv = warp_max_u32(kinv);
@@ -216,6 +301,7 @@ union LoopSmem {
   GemmSmem<BM, BN> gemm;
   ResidualSmem res;
   unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16)>::kBytes : 16];
+  SkinnySmem<(TCBN < 0 ? -TCBN : 1)> skinny;
 };
 
 // sum over the CTA of four per-thread doubles, result valid in every thread
@@ -238,7 +324,8 @@ __device__ __forceinline__ void cta_sum4(double v[4], ResidualSmem& rs) {
   }
 }
 
-// TCBN = 0: P1 as float32 FFMA tiles (BM x BN, TM x TN per thread); TCBN = 16 / 32: P1 on the tensor cores.
+// TCBN = 0: P1 as float32 FFMA tiles (BM x BN, TM x TN per thread); TCBN = 16 / 32 / 64: P1 on the tensor cores;
+// TCBN = -MI: P1 for factors with at most MI rows (gemm_phase_skinny).
 template <int BM, int BN, int TM, int TN, int TCBN>
 __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant__ LoopParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -302,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
     // ---------------- P1
     if constexpr (TCBN > 0) gemm_phase_tc<TCBN>(p, sm.tc_tiles, pipe, pst, hdr->keys[slot]);
+    else if constexpr (TCBN < 0) gemm_phase_skinny<-TCBN>(p, sm.skinny, hdr->keys[slot]);
     else gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
     if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
       if (t < 4) hdr->keys[next_slot][t] = 0u;
@@ -575,7 +663,18 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   size_t smem = 0;
   // tensor-core P1 only pays off when the factor has enough rows to fill a good part of a 128-row tile
   const bool use_tc = precision == 1 && I >= 64 && R >= 32;
-  if (use_tc) {
+  const bool use_skinny = I <= 16 && (long long)I * l.Rp <= SkinnySmem<16>::kRhsFloats;
+  if (use_skinny) {
+    memset(&p.tm_rhs, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv, 0, sizeof(CUtensorMap));
+    if (I <= 9) {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, -9>;
+      smem = sizeof(LoopSmem<16, 32, -9>);
+    } else {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, -16>;
+      smem = sizeof(LoopSmem<16, 32, -16>);
+    }
+  } else if (use_tc) {
     const int tilesM = (I + tc::kTileM - 1) / tc::kTileM;
     // tile width: the cost of a tile is dominated by staging its 128 rows of A (independent of the width) plus the
     // BN rows of B, so minimise waves * (128 + BN); ties go to the wider tile

@@ -46,15 +46,28 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * BN;
     tc::tile_3xtf32<BN>(&maps.a, i0, &maps.b, n0, K, smem_dyn, pipe, st);
-    float v[BN / 4];
-    int row, col0;
-    tc::load_acc<BN>(pipe, v, row, col0);
-    if (i0 + row < M) {
+    const float* tile_c = tc::acc_to_smem<BN>(pipe, smem_dyn);
+    using ET = tc::EpiTile<BN>;
+    const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
-      for (int i = 0; i < BN / 4; ++i)
-        if (n0 + col0 + i < N) C[(size_t)(i0 + row) * ldc + n0 + col0 + i] = v[i];
+    for (int g0 = 0; g0 < ET::kGroups; g0 += tc::kThreadsTC) {
+      const int g = g0 + (int)threadIdx.x;
+      const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
+      const int i = i0 + row, n = n0 + c4;
+      if (g < ET::kGroups && i < M && n < N) {
+        const float4 h4 = *reinterpret_cast<const float4*>(tile_c + row * ET::kLd + c4);
+        float* dst = C + (size_t)i * ldc + n;
+        if (vec && n + 3 < N) {
+          *reinterpret_cast<float4*>(dst) = h4;
+        } else {
+          const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (n + q < N) dst[q] = h[q];
+        }
+      }
     }
-    tc::release_acc();
+    __syncthreads();
   }
   tc::pipe_teardown(pipe);
 }

@@ -360,6 +360,7 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
       TC_T0();
       const unsigned char* raw = raw_ptr + (size_t)d * TS::kRawBytes;
       const unsigned int col0 = lane_addr + (unsigned int)(TS::kAccCols + s * kStageCols);
+#ifndef TC_EXP_NO_A
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         if (i < c_count) {
@@ -371,7 +372,9 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
           tmem_store4(col0 + (unsigned int)(kBlockK + c * 4), lo);
         }
       }
+#endif
       unsigned char* stage = tiles_ptr + (size_t)s * TS::kStageBytes;
+#ifndef TC_EXP_NO_B
       for (int bi = bi0; bi < kChunksB; bi += 384) {
         const int atom = bi / (BN * 8), lid = bi % (BN * 8);
         const unsigned int off = (unsigned int)(atom * TS::kBAtomBytes) + sw128(lid >> 3, lid & 7);
@@ -381,9 +384,14 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
         *reinterpret_cast<float4*>(stage + off) = hi;
         *reinterpret_cast<float4*>(stage + TS::kBBytes + off) = lo;
       }
+#endif
+#ifndef TC_EXP_NO_A
       tmem_store_wait();
+#endif
       tc_fence_before();
+#ifndef TC_EXP_NO_FENCE
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(&pipe.stage_full[s]);
       TC_ACC(2);
@@ -439,6 +447,34 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
 __device__ __forceinline__ void release_acc() {
   tc_fence_before();
   __syncthreads();
+}
+
+// Epilogue staging.  A thread holds one ROW of the accumulator (TMEM lane = row), so writing results straight to
+// row-major global memory touches 32 different rows per warp instruction (4 useful bytes per 32-byte sector, measured
+// ~6-8 k cycles per 128 x 64 tile).  acc_to_smem() parks the tile in shared memory instead - rows of BN + 4 floats
+// (the pad keeps the per-row float4 stores conflict free) in the operand stage buffers, which are idle once tile_done
+// has completed - releases the accumulator and returns the tile, so that the caller can walk it in row-contiguous
+// float4 groups (thread t -> group t, t + 512, ...; group g = row g / (BN / 4), columns 4 (g % (BN / 4)) .. +3).  The
+// caller must __syncthreads() after its last read and before the next tile_3xtf32().
+template <int BN>
+struct EpiTile {
+  static constexpr int kLd = BN + 4;
+  static constexpr int kGroupsPerRow = BN / 4;
+  static constexpr int kGroups = kTileM * kGroupsPerRow;
+  static_assert(kTileM * kLd * 4 <= TileSmem<BN>::kStages * TileSmem<BN>::kStageBytes, "staging tile must fit in the operand stages");
+};
+template <int BN>
+__device__ __forceinline__ const float* acc_to_smem(const Pipe& pipe, unsigned char* smem_tiles) {
+  const unsigned int tiles_base = (smem_u32(smem_tiles) + 1023u) & ~1023u;
+  float* tile = reinterpret_cast<float*>(smem_tiles + (tiles_base - smem_u32(smem_tiles)));
+  float v[BN / 4];
+  int row, col0;
+  load_acc<BN>(pipe, v, row, col0);
+  float* dst = tile + row * EpiTile<BN>::kLd + col0;
+#pragma unroll
+  for (int c = 0; c < BN / 4; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  release_acc();
+  return tile;
 }
 
 // Host: TMA descriptor of a row-major float32 matrix (rows x cols, leading dimension ld floats, ld % 4 == 0, base
