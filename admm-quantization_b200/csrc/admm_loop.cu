@@ -37,8 +37,12 @@ struct IterationHeader {  // admmq_admm_iteration only: scalars handed from the 
 };
 
 struct LoopParams {
-  CUtensorMap tm_rhs;   // TMA descriptors of RHS (I x R, ld Rp) and Minv (R x R, ld Rp); only used by the
-  CUtensorMap tm_minv;  // tensor-core variant of P1
+  CUtensorMap tm_rhs;      // TMA descriptors of RHS (I x R, ld Rp) and of the hi / lo tf32 parts of Minv (R x R, ld Rp);
+  CUtensorMap tm_minv_hi;  // only used by the tensor-core variant of P1
+  CUtensorMap tm_minv_lo;
+  float* MinvHi;           // R x Rp each, made from Minv by the kernel's prologue (tensor-core variant)
+  float* MinvLo;
+  int tc_bn;               // tile width of the tensor-core variant (multiple of 16, <= TCBN)
   float* H;
   float* U;
   const float* F;
@@ -237,29 +241,33 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
   }
 }
 
-// P1 on the tensor cores: 128 x TCBN tiles of H_ls = RHS . Minv^T (Minv is symmetric) in 3xTF32.
+// P1 on the tensor cores: 128 x bn tiles (bn = p.tc_bn <= TCBN) of H_ls = RHS . Minv^T (Minv is symmetric) in 3xTF32;
+// Minv comes pre-split into its tf32 hi / lo parts (constant over the call, made by the kernel's prologue).
 template <int TCBN>
 __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc::Pipe& pipe, tc::PipeState& st,
                               unsigned int* keys) {
-  const int I = p.I, R = p.R, Rp = p.Rp;
-  const int tilesN = (R + TCBN - 1) / TCBN, tilesM = (I + tc::kTileM - 1) / tc::kTileM;
+  const int I = p.I, R = p.R, Rp = p.Rp, bn = p.tc_bn;
+  const int tilesN = (R + bn - 1) / bn, tilesM = (I + tc::kTileM - 1) / tc::kTileM;
   unsigned int kmax = 0u, kinv = 0u;
   // RHS was written with ordinary stores by other CTAs before the grid barrier; the TMA engine reads through the
   // async proxy
   asm volatile("fence.proxy.async;" ::: "memory");
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
-    const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * TCBN;
-    tc::tile_3xtf32<TCBN>(&p.tm_rhs, i0, &p.tm_minv, n0, R, smem_tiles, pipe, st);
+    const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * bn;
+    const int next = tile + (int)gridDim.x;
+    const bool has_next = next < tilesM * tilesN;
+    tc::tile_3xtf32<TCBN, true>(&p.tm_rhs, i0, &p.tm_minv_hi, &p.tm_minv_lo, n0, bn, R, smem_tiles, pipe, st,
+                                has_next ? (next / tilesN) * tc::kTileM : -1, has_next ? (next % tilesN) * bn : -1);
     // epilogue over row-contiguous float4 groups of the tile parked in shared memory (coalesced global traffic)
-    const float* tile_h = tc::acc_to_smem<TCBN>(pipe, smem_tiles);
+    const float* tile_h = tc::acc_to_smem<TCBN, true>(pipe, smem_tiles);
     using ET = tc::EpiTile<TCBN>;
 #pragma unroll
     for (int g0 = 0; g0 < ET::kGroups; g0 += kThreads) {
       const int g = g0 + (int)threadIdx.x;
       const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
       const int i = i0 + row, n = n0 + c4;
-      if (g < ET::kGroups && i < I && n < R) {
-        const float4 h4 = *reinterpret_cast<const float4*>(tile_h + row * ET::kLd + c4);
+      if (g < ET::kGroups && c4 < bn && i < I && n < R) {
+        const float4 h4 = *reinterpret_cast<const float4*>(tile_h + ET::offset(row, c4 >> 2));
         const float h[4] = {h4.x, h4.y, h4.z, h4.w};
         *reinterpret_cast<float4*>(p.Hls + (size_t)i * Rp + n) = h4;  // n + 3 < Rp: pad columns hold the zero-filled product
         const size_t e = (size_t)i * R + n;
@@ -300,7 +308,7 @@ union LoopSmem {
   SearchSmem search;
   GemmSmem<BM, BN> gemm;
   ResidualSmem res;
-  unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16)>::kBytes : 16];
+  unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16), true>::kBytes : 16];
   SkinnySmem<(TCBN < 0 ? -TCBN : 1)> skinny;
 };
 
@@ -370,6 +378,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   const int row0 = (int)((e0 + t) / R), col0 = (int)((e0 + t) - (long long)row0 * R);
   const int drow = kThreads / R, dcol = kThreads - drow * R;
 
+  if constexpr (TCBN > 0) {  // tf32 hi / lo parts of Minv for the tensor-core product (same split as the A operand)
+    const long long n4 = (long long)R * Rp / 4;
+    for (long long e = (long long)blockIdx.x * kThreads + t; e < n4; e += (long long)gridDim.x * kThreads) {
+      float4 hi, lo;
+      tc::split4(__ldg(reinterpret_cast<const float4*>(p.Minv) + e), pst.nz2, hi, lo);
+      reinterpret_cast<float4*>(p.MinvHi)[e] = hi;
+      reinterpret_cast<float4*>(p.MinvLo)[e] = lo;
+    }
+  }
   // RHS = F + rho * (H + U) for the first iteration (:56)
   {
     int i = row0, n = col0;
@@ -522,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
 
 // ------------------------------------------------------------------------------------ host side
 struct LoopLayout {  // workspace of admmq_admm_loop
-  size_t header, cand, slots, hls, rhs, v, total;
+  size_t header, cand, slots, hls, rhs, v, minv_hi, minv_lo, total;
   int Rp;
 };
 
@@ -541,6 +558,8 @@ static LoopLayout loop_layout(int I, int R, int grid) {
   l.rhs = take((size_t)I * l.Rp * sizeof(float));
   l.hls = take((size_t)I * l.Rp * sizeof(float));
   l.v = take((size_t)I * R * sizeof(float));
+  l.minv_hi = take((size_t)R * l.Rp * sizeof(float));
+  l.minv_lo = take((size_t)R * l.Rp * sizeof(float));
   l.total = off;
   return l;
 }
@@ -571,6 +590,7 @@ static IterationLayout iteration_layout(int I, int R, int grid) {
   return l;
 }
 
+constexpr int kTileFixed = 128;  // cost of a tensor-core tile that does not depend on its width, in columns of width
 constexpr int kMaxGrid = 1024;  // workspaces are sized for any cooperative grid up to this many CTAs
 
 static int coop_grid(const DeviceProps& dp, int max_ctas) {
@@ -658,6 +678,9 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.V = (float*)(ws + l.v);
   p.RHS = (float*)(ws + l.rhs);
   p.Minv = Minv;
+  p.MinvHi = (float*)(ws + l.minv_hi);
+  p.MinvLo = (float*)(ws + l.minv_lo);
+  p.tc_bn = 0;
   void* args[] = {&p};
   const void* fn = nullptr;
   size_t smem = 0;
@@ -666,7 +689,8 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   const bool use_skinny = I <= 16 && (long long)I * l.Rp <= SkinnySmem<16>::kRhsFloats;
   if (use_skinny) {
     memset(&p.tm_rhs, 0, sizeof(CUtensorMap));
-    memset(&p.tm_minv, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv_hi, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv_lo, 0, sizeof(CUtensorMap));
     if (I <= 9) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, -9>;
       smem = sizeof(LoopSmem<16, 32, -9>);
@@ -676,26 +700,28 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     }
   } else if (use_tc) {
     const int tilesM = (I + tc::kTileM - 1) / tc::kTileM;
-    // tile width: the cost of a tile is dominated by staging its 128 rows of A (independent of the width) plus the
-    // BN rows of B, so minimise waves * (128 + BN); ties go to the wider tile
+    // tile width (multiple of 16): a tile costs its 128 rows of A (staging, independent of the width) plus bn columns
+    // of tensor-core work; minimise waves * (kTileFixed + bn), ties go to the wider tile
     int tcbn = 64;
     {
       long long best = -1;
-      for (int bn = 64; bn >= 16; bn >>= 1) {
+      for (int bn = 64; bn >= 16; bn -= 16) {
         const long long tiles = (long long)tilesM * ((R + bn - 1) / bn);
-        const long long cost = ((tiles + grid - 1) / grid) * (128 + bn);
+        const long long cost = ((tiles + grid - 1) / grid) * (kTileFixed + bn);
         if (best < 0 || cost < best) {
           best = cost;
           tcbn = bn;
         }
       }
     }
+    p.tc_bn = tcbn;
     if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
-    if (int e = tc::make_operand_tmap(&p.tm_minv, Minv, R, R, l.Rp, tcbn)) return e;
-    if (tcbn == 64) {
+    if (int e = tc::make_operand_tmap(&p.tm_minv_hi, p.MinvHi, R, R, l.Rp, tcbn)) return e;
+    if (int e = tc::make_operand_tmap(&p.tm_minv_lo, p.MinvLo, R, R, l.Rp, tcbn)) return e;
+    if (tcbn > 32) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, 64>;
       smem = sizeof(LoopSmem<16, 32, 64>);
-    } else if (tcbn == 32) {
+    } else if (tcbn > 16) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, 32>;
       smem = sizeof(LoopSmem<16, 32, 32>);
     } else {
@@ -704,7 +730,8 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     }
   } else {
     memset(&p.tm_rhs, 0, sizeof(CUtensorMap));
-    memset(&p.tm_minv, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv_hi, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv_lo, 0, sizeof(CUtensorMap));
     switch (pick_tile(I, R, grid)) {
       case 0: fn = (const void*)k_admm_loop<64, 64, 4, 4, 0>; smem = sizeof(LoopSmem<64, 64, 0>); break;
       case 1: fn = (const void*)k_admm_loop<32, 32, 2, 2, 0>; smem = sizeof(LoopSmem<32, 32, 0>); break;

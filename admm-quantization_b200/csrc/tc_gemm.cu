@@ -45,8 +45,11 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM, tilesN = (N + BN - 1) / BN;
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * BN;
-    tc::tile_3xtf32<BN>(&maps.a, i0, &maps.b, n0, K, smem_dyn, pipe, st);
-    const float* tile_c = tc::acc_to_smem<BN>(pipe, smem_dyn);
+    const int next = tile + (int)gridDim.x;
+    const bool has_next = next < tilesM * tilesN;
+    tc::tile_3xtf32<BN, false>(&maps.a, i0, &maps.b, nullptr, n0, BN, K, smem_dyn, pipe, st,
+                               has_next ? (next / tilesN) * tc::kTileM : -1, has_next ? (next % tilesN) * BN : -1);
+    const float* tile_c = tc::acc_to_smem<BN, false>(pipe, smem_dyn);
     using ET = tc::EpiTile<BN>;
     const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
@@ -55,7 +58,7 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
       const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
       const int i = i0 + row, n = n0 + c4;
       if (g < ET::kGroups && i < M && n < N) {
-        const float4 h4 = *reinterpret_cast<const float4*>(tile_c + row * ET::kLd + c4);
+        const float4 h4 = *reinterpret_cast<const float4*>(tile_c + ET::offset(row, c4 >> 2));
         float* dst = C + (size_t)i * ldc + n;
         if (vec && n + 3 < N) {
           *reinterpret_cast<float4*>(dst) = h4;

@@ -35,48 +35,58 @@ namespace admmq {
 namespace tc {
 
 constexpr int kThreadsTC = 512;
-constexpr int kMmaWarp = 15;     // its lane 0 also issues the MMAs
+constexpr int kMmaWarp = 15;     // one elected lane issues the MMAs
+constexpr int kTmaWarp = 14;     // one elected lane issues every TMA load
+constexpr int kConverters = 14;  // warps 0 .. 13 convert operands
 constexpr int kAtomK = 32;       // floats per 128-byte swizzle row
 constexpr int kAtoms = 2;        // swizzle atoms along K per K-block
 constexpr int kBlockK = kAtomK * kAtoms;  // 64: halves the per-block synchronisation cost of a 32-deep block
 constexpr int kUmmaK = 8;        // k per tcgen05.mma.kind::tf32
-constexpr int kMaxStages = 3;    // operand stages (hi/lo, swizzled): 3 for BN <= 32, 2 for BN = 64 (TMEM budget)
+constexpr int kMaxStages = 3;    // operand stages (B hi/lo swizzled in shared memory, A hi/lo in tensor memory)
 constexpr int kTileM = 128;
+constexpr int kPrefetchB = 2;     // operand stages whose B hi / lo may be requested across a tile boundary (PS)
 
-constexpr int kRawDepth = 3;     // K-blocks of raw float32 in flight (TMA)
+constexpr int kMaxRawDepth = 4;  // K-blocks of raw float32 in flight (TMA): TileSmem::kRawDepth = 4 with PS, 3 without
 constexpr int kStageCols = 2 * kBlockK;  // TMEM columns of one A stage: hi [0, 64), lo [64, 128)
-constexpr int kTmemCols = 512;   // 3 accumulators + stages x 128: 96 + 3 x 128 = 480 (BN <= 32), 192 + 2 x 128 = 448 (BN = 64)
+constexpr int kTmemCols = 512;   // 2 accumulators + stages x 128: 64 + 3 x 128 = 448 (BN <= 32), 128 + 3 x 128 = 512 (BN = 64)
 
-template <int BN>
+// PS ("pre-split B"): the B operand is given as two tf32-valued float32 matrices hi / lo made once by the caller (the
+// ridge inverse is constant for all inner iterations of an ADMM call), fetched by TMA straight into the operand stage
+// in the layout the MMA reads, so that the producer warps only convert A.
+template <int BN, bool PS = false>
 struct TileSmem {
   static_assert(BN == 16 || BN == 32 || BN == 64, "BN must be 16, 32 or 64");
-  static constexpr int kStages = (BN == 64) ? 2 : 3;
-  static constexpr int kAccStride = (BN == 64) ? 64 : 32;        // TMEM columns between the three accumulators
-  static constexpr int kAccCols = 3 * kAccStride;                // hi.hi at +0, hi.lo at +stride, lo.hi at +2 stride
+  static constexpr int kStages = (BN == 64 && !PS) ? 2 : 3;      // shared-memory budget (BN = 64 without PS: 2 x 32 + 3 x 48 KB)
+  static constexpr int kRawDepth = PS ? 4 : 3;                   // (BN = 64 with PS: 3 x 32 + 4 x 32 KB)
+  static constexpr int kAccStride = (BN == 64) ? 64 : 32;        // TMEM columns between the two accumulators
+  static constexpr int kAccCols = 2 * kAccStride;                // hi.hi at +0, hi.lo + lo.hi at +stride
   static_assert(kAccCols + kStages * kStageCols <= kTmemCols, "tensor memory budget");
   static constexpr int kAAtomBytes = kTileM * 128;               // one 32-deep atom of A as raw float32
   static constexpr int kBAtomBytes = BN * 128;
   static constexpr int kABytes = kAtoms * kAAtomBytes;           // one K-block of A
   static constexpr int kBBytes = kAtoms * kBAtomBytes;
   static constexpr int kStageBytes = 2 * kBBytes;                // B_hi, B_lo (A goes to tensor memory)
-  static constexpr int kRawBytes = kABytes + kBBytes;            // one K-block of raw float32
+  static constexpr int kRawBytes = kABytes + (PS ? 0 : kBBytes); // one K-block of raw float32
   static constexpr int kBytes = kStages * kStageBytes + kRawDepth * kRawBytes + 1024;  // + slack for 1024-byte alignment
   static_assert(kBytes <= 227 * 1024, "tile does not fit in shared memory");
 };
 
 struct Pipe {  // lives in shared memory (static), one per CTA
-  unsigned long long raw_full[kRawDepth];  // cp.async data of a K-block has landed (one arrival per thread)
+  unsigned long long raw_full[kMaxRawDepth];  // the TMA data of a K-block has landed
+  unsigned long long raw_free[kMaxRawDepth];  // every converter warp has finished reading the slot
   unsigned long long stage_full[kMaxStages];
   unsigned long long stage_free[kMaxStages];
+  unsigned long long b_full[kMaxStages];   // PS only: the TMA loads of B hi / lo into the stage have landed
   unsigned long long tile_done;
   unsigned int tmem_base;
   unsigned int pad;
 };
 
 struct PipeState {  // per-thread copy, uniform across the CTA
-  unsigned int raw_uses[kRawDepth];  // how often each raw slot has been filled so far
+  unsigned int raw_uses[kMaxRawDepth];  // how often each raw slot has been filled so far
   unsigned int uses[kMaxStages];  // how often each stage has been filled / consumed so far
   unsigned int tiles;          // commits issued so far on tile_done
+  unsigned int prefetched;     // the first K-blocks of the coming tile were already requested at the end of the previous one
   unsigned long long nz2;      // (-0.0f, -0.0f) as a run-time value (see split2)
 #ifdef ADMMQ_TC_PROFILE
   long long cyc[6];            // producer: cp.async wait, stage_free wait, convert; mma: full wait, issue; all: tile_done wait
@@ -230,10 +240,14 @@ __device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, float neg_
   const unsigned int tmem_cols = kTmemCols;
   asm("mov.b64 %0, {%1, %1};" : "=l"(st.nz2) : "f"(neg_zero));
   if (threadIdx.x == 0) {
-    for (int d = 0; d < kRawDepth; ++d) mbar_init(&pipe.raw_full[d], 1);
+    for (int d = 0; d < kMaxRawDepth; ++d) {
+      mbar_init(&pipe.raw_full[d], 1);
+      mbar_init(&pipe.raw_free[d], kConverters);
+    }
     for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(&pipe.stage_full[s], kThreadsTC / 32 - 1);
+      mbar_init(&pipe.stage_full[s], kConverters);
       mbar_init(&pipe.stage_free[s], 1);
+      mbar_init(&pipe.b_full[s], 1);
     }
     mbar_init(&pipe.tile_done, 1);
     fence_barrier_init();
@@ -243,8 +257,9 @@ __device__ __forceinline__ void pipe_setup(Pipe& pipe, PipeState& st, float neg_
   __syncthreads();
   tc_fence_after();
   for (int s = 0; s < kMaxStages; ++s) st.uses[s] = 0u;
-  for (int d = 0; d < kRawDepth; ++d) st.raw_uses[d] = 0u;
+  for (int d = 0; d < kMaxRawDepth; ++d) st.raw_uses[d] = 0u;
   st.tiles = 0u;
+  st.prefetched = 0u;
 #ifdef ADMMQ_TC_PROFILE
   for (int i = 0; i < 6; ++i) st.cyc[i] = 0;
 #endif
@@ -264,51 +279,61 @@ __device__ __forceinline__ void tmem_store4(unsigned int taddr, const float4 v) 
                : "memory");
 }
 
-// One 128 x BN tile: the 128 rows of A starting at a_row0 against the BN rows of B starting at b_row0, over K
-// columns.  tmA / tmB are TMA descriptors of the two row-major float32 matrices with boxes {32, 128} and {32, BN}
-// (make_operand_tmap); rows and columns outside the matrices read as zero.
-// On return the accumulator is complete in TMEM (columns [0, BN) at pipe.tmem_base) and visible to every thread.
+// One 128 x bn tile (bn <= BN, a multiple of 16): the 128 rows of A starting at a_row0 against the bn rows of B starting
+// at b_row0, over K columns.  tmA / tmB are TMA descriptors of the row-major float32 matrices with boxes {32, 128} and
+// {32, bn} (make_operand_tmap); rows and columns outside the matrices read as zero.  With PS the B operand comes
+// pre-split: tmB = hi part, tmBlo = lo part (both tf32-valued float32, same shape and box).
+// On return the accumulators are complete in TMEM and visible to every thread (load_acc / acc_to_smem).
 //
-// Roles: warp 15 issues MMAs and TMA loads.  Warps 0..14 convert: warp w writes TMEM lanes 32 * (w % 4) .. +31; the
-// 8 chunks (4 k-columns each) of a K-block row are split 2/2/2/2 over the four warps of quarters 0-2 and 3/3/2 over
-// warps 3, 7, 11 of quarter 3; the B chunks go to the twelve warps of quarters 0-2.
-template <int BN>
-__device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMap* tmB, int b_row0, int K,
-                            unsigned char* smem_tiles, Pipe& pipe, PipeState& st) {
-  using TS = TileSmem<BN>;
+// Roles: warp 15 issues MMAs and the TMA loads of the raw ring.  Warps 0..14 convert: warp w writes TMEM lanes
+// 32 * (w % 4) .. +31; the 16 chunks (4 k-columns each) of a K-block row are split 4/4/4/4 over the four warps of
+// quarters 0-2 and 6/5/5 over warps 3, 7, 11 of quarter 3; without PS the B chunks go to the twelve warps of quarters
+// 0-2, with PS warp 0 issues the TMA loads of B hi / lo into the stage as soon as the tensor pipe has released it.
+// next_a_row0 / next_b_row0 >= 0 name the tile this CTA computes next: its first K-blocks are requested as soon as this
+// tile no longer needs the buffers, so that the TMA latency overlaps the caller's epilogue.
+//
+// Roles (16 warps):
+//   warp 15  MMA: waits for a stage (A hi/lo in tensor memory from the converters, B hi/lo in shared memory), issues
+//            the 24 MMAs of the K-block, commits them to stage_free
+//   warp 14  TMA: keeps the raw ring (float32 K-blocks of A, and of B without PS) and, with PS, the B hi/lo halves of the
+//            operand stages filled; a slot / stage is refilled as soon as its previous content has been consumed
+//            (measured: issuing the TMA loads from the MMA warp or from a converting warp stalls that warp for ~75
+//            cycles per load and makes it the straggler of every K-block)
+//   14 converters (warps 0 .. 13): warp w writes TMEM lanes 32 * (w % 4) .. +31; the 16 chunks (4 k-columns each) of a K-block row are
+//            split 4/4/4/4 over the four warps of quarters 0-1 and 6/5/5 over the three warps of quarters 2-3; without
+//            PS the B chunks are split over all converters
+// Barrier phases: K-block j of this tile is fill number st.uses[j % kStages] + j / kStages + 1 of its stage (st.uses =
+// fills before this tile, the same in every thread), raw slots likewise with st.raw_uses; nothing is mutated inside
+// the loops, every thread adds the tile's counts at the end.
+template <int BN, bool PS>
+__device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMap* tmB, const CUtensorMap* tmBlo,
+                            int b_row0, int bn, int K, unsigned char* smem_tiles, Pipe& pipe, PipeState& st,
+                            int next_a_row0 = -1, int next_b_row0 = -1) {
+  using TS = TileSmem<BN, PS>;
   constexpr int kChunksB = BN * 8 * kAtoms;  // 16-byte chunks of B per K-block
   constexpr int kRowChunks = 8 * kAtoms;     // 16-byte chunks per row per K-block
+  constexpr int kNS = TS::kStages;
+  constexpr int kRawDepth = TS::kRawDepth;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const unsigned int tiles_base = (smem_u32(smem_tiles) + 1023u) & ~1023u;
   unsigned char* tiles_ptr = smem_tiles + (tiles_base - smem_u32(smem_tiles));
-  const unsigned int raw_base = tiles_base + (unsigned int)(TS::kStages * TS::kStageBytes);
-  unsigned char* raw_ptr = tiles_ptr + (size_t)TS::kStages * TS::kStageBytes;
+  const unsigned int raw_base = tiles_base + (unsigned int)(kNS * TS::kStageBytes);
+  unsigned char* raw_ptr = tiles_ptr + (size_t)kNS * TS::kStageBytes;
   const int nkb = (K + kBlockK - 1) / kBlockK;
   const unsigned int tmem = pipe.tmem_base;  // keep in a register: the asm memory clobbers would re-read it
+  const unsigned int b_atom_tx = (unsigned int)(bn * 128);  // bytes one TMA box of B delivers
+  // parity of the phase that completes with fill number n (n = 1, 2, ...) of a barrier: (n - 1) & 1
+  auto fills_before = [&](int j) { return st.uses[j % kNS] + (unsigned int)(j / kNS); };        // stage fills before K-block j
+  auto raw_before = [&](int j) { return st.raw_uses[j % kRawDepth] + (unsigned int)(j / kRawDepth); };
 
   if (warp == kMmaWarp) {
-    // ---------------- MMA + TMA warp: the whole warp runs the loop, one elected lane issues
-    const unsigned int idesc = make_idesc<BN>();
-    auto fetch = [&](int kb) {  // elected lane only
-      const int d = kb % kRawDepth;
-      const unsigned int slot = raw_base + (unsigned int)(d * TS::kRawBytes);
-      mbar_expect_tx(&pipe.raw_full[d], (unsigned int)TS::kRawBytes);
-#pragma unroll
-      for (int a = 0; a < kAtoms; ++a) {
-        tma_load_2d(slot + (unsigned int)(a * TS::kAAtomBytes), tmA, kb * kBlockK + a * kAtomK, a_row0, &pipe.raw_full[d]);
-        tma_load_2d(slot + (unsigned int)(TS::kABytes + a * TS::kBAtomBytes), tmB, kb * kBlockK + a * kAtomK, b_row0,
-                    &pipe.raw_full[d]);
-      }
-    };
-    if (elect_one()) {
-      for (int d = 0; d < kRawDepth; ++d)
-        if (d < nkb) fetch(d);
-    }
-    __syncwarp();
+    // ---------------- MMA warp: the whole warp runs the loop, one elected lane issues
+    const unsigned int idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned int)(bn >> 3) << 17) | ((unsigned int)(kTileM >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % TS::kStages;
-      { TC_T0(); mbar_wait(&pipe.stage_full[s], st.uses[s] & 1u); TC_ACC(3); }
-      st.uses[s] += 1u;
+      const int s = kb % kNS;
+      const unsigned int par = fills_before(kb) & 1u;
+      { TC_T0(); mbar_wait(&pipe.stage_full[s], par); TC_ACC(3); }
+      if constexpr (PS) { TC_T0(); mbar_wait(&pipe.b_full[s], par); TC_ACC(0); }
       tc_fence_after();
       TC_T0();
       const unsigned int a_col = tmem + (unsigned int)(TS::kAccCols + s * kStageCols);
@@ -326,41 +351,106 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
           for (int ks = 0; ks < kAtomK / kUmmaK; ++ks) {
             const unsigned long long adv = (unsigned long long)((ks * kUmmaK * 4) >> 4);  // +32 bytes per k-step
             const unsigned int a_hi = a_col + (unsigned int)(a * kAtomK + ks * kUmmaK), a_lo = a_hi + (unsigned int)kBlockK;
-            // three independent accumulators, added small terms first by the epilogue: besides shortening the
-            // dependent chain this keeps the lo terms from being absorbed into the large hi.hi sums
+            // the small cross terms get their own accumulator (added to hi.hi by the epilogue): this keeps them from
+            // being absorbed into the large hi.hi sums and halves the dependent chain on each accumulator
             const unsigned int acc = (a | ks) != 0 ? 1u : first;
-            umma_tf32_ts(tmem + 2u * TS::kAccStride, a_lo, b_hi + adv, idesc, acc);
-            umma_tf32_ts(tmem + 1u * TS::kAccStride, a_hi, b_lo + adv, idesc, acc);
+            umma_tf32_ts(tmem + (unsigned int)TS::kAccStride, a_lo, b_hi + adv, idesc, acc);
+            umma_tf32_ts(tmem + (unsigned int)TS::kAccStride, a_hi, b_lo + adv, idesc, 1u);
             umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
           }
         }
         umma_commit(free_bar);
         if (last) umma_commit(done_bar);
-        // every producer has finished reading raw slot kb % kRawDepth (stage_full completed): refill it
-        if (kb + kRawDepth < nkb) fetch(kb + kRawDepth);
       }
       __syncwarp();
       TC_ACC(4);
     }
+  } else if (warp == kTmaWarp) {
+    // ---------------- TMA warp (one elected lane works)
+    if (elect_one()) {
+      auto fetch_raw = [&](int j, int arow, int brow) {  // K-block j of the tile with rows arow / brow into slot j % kRawDepth
+        const int d = j % kRawDepth;
+        const unsigned int slot = raw_base + (unsigned int)(d * TS::kRawBytes);
+        mbar_expect_tx(&pipe.raw_full[d], (unsigned int)TS::kABytes + (PS ? 0u : (unsigned int)kAtoms * b_atom_tx));
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a) {
+          tma_load_2d(slot + (unsigned int)(a * TS::kAAtomBytes), tmA, j * kBlockK + a * kAtomK, arow, &pipe.raw_full[d]);
+          if constexpr (!PS)
+            tma_load_2d(slot + (unsigned int)(TS::kABytes + a * TS::kBAtomBytes), tmB, j * kBlockK + a * kAtomK, brow,
+                        &pipe.raw_full[d]);
+        }
+      };
+      auto fetch_b = [&](int j, int brow) {  // PS: B hi / lo of K-block j into stage j % kNS
+        const int s = j % kNS;
+        const unsigned int sb = tiles_base + (unsigned int)(s * TS::kStageBytes);
+        mbar_expect_tx(&pipe.b_full[s], 2u * (unsigned int)kAtoms * b_atom_tx);
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a) {
+          tma_load_2d(sb + (unsigned int)(a * TS::kBAtomBytes), tmB, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
+          tma_load_2d(sb + (unsigned int)(TS::kBBytes + a * TS::kBAtomBytes), tmBlo, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
+        }
+      };
+      const int npre_raw = min(kRawDepth, nkb), npre_b = min(kPrefetchB, nkb);
+      unsigned int raw_fills[kRawDepth];  // fills of each raw slot so far (previous tiles + this one)
+#pragma unroll
+      for (int d = 0; d < kRawDepth; ++d) raw_fills[d] = st.raw_uses[d];
+      // kb runs past nkb by kRawDepth: those steps request the next tile's first K-blocks (slot order restarts with
+      // every tile, so the previous user of a slot is tracked per slot, not per K-block)
+      for (int kb = 0; kb < nkb + kRawDepth; ++kb) {
+        const bool cur = kb < nkb;
+        const int j = cur ? kb : kb - nkb;
+        const int d = j % kRawDepth;
+        if (cur && st.prefetched != 0u && kb < npre_raw) {
+          raw_fills[d] += 1u;  // requested at the end of the previous tile
+        } else if (cur || (next_a_row0 >= 0 && j < npre_raw)) {
+          // raw slot d is free once every converter warp has read its previous content
+          if (raw_fills[d] > 0u) mbar_wait(&pipe.raw_free[d], (raw_fills[d] - 1u) & 1u);
+          if (cur) {
+            fetch_raw(j, a_row0, b_row0);
+            raw_fills[d] += 1u;
+          } else {
+            fetch_raw(j, next_a_row0, next_b_row0);
+          }
+        }
+        if constexpr (PS) {
+          // stage kb % kNS: free once the MMAs of its previous fill have completed
+          if (cur && !(st.prefetched != 0u && kb < npre_b)) {
+            const unsigned int fb = fills_before(kb);
+            if (fb > 0u) mbar_wait(&pipe.stage_free[kb % kNS], (fb - 1u) & 1u);
+            fetch_b(kb, b_row0);
+          }
+        }
+      }
+      if constexpr (PS) {
+        // every MMA of this tile has completed => all stages are free: B hi / lo of the next tile's first K-blocks go
+        // into stages 0 .. kPrefetchB-1 (the caller's epilogue parks the accumulator in the LAST stage)
+        if (next_a_row0 >= 0) {
+          mbar_wait(&pipe.tile_done, st.tiles & 1u);
+          for (int j = 0; j < npre_b; ++j) fetch_b(j, next_b_row0);
+        }
+      }
+    }
+    __syncwarp();
   } else {
-    // ---------------- producers
+    // ---------------- converters
     const int q = warp & 3, kgi = warp >> 2;
     const int ar = q * 32 + lane;  // tile row = TMEM lane of this thread
-    // chunks (4 k-columns each) of the row this thread converts: 4/4/4/4 in quarters 0-2, 6/5/5 over warps 3, 7, 11
-    const int c_begin = (q == 3) ? (kgi == 0 ? 0 : 1 + 5 * kgi) : kgi * (kRowChunks / 4);
-    const int c_count = (q == 3) ? (kgi == 0 ? 6 : 5) : kRowChunks / 4;
+    // chunks (4 k-columns each) of the row this thread converts: 4/4/4/4 in quarters 0-1, 6/5/5 in quarters 2-3
+    const int c_begin = (q >= 2) ? (kgi == 0 ? 0 : 1 + 5 * kgi) : kgi * (kRowChunks / 4);
+    const int c_count = (q >= 2) ? (kgi == 0 ? 6 : 5) : kRowChunks / 4;
     const unsigned int lane_addr = tmem + ((unsigned int)(q * 32) << 16);
-    // B chunk ids handled by this thread: bi0, bi0 + 384, ... (warps of quarters 0-2)
-    const int bi0 = (q == 3) ? kChunksB : (kgi * 3 + q) * 32 + lane;
+    // without PS: B chunk ids handled by this thread: bi0, bi0 + 14 * 32, ...
+    const int cw = (q >= 2) ? 8 + (q - 2) * 3 + kgi : q * 4 + kgi;  // converter index 0 .. 13
+    const int bi0 = cw * 32 + lane;
     for (int kb = 0; kb < nkb; ++kb) {
       const int d = kb % kRawDepth;
-      { TC_T0(); mbar_wait(&pipe.raw_full[d], (st.raw_uses[d] + (unsigned int)(kb / kRawDepth)) & 1u); TC_ACC(0); }  // K-block kb has landed
-      const int s = kb % TS::kStages;
-      { TC_T0(); if (st.uses[s] > 0u) { mbar_wait(&pipe.stage_free[s], (st.uses[s] - 1u) & 1u); tc_fence_after(); } TC_ACC(1); }
+      const int s = kb % kNS;
+      const unsigned int fb = fills_before(kb);
+      { TC_T0(); if (fb > 0u) { mbar_wait(&pipe.stage_free[s], (fb - 1u) & 1u); tc_fence_after(); } TC_ACC(1); }
+      { TC_T0(); mbar_wait(&pipe.raw_full[d], raw_before(kb) & 1u); TC_ACC(0); }  // K-block kb has landed
       TC_T0();
       const unsigned char* raw = raw_ptr + (size_t)d * TS::kRawBytes;
       const unsigned int col0 = lane_addr + (unsigned int)(TS::kAccCols + s * kStageCols);
-#ifndef TC_EXP_NO_A
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         if (i < c_count) {
@@ -372,41 +462,43 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
           tmem_store4(col0 + (unsigned int)(kBlockK + c * 4), lo);
         }
       }
-#endif
-      unsigned char* stage = tiles_ptr + (size_t)s * TS::kStageBytes;
-#ifndef TC_EXP_NO_B
-      for (int bi = bi0; bi < kChunksB; bi += 384) {
-        const int atom = bi / (BN * 8), lid = bi % (BN * 8);
-        const unsigned int off = (unsigned int)(atom * TS::kBAtomBytes) + sw128(lid >> 3, lid & 7);
-        const float4 v = *reinterpret_cast<const float4*>(raw + TS::kABytes + off);
-        float4 hi, lo;
-        split4(v, st.nz2, hi, lo);
-        *reinterpret_cast<float4*>(stage + off) = hi;
-        *reinterpret_cast<float4*>(stage + TS::kBBytes + off) = lo;
+      if constexpr (!PS) {
+        unsigned char* stage = tiles_ptr + (size_t)s * TS::kStageBytes;
+        for (int bi = bi0; bi < kChunksB; bi += kConverters * 32) {
+          const int atom = bi / (BN * 8), lid = bi % (BN * 8);
+          const unsigned int off = (unsigned int)(atom * TS::kBAtomBytes) + sw128(lid >> 3, lid & 7);
+          const float4 v = *reinterpret_cast<const float4*>(raw + TS::kABytes + off);
+          float4 hi, lo;
+          split4(v, st.nz2, hi, lo);
+          *reinterpret_cast<float4*>(stage + off) = hi;
+          *reinterpret_cast<float4*>(stage + TS::kBBytes + off) = lo;
+        }
       }
-#endif
-#ifndef TC_EXP_NO_A
       tmem_store_wait();
-#endif
       tc_fence_before();
-#ifndef TC_EXP_NO_FENCE
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-#endif
+      if constexpr (!PS) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pipe.stage_full[s]);
+      if (lane == 0) {
+        mbar_arrive(&pipe.raw_free[d]);
+        mbar_arrive(&pipe.stage_full[s]);
+      }
       TC_ACC(2);
-      st.uses[s] += 1u;
     }
   }
-  // raw slot use counts advance identically in both roles (fills == consumptions)
-  for (int kb = 0; kb < nkb; ++kb) st.raw_uses[kb % kRawDepth] += 1u;
   { TC_T0(); mbar_wait(&pipe.tile_done, st.tiles & 1u); TC_ACC(5); }
+  // the tile's fills, identically in every thread
+  for (int kb = 0; kb < nkb; ++kb) {
+    st.uses[kb % kNS] += 1u;
+    st.raw_uses[kb % kRawDepth] += 1u;
+  }
   st.tiles += 1u;
   tc_fence_after();
+  st.prefetched = next_a_row0 >= 0 ? 1u : 0u;
 }
 
 // Accumulator read-back for the calling warp: TMEM lanes 32 * (warp % 4) .. +31 (= tile rows), BN / 4 columns
 // starting at (warp / 4) * BN / 4.  v[i] = D[row = 32 * (warp % 4) + lane][col0 + i] = (lo.hi + hi.lo) + hi.hi.
+// (kAccStride does not depend on PS.)
 template <int N>
 __device__ __forceinline__ void tmem_load(unsigned int taddr, unsigned int r[N]) {
   if constexpr (N == 8) {
@@ -435,12 +527,11 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
   row = q * 32 + lane;
   col0 = cgp * (BN / 4);
   const unsigned int taddr = pipe.tmem_base + ((unsigned int)(q * 32) << 16) + (unsigned int)col0;
-  unsigned int hh[BN / 4], hl[BN / 4], lh[BN / 4];
+  unsigned int hh[BN / 4], cr[BN / 4];
   tmem_load<BN / 4>(taddr, hh);
-  tmem_load<BN / 4>(taddr + 1u * TileSmem<BN>::kAccStride, hl);
-  tmem_load<BN / 4>(taddr + 2u * TileSmem<BN>::kAccStride, lh);
+  tmem_load<BN / 4>(taddr + (unsigned int)TileSmem<BN>::kAccStride, cr);
 #pragma unroll
-  for (int i = 0; i < BN / 4; ++i) v[i] = (__uint_as_float(lh[i]) + __uint_as_float(hl[i])) + __uint_as_float(hh[i]);
+  for (int i = 0; i < BN / 4; ++i) v[i] = __uint_as_float(cr[i]) + __uint_as_float(hh[i]);
 }
 
 // all accumulator reads of this tile are done: the next tile may overwrite TMEM
@@ -451,28 +542,34 @@ __device__ __forceinline__ void release_acc() {
 
 // Epilogue staging.  A thread holds one ROW of the accumulator (TMEM lane = row), so writing results straight to
 // row-major global memory touches 32 different rows per warp instruction (4 useful bytes per 32-byte sector, measured
-// ~6-8 k cycles per 128 x 64 tile).  acc_to_smem() parks the tile in shared memory instead - rows of BN + 4 floats
-// (the pad keeps the per-row float4 stores conflict free) in the operand stage buffers, which are idle once tile_done
-// has completed - releases the accumulator and returns the tile, so that the caller can walk it in row-contiguous
-// float4 groups (thread t -> group t, t + 512, ...; group g = row g / (BN / 4), columns 4 (g % (BN / 4)) .. +3).  The
-// caller must __syncthreads() after its last read and before the next tile_3xtf32().
+// ~6-8 k cycles per 128 x 64 tile).  acc_to_smem() parks the tile in shared memory instead - in the LAST operand
+// stage, which is idle once tile_done has completed and is not a target of the cross-tile prefetch - releases the
+// accumulator and returns the tile, so that the caller can walk it in row-contiguous float4 groups (thread t -> group
+// t, t + 512, ...; group g = row g / (BN / 4), columns 4 (g % (BN / 4)) .. +3, at EpiTile::offset(row, g % (BN / 4))).
+// The caller must __syncthreads() after its last read and before the next tile_3xtf32().
 template <int BN>
 struct EpiTile {
-  static constexpr int kLd = BN + 4;
   static constexpr int kGroupsPerRow = BN / 4;
   static constexpr int kGroups = kTileM * kGroupsPerRow;
-  static_assert(kTileM * kLd * 4 <= TileSmem<BN>::kStages * TileSmem<BN>::kStageBytes, "staging tile must fit in the operand stages");
+  static_assert(kTileM * BN * 4 <= TileSmem<BN>::kStageBytes, "staging tile must fit in one operand stage");
+  // float offset of float4 group g of `row`: rows of BN floats, groups XOR-swizzled so that both the per-row writes
+  // (32 rows per warp) and the row-contiguous reads are bank-conflict free without padding
+  __device__ static __forceinline__ int offset(int row, int g) {
+    const int sw = (BN == 16) ? ((row >> 1) & 3) : (row & 7);
+    return row * BN + ((g ^ sw) << 2);
+  }
 };
-template <int BN>
+template <int BN, bool PS>
 __device__ __forceinline__ const float* acc_to_smem(const Pipe& pipe, unsigned char* smem_tiles) {
+  using TS = TileSmem<BN, PS>;
   const unsigned int tiles_base = (smem_u32(smem_tiles) + 1023u) & ~1023u;
-  float* tile = reinterpret_cast<float*>(smem_tiles + (tiles_base - smem_u32(smem_tiles)));
+  float* tile = reinterpret_cast<float*>(smem_tiles + (tiles_base - smem_u32(smem_tiles)) + (size_t)(TS::kStages - 1) * TS::kStageBytes);
   float v[BN / 4];
   int row, col0;
   load_acc<BN>(pipe, v, row, col0);
-  float* dst = tile + row * EpiTile<BN>::kLd + col0;
 #pragma unroll
-  for (int c = 0; c < BN / 4; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  for (int c = 0; c < BN / 4; c += 4)
+    *reinterpret_cast<float4*>(tile + EpiTile<BN>::offset(row, (col0 + c) >> 2)) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
   release_acc();
   return tile;
 }
