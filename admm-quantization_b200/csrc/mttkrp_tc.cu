@@ -12,10 +12,10 @@
 #include <algorithm>
 #include "common.cuh"
 
-extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int ldb, int N, int K, float* C, int ldc,
-                             void* stream);
-
 namespace admmq {
+
+int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, int ldb, int N, int K, float* C, int ldc,
+            cudaStream_t stream);  // tc_gemm.cu
 
 constexpr int kTT = 256;
 
@@ -38,9 +38,12 @@ __global__ void __launch_bounds__(kTT) k_permute_myx(const float* __restrict__ W
   }
 }
 
-// out[c, r] = in[r, c]  (rows x cols -> cols x rows, leading dimension ldo), zero-filling columns [rows, ldo)
-__global__ void __launch_bounds__(kTT) k_transpose(const float* __restrict__ in, int rows, int cols,
-                                                  float* __restrict__ out, int ldo) {
+// out[c, r] = in[r, c]  (rows x cols -> cols x rows, leading dimension ldo), zero-filling columns [rows, ldo), split
+// into the tf32 hi / lo parts the tensor-core product takes as its pre-split B operand (Veltkamp split as in
+// tc_gemm.cuh::split2; neg_zero = -0.0f as a run-time value keeps the product from being contracted away)
+__global__ void __launch_bounds__(kTT) k_transpose_split(const float* __restrict__ in, int rows, int cols,
+                                                        float* __restrict__ out, float* __restrict__ out_lo, int ldo,
+                                                        float neg_zero) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -51,7 +54,13 @@ __global__ void __launch_bounds__(kTT) k_transpose(const float* __restrict__ in,
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const int cc = c0 + r, rr = r0 + tx;
-    if (cc < cols && rr < ldo) out[(size_t)cc * ldo + rr] = (rr < rows) ? tile[tx][r] : 0.0f;
+    if (cc < cols && rr < ldo) {
+      const float x = (rr < rows) ? tile[tx][r] : 0.0f;
+      const float tt = __fmaf_rn(x, 8193.0f, neg_zero);
+      const float hi = __fsub_rn(tt, __fsub_rn(tt, x));
+      out[(size_t)cc * ldo + rr] = hi;
+      out_lo[(size_t)cc * ldo + rr] = __fsub_rn(x, hi);
+    }
   }
 }
 
@@ -71,7 +80,7 @@ static size_t tc_layout(int M, int nx, int ny, int R, size_t* xt_off, size_t* t_
   const size_t ldx = (size_t)(nx + 3) / 4 * 4;
   size_t off = 0;
   *xt_off = off;
-  off += align_up((size_t)R * ldx * sizeof(float), 256);
+  off += 2 * align_up((size_t)R * ldx * sizeof(float), 256);  // hi and lo parts of X^T
   *t_off = off;
   if (ny > 1) off += align_up((size_t)M * ny * R * sizeof(float), 256);
   return off;
@@ -92,12 +101,13 @@ int mttkrp_tc(const float* V, int M, const float* X, int nx, const float* Y, int
     return fail(ADMMQ_E_WORKSPACE, "admmq_mttkrp_tc: workspace needs %zu bytes, 256-byte aligned", need);
   const int ldx = (nx + 3) / 4 * 4;
   float* Xt = (float*)((char*)workspace + xt_off);
+  float* XtLo = (float*)((char*)workspace + xt_off + align_up((size_t)R * ldx * sizeof(float), 256));
   float* T = (ny > 1) ? (float*)((char*)workspace + t_off) : F;
   dim3 tg((R + 31) / 32, (ldx + 31) / 32);
-  k_transpose<<<tg, kTT, 0, stream>>>(X, nx, R, Xt, ldx);  // Xt (R x ldx) = X^T, pad columns zero
+  k_transpose_split<<<tg, kTT, 0, stream>>>(X, nx, R, Xt, XtLo, ldx, -0.0f);  // (R x ldx) = X^T, pad columns zero
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);
-  if (int e = admmq_gemm_nt(V, ldx, M * ny, Xt, ldx, R, nx, T, R, (void*)stream)) return e;
+  if (int e = gemm_nt(V, ldx, M * ny, Xt, XtLo, ldx, R, nx, T, R, stream)) return e;
   if (ny > 1) {
     const long long n = (long long)M * R;
     k_fold_y<<<(int)std::min<long long>((n + kTT - 1) / kTT, 148 * 8), kTT, 0, stream>>>(T, M, ny, R, R, Y, F);

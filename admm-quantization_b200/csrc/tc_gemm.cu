@@ -32,10 +32,10 @@ int make_operand_tmap(CUtensorMap* out, const float* base, int rows, int cols, i
 }  // namespace tc
 
 struct GemmMaps {
-  CUtensorMap a, b;
+  CUtensorMap a, b, blo;  // blo: lo part of a pre-split B (PS), otherwise unused
 };
 
-template <int BN>
+template <int BN, bool PS>
 __global__ void __launch_bounds__(tc::kThreadsTC, 1)
 k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* __restrict__ C, int ldc, float neg_zero) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -47,9 +47,9 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * BN;
     const int next = tile + (int)gridDim.x;
     const bool has_next = next < tilesM * tilesN;
-    tc::tile_3xtf32<BN, false>(&maps.a, i0, &maps.b, nullptr, n0, BN, K, smem_dyn, pipe, st,
+    tc::tile_3xtf32<BN, PS>(&maps.a, i0, &maps.b, &maps.blo, n0, BN, K, smem_dyn, pipe, st,
                                has_next ? (next / tilesN) * tc::kTileM : -1, has_next ? (next % tilesN) * BN : -1);
-    const float* tile_c = tc::acc_to_smem<BN, false>(pipe, smem_dyn);
+    const float* tile_c = tc::acc_to_smem<BN, PS>(pipe, smem_dyn);
     using ET = tc::EpiTile<BN>;
     const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
@@ -75,22 +75,27 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
   tc::pipe_teardown(pipe);
 }
 
-}  // namespace admmq
+template <int BN, bool PS>
+static int launch_gemm(const GemmMaps& maps, int M, int N, int K, float* C, int ldc, int grid, cudaStream_t stream) {
+  const int smem = tc::TileSmem<BN, PS>::kBytes;
+  ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<BN, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_gemm_nt_tc<BN, PS><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
+  return ADMMQ_OK;
+}
 
-using namespace admmq;
-
-extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int ldb, int N, int K, float* C, int ldc,
-                             void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// C = A . B^T.  B either as one float32 matrix (Blo == nullptr; split into tf32 hi / lo tile by tile on the fly) or
+// pre-split by the caller into B (hi part) and Blo (lo part), both tf32-valued float32 with the same layout.
+int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, int ldb, int N, int K, float* C, int ldc,
+            cudaStream_t stream) {
   if (A == nullptr || B == nullptr || C == nullptr || M <= 0 || N <= 0 || K <= 0)
     return fail(ADMMQ_E_BADARG, "admmq_gemm_nt: null pointer or empty shape");
-  if ((lda & 3) || (ldb & 3) || lda < K || ldb < K || ldc < N || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
+  if ((lda & 3) || (ldb & 3) || lda < K || ldb < K || ldc < N || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)Blo & 15))
     return fail(ADMMQ_E_BADARG, "admmq_gemm_nt: lda/ldb must be multiples of 4 and >= K, A/B 16-byte aligned, ldc >= N");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;
   if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "admmq_gemm_nt needs an sm_100 device (tcgen05)");
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM;
-  // widest tile that still gives every SM one: a wider MMA costs the issuing thread the same ~28 cycles
+  // widest tile that still gives every SM one (a tile's cost is dominated by staging its 128 rows of A)
   const int bn = ((long long)tilesM * ((N + 63) / 64) >= dp.sm_count) ? 64
                                                                        : ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count ? 32 : 16);
   const int tiles = tilesM * ((N + bn - 1) / bn);
@@ -98,20 +103,28 @@ extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int
   GemmMaps maps;
   if (int e = tc::make_operand_tmap(&maps.a, A, M, K, lda, tc::kTileM)) return e;
   if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
-  if (bn == 64) {
-    const int smem = tc::TileSmem<64>::kBytes;
-    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
-  } else if (bn == 32) {
-    const int smem = tc::TileSmem<32>::kBytes;
-    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<32><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
+  if (int e = tc::make_operand_tmap(&maps.blo, Blo != nullptr ? Blo : B, N, K, ldb, bn)) return e;
+  int e = ADMMQ_OK;
+  if (Blo != nullptr) {
+    e = bn == 64 ? launch_gemm<64, true>(maps, M, N, K, C, ldc, grid, stream)
+                 : (bn == 32 ? launch_gemm<32, true>(maps, M, N, K, C, ldc, grid, stream)
+                             : launch_gemm<16, true>(maps, M, N, K, C, ldc, grid, stream));
   } else {
-    const int smem = tc::TileSmem<16>::kBytes;
-    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_gemm_nt_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gemm_nt_tc<16><<<grid, tc::kThreadsTC, smem, stream>>>(maps, M, N, K, C, ldc, -0.0f);
+    e = bn == 64 ? launch_gemm<64, false>(maps, M, N, K, C, ldc, grid, stream)
+                 : (bn == 32 ? launch_gemm<32, false>(maps, M, N, K, C, ldc, grid, stream)
+                             : launch_gemm<16, false>(maps, M, N, K, C, ldc, grid, stream));
   }
+  if (e) return e;
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return ADMMQ_OK;
+}
+
+}  // namespace admmq
+
+using namespace admmq;
+
+extern "C" int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int ldb, int N, int K, float* C, int ldc,
+                             void* stream_) {
+  return gemm_nt(A, lda, M, B, nullptr, ldb, N, K, C, ldc, (cudaStream_t)stream_);
 }
