@@ -215,7 +215,8 @@ ADMMQ_HD float mse_from_fixed(long long fixed_sum, double unit, float n_elems_f)
 // which needs C and P at (2q-1) * num_attempts thresholds instead of num_attempts evaluations per element.  C is an
 // integer, P is accumulated in 64-bit fixed point (x rounded to 2^-41 of the power of two above absmax), the bracket is
 // evaluated in float64 and converted to the fixed-point unit of the per-candidate accumulators, so the result is
-// independent of grid size, chunking and arrival order.  It is the exact real-number value of the reference's
+// independent of arrival order (bit-reproducible) and depends on the chunking only through the fixed-point rounding
+// of the per-chunk terms (~1e-13 relative).  It is the exact real-number value of the reference's
 // sum((x - xq)**2) up to ~1e-12 relative; the reference's own float32 evaluation of that sum carries ~1e-7.
 ADMMQ_HD unsigned int f32_bits(float f) {
 #if defined(__CUDA_ARCH__)

@@ -1,31 +1,27 @@
 // tc_gemm.cuh - 3xTF32 tile product on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
-//   D[128 x BN] (TMEM, float32) = A[128 x K] . B[BN x K]^T          A, B: float32, K-major
+//   D[128 x bn] (TMEM, float32) = A[128 x K] . B[bn x K]^T          A, B: float32, K-major, bn <= BN, bn % 16 == 0
 //
 // Every float32 operand x is split as x = hi + lo + O(2^-22 |x|) with hi = tf32_rn(x), lo = tf32_rn(x - hi), and
-// the tile is accumulated as lo.hi + hi.lo + hi.hi (small terms first) by three tcgen05.mma.kind::tf32
-// per 8-deep k-step into one TMEM accumulator, which keeps float32-level accuracy (the dropped lo.lo term
-// and the split residuals are 2^-22 relative) at 1/3 of the TF32 rate.
+// the tile is accumulated as (lo.hi + hi.lo) + hi.hi by three tcgen05.mma.kind::tf32 per 8-deep k-step: the two
+// cross terms into one TMEM accumulator, hi.hi into another, added small-terms-first by the epilogue.  This keeps
+// float32-level accuracy (the dropped lo.lo term and the split residuals are 2^-22 relative) at 1/3 of the TF32 rate.
 //
 // Operand paths.  Measured on B200: with BOTH operands in shared memory one tcgen05.mma of 128 x N x 8 tf32 costs
 // ~90 cycles for every N <= 64 - the tensor core re-reads the 128-row A slab (32 bytes from each of 128 rows) for
 // every instruction - so narrow tiles, which this path needs to keep 148 SMs busy on 512 x 1141 outputs, were
 // MMA-issue bound.  The A operand therefore lives in TENSOR MEMORY (TS form of tcgen05.mma): lane = tile row,
-// column = k, written there by the producers with tcgen05.st, and only the small B slab (N rows x 32 bytes) is read
-// from shared memory per instruction.
+// column = k, written there by the converter warps with tcgen05.st, and only the small B slab (N rows x 32 bytes) is
+// read from shared memory per instruction (measured 25 / 31 / 38 cycles per MMA at N = 32 / 48 / 64; floor N / 2).
 //
-// Staging (512 threads, all 16 warps produce): warp w owns TMEM lanes 32 * (w % 4) .. +31 (the hardware restricts a
-// warp to its lane quarter) and a share of the k-columns of each 32-deep K-block.  Operands are fetched from
-// global/L2 ONCE as float32 by TMA (cp.async.bulk.tensor, 128B swizzle, out-of-range rows/columns zero-filled by the
-// hardware; 4 K-blocks in flight; LDGSTS-based fetching measured ~1000 cycles per 20 KB K-block and was the
-// bottleneck) into a raw ring in shared memory whose swizzle makes the row-per-lane read-back conflict free;
-// raw_full[d] (expect_tx / complete_tx) publishes a K-block to the CTA.  Each producer thread then splits the chunks of
-// ITS row into hi/lo in registers and
-// stores A to TMEM (tcgen05.st) and B to shared memory in the canonical K-major SWIZZLE_128B layout (row r of a
-// K-block = 128 bytes; 16-byte chunk c of row r is stored at chunk c ^ (r & 7); 8-row groups 1024 bytes apart).
-// full[s] (one arrival per producer warp) hands a stage to warp 15, whose elected lane issues the 12 MMAs of the
-// K-block, commits them to free[s] (which hands the stage back once the tensor pipe has consumed it) and then
-// re-arms the raw slot the producers have just finished with by issuing the TMA loads of K-block k + 4.
+// Staging (512 threads = MMA warp + TMA warp + 14 converter warps, see tile_3xtf32): A is fetched from global/L2 ONCE as
+// float32 by TMA (cp.async.bulk.tensor, 128B swizzle, out-of-range rows/columns zero-filled by the hardware) into a
+// raw ring in shared memory whose swizzle makes the row-per-lane read-back conflict free; each converter thread
+// splits the chunks of ITS row (the hardware restricts a warp to TMEM lanes 32 * (w % 4) .. +31) into hi/lo in
+// registers and stores them to TMEM.  B reaches the operand stage in the canonical K-major SWIZZLE_128B layout (row r
+// of a K-block = 128 bytes; 16-byte chunk c of row r at chunk c ^ (r & 7); 8-row groups 1024 bytes apart) either
+// through the same raw ring + conversion (PS = false) or, when the caller provides it pre-split (PS = true: the
+// operand is constant over many products), by TMA directly.
 #pragma once
 #include <cuda.h>
 #include <cstdint>
