@@ -458,3 +458,73 @@ def test_outer_loop_full_inner_budget_first_sweep(golden_outer, capsys, precisio
     assert abs(err - ref) <= 2e-3 * ref
     assert abs(errq - refq) <= 2e-3 * refq
     assert all(r.iterations == 999 for r in s.last_reports)  # the exit test never fires
+
+
+# ------------------------------------------------------------------ model level (north_star: top-1 on synthetic-calibrated weights)
+class _PrototypeTask:
+    """10-class synthetic image task with a real decision margin: class prototype + unit Gaussian noise."""
+
+    def __init__(self, n_batches, batch_size, seed, device="cuda"):
+        self.n_batches, self.batch_size, self.seed, self.device = n_batches, batch_size, seed, device
+        self.protos = torch.randn(10, 3, 32, 32, generator=torch.Generator().manual_seed(1234))
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        for _ in range(self.n_batches):
+            y = torch.randint(0, 10, (self.batch_size,), generator=g)
+            x = 0.6 * self.protos[y] + torch.randn(self.batch_size, 3, 32, 32, generator=g)
+            yield x.to(self.device), y.to(self.device)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_model_top1_with_our_factors_vs_reference_factors(capsys, precision):
+    """north_star: "ResNet-18 top-1 must stay within 0.1 pp on synthetic-calibrated weights".  A ResNet-18 is trained
+    for a few steps on a synthetic 10-class task (no dataset or checkpoint exists offline), its four layer1
+    convolutions are factorized with the CUDA solver and with the CPU oracle (same weights, same random init,
+    2 sweeps x 30 inner iterations), both factor sets go through source/models.py into CP models, both are
+    BN-calibrated on the same synthetic images (source/utils.py) and scored on 2048 held-out images."""
+    import copy
+    import torchvision
+    from oracle import admm_oracle as orc
+    from source import workloads as wl
+    from source.models import get_submodule, replace_with_cp
+    from source.solver import LayerSolver, layer_weight_as_tensor, rank_from_reduction_rate
+    from source.utils import bncalibrate_model, top1_accuracy
+    torch.set_num_threads(8)
+    torch.manual_seed(42)
+    base = torchvision.models.resnet18(weights=None, num_classes=10).cuda()
+    opt = torch.optim.SGD(base.parameters(), lr=0.05, momentum=0.9)
+    base.train()
+    for x, y in _PrototypeTask(120, 128, seed=5):
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(base(x), y).backward()
+        opt.step()
+    base.eval()
+    acc_base = top1_accuracy(base, _PrototypeTask(32, 64, seed=2), "cuda")
+    ours, ref = copy.deepcopy(base), copy.deepcopy(base)
+    errs = []
+    for path in ("layer1.0.conv1", "layer1.0.conv2", "layer1.1.conv1", "layer1.1.conv2"):
+        W = layer_weight_as_tensor(get_submodule(base, path).weight.detach()).contiguous()
+        R = rank_from_reduction_rate(W, 2.0)
+        init = wl.random_init(W.shape, R, 42)
+        s = LayerSolver(W, [f.cuda() for f in init], 4, MSE, max_iter_admm=30, solve_precision=precision,
+                        mttkrp_precision=precision)
+        for _ in range(2):
+            s.sweep()
+        fac, _, loss, _, _ = orc.factorize(W.cpu(), init, 4, MSE, 2, 30, stop_rules=False)
+        errs.append((round(s.loss_hist[-1], 5), round(loss[-1], 5)))
+        replace_with_cp(ours, path, [f.clone() for f in s.factors], R)
+        replace_with_cp(ref, path, fac, R)
+    accs = []
+    for m in (ours, ref):
+        bncalibrate_model(m, _PrototypeTask(18, 64, seed=1), num_samples=1000, device="cuda")
+        accs.append(top1_accuracy(m, _PrototypeTask(32, 64, seed=2), "cuda"))
+    with capsys.disabled():
+        print(f"\n[top-1] precision {precision}: uncompressed {acc_base:.2f} %, CP model from our factors {accs[0]:.2f} %, "
+              f"CP model from the reference's factors {accs[1]:.2f} % (2048 held-out synthetic images, 4-bit, rr = 2, "
+              f"BN-calibrated); rec_error ours/ref per layer {errs}")
+    for e, l in errs:
+        assert abs(e - l) <= 5e-3 * l       # second sweep, free-running: the reference's own self-divergence is 2e-3 there
+    assert acc_base >= 95.0                      # the synthetic task was learnt: the labels carry a margin
+    assert abs(accs[0] - accs[1]) <= 0.1 + 1e-9  # north_star: within 0.1 pp of the reference
+    torch.set_num_threads(1)

@@ -143,3 +143,57 @@ def test_two_rank_gather_on_gloo_is_bitwise_identical():
         p.join(120)
         assert p.exitcode == 0
     assert out.get() is True
+
+
+# ------------------------------------------------------------------ factor files -> CP model
+def test_cp_layers_reproduce_the_convolution_they_factorize():
+    """reference source/models.py:24-74: conv1 (B^T) -> depthwise conv2 (C) -> conv3 (A, bias) equals the dense
+    convolution with W[o,i,k] = sum_r A[o,r] B[i,r] C[k,r]; same for the two-layer form of a 1x1 convolution."""
+    import torch
+    from source.models import build_cp_layer, build_cp2conv_layer, build_cpfc_layer
+    g = torch.Generator().manual_seed(0)
+    R = 5
+    A, B, C = (torch.randn(n, R, generator=g) for n in (8, 6, 9))
+    conv = torch.nn.Conv2d(6, 8, 3, padding=1, stride=2, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(torch.einsum("or,ir,kr->oik", A, B, C).reshape(8, 6, 3, 3))
+    cp = build_cp_layer(R, [A, B, C], conv.bias.detach(), 6, 8, (3, 3), (1, 1), (2, 2), 1)
+    assert [n for n, _ in cp.named_children()] == ["conv1", "conv2", "conv3"]
+    x = torch.randn(2, 6, 10, 10, generator=g)
+    assert torch.allclose(conv(x), cp(x), atol=1e-4)
+    pw = torch.nn.Conv2d(6, 8, 1, stride=2, bias=False)
+    with torch.no_grad():
+        pw.weight.copy_((A @ B.t())[:, :, None, None])
+    cp2 = build_cp2conv_layer(R, [A, B], None, 6, 8, (0, 0), (2, 2))
+    assert torch.allclose(pw(x), cp2(x), atol=1e-4)
+    fc = build_cpfc_layer(R, [A, B], torch.zeros(8), 6, 8)
+    v = torch.randn(3, 6, generator=g)
+    assert torch.allclose(fc(v), v @ (A @ B.t()).t(), atol=1e-4)
+    with pytest.raises(AssertionError):   # wrong factor shape (reference: the shape asserts of source/models.py:39-41)
+        build_cp_layer(R, [A[:7], B, C], None, 6, 8, (3, 3), (1, 1), (1, 1), 1)
+
+
+def test_replace_calibrate_and_score_on_synthetic_images():
+    """replace_with_cp + bncalibrate_model + top1_accuracy (reference scripts/calibrate.py:161-189,
+    source/utils.py:134-155) on a seeded ResNet-18: exact rank-full factors keep every prediction."""
+    import copy
+    import torch
+    import torchvision
+    from source.models import get_submodule, replace_with_cp
+    from source.utils import SyntheticImages, bncalibrate_model, top1_accuracy
+    torch.manual_seed(3)
+    model = torchvision.models.resnet18(weights=None).eval()
+    teacher = copy.deepcopy(model)
+    w = get_submodule(model, "layer1.0.conv1").weight.detach()          # (64, 64, 3, 3)
+    # an exact CP representation: one component per (input channel, tap) pair
+    cin, taps = 64, 9
+    A = w.reshape(64, cin * taps).clone()
+    B = torch.eye(cin).repeat_interleave(taps, dim=1)
+    C = torch.eye(taps).repeat(1, cin)
+    replace_with_cp(model, "layer1.0.conv1", [A, B, C])
+    ev = SyntheticImages(2, 8, image_size=32, seed=2, labels_from=teacher)
+    assert top1_accuracy(model, ev, "cpu") == 100.0
+    bn_before = model.bn1.running_mean.clone()
+    bncalibrate_model(model, SyntheticImages(3, 8, image_size=32, seed=1), num_samples=16, device="cpu")
+    assert not torch.equal(bn_before, model.bn1.running_mean)            # statistics were re-estimated
+    assert not model.training and all(not p.requires_grad for p in model.parameters())
