@@ -81,8 +81,105 @@ def parafac_als(tensor, rank, n_iter_max=100, tol=1e-8, random_state=None, norma
     return weights, factors
 
 
-def epc_sweep(Y, factors, delta, norm_y2=None):
-    """One error-preserving-correction pass over all modes (the body of musco's `cp_anc`)."""
+def _mu_by_eigh(gamma, T, norm_y2, target):
+    """mu and the new factor through the eigen-decomposition of gamma (reference formulation)."""
+    sig, V = torch.linalg.eigh(gamma)
+    sig = torch.clamp(sig, min=0.0)
+    Tt = T @ V
+    s = (Tt * Tt).sum(dim=0)
+    # residual(mu) = ||Y||^2 - sum_i s_i (sig_i + 2 mu) / (sig_i + mu)^2, increasing in mu: bisection on the host
+    # (numpy: with torch CPU tensors the 200 evaluations cost more than the eigen-decomposition at R < 600)
+    sig_c, s_c = sig.cpu().numpy(), s.cpu().numpy()
+
+    def resid(mu):
+        d = sig_c + mu
+        return norm_y2 - float(np.sum(s_c * (d + mu) / (d * d)))
+
+    floor = float(sig_c.max()) * 1e-14
+    mu = 0.0
+    if resid(floor) < target:
+        lo, hi = floor, max(float(sig_c.max()), 1e-300)
+        while resid(hi) < target and hi < 1e300:
+            hi *= 2.0
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            if resid(mid) < target:
+                lo = mid
+            else:
+                hi = mid
+            if hi - lo <= 1e-15 * hi:
+                break
+        mu = 0.5 * (lo + hi)
+    mu = max(mu, floor)
+    return mu, (Tt / (sig + mu)) @ V.T
+
+
+def _mu_by_cholesky(gamma, T, norm_y2, target, mu0):
+    """The same root without an eigen-decomposition: with M = gamma + mu I and S = T^T T,
+        residual(mu)  = ||Y||^2 - tr(M^-1 S M^-1 (gamma + 2 mu I)),      residual'(mu) = 2 mu tr(M^-1 S M^-1 M^-1),
+    three Cholesky solves per evaluation; safeguarded Newton from the previous visit's mu.  Returns None when the
+    constraint is inactive or M is numerically singular (the caller then takes the eigh path)."""
+    R = gamma.shape[0]
+    eye = torch.eye(R, dtype=gamma.dtype, device=gamma.device)
+    S = T.T @ T
+    scale = float(torch.trace(gamma)) / R
+
+    def evaluate(mu):
+        L, info = torch.linalg.cholesky_ex(gamma + mu * eye)
+        if int(info) != 0:
+            return None
+        W2 = torch.cholesky_solve(torch.cholesky_solve(S, L).T.contiguous(), L)       # M^-1 S M^-1
+        W3 = torch.cholesky_solve(W2, L)
+        vals = torch.stack([(gamma * W2).sum() + 2.0 * mu * torch.trace(W2), torch.trace(W3)]).cpu()
+        return norm_y2 - float(vals[0]) - target, 2.0 * mu * float(vals[1]), L
+
+    mu = mu0 if (mu0 is not None and mu0 > 0.0) else scale
+    lo = hi = None
+    ev = evaluate(mu)
+    if ev is None:
+        return None
+    for _ in range(60):                       # bracket the root: f increases with mu
+        f = ev[0]
+        if f < 0.0:
+            lo = mu
+            if hi is not None:
+                break
+            mu *= 4.0
+        else:
+            hi = mu
+            if lo is not None:
+                break
+            mu *= 0.25
+            if mu < scale * 1e-9:
+                return None                   # constraint inactive (or nearly): let the eigh path decide
+        ev = evaluate(mu)
+        if ev is None:
+            return None
+    else:
+        return None
+    mu = lo if ev is None else mu
+    tol_f = 1e-13 * norm_y2
+    L = None
+    for _ in range(100):
+        f, g, L = ev
+        if abs(f) <= tol_f or (hi - lo) <= 1e-15 * hi:
+            break
+        if f < 0.0:
+            lo = mu
+        else:
+            hi = mu
+        step = mu - f / g if g > 0.0 else -1.0
+        mu = step if (lo < step < hi) else math.sqrt(lo * hi)
+        ev = evaluate(mu)
+        if ev is None:
+            return None
+    return mu, torch.cholesky_solve(T.T.contiguous(), L).T
+
+
+def epc_sweep(Y, factors, delta, norm_y2=None, mu_cache=None):
+    """One error-preserving-correction pass over all modes (the body of musco's `cp_anc`).  `mu_cache` (a list with
+    one entry per mode, updated in place) switches the multiplier search to the Cholesky/Newton form warm-started from
+    the previous pass; without it the eigen-decomposition form is used."""
     N = Y.ndim
     rank = factors[0].shape[1]
     norm_y2 = float(torch.sum(Y * Y)) if norm_y2 is None else norm_y2
@@ -101,32 +198,14 @@ def epc_sweep(Y, factors, delta, norm_y2=None):
             if k != m:
                 gamma = gamma * (factors[k].T @ factors[k])
         T = _mttkrp(Y, factors, m)
-        sig, V = torch.linalg.eigh(gamma)
-        sig = torch.clamp(sig, min=0.0)
-        Tt = T @ V
-        s = (Tt * Tt).sum(dim=0)
-        # residual(mu) = ||Y||^2 - sum_i s_i (sig_i + 2 mu) / (sig_i + mu)^2, increasing in mu: bisection on the host
-        sig_c, s_c = sig.cpu(), s.cpu()
-
-        def resid(mu):
-            return norm_y2 - float((s_c * (sig_c + 2 * mu) / (sig_c + mu) ** 2).sum())
-
-        floor = float(sig_c.max()) * 1e-14
-        mu = 0.0
-        if resid(floor) < target:
-            lo, hi = floor, max(float(sig_c.max()), 1e-300)
-            while resid(hi) < target and hi < 1e300:
-                hi *= 2.0
-            for _ in range(200):
-                mid = 0.5 * (lo + hi)
-                if resid(mid) < target:
-                    lo = mid
-                else:
-                    hi = mid
-                if hi - lo <= 1e-15 * hi:
-                    break
-            mu = 0.5 * (lo + hi)
-        factors[m] = (Tt / (sig + max(mu, floor))) @ V.T
+        out = None
+        if mu_cache is not None:
+            out = _mu_by_cholesky(gamma, T, norm_y2, target, mu_cache[m])
+        if out is None:
+            out = _mu_by_eigh(gamma, T, norm_y2, target)
+        if mu_cache is not None:
+            mu_cache[m] = out[0]
+        factors[m] = out[1]
     return factors
 
 
@@ -157,6 +236,8 @@ def parafac_epc(tensor, rank, als_maxiter=5000, als_tol=1e-5, num_threads=4, ini
     norm_y2 = float(torch.sum(Yp * Yp))
     stopflag = 0
     lam = _intensities(factors)
+    # multiplier search: eigen-decomposition form (measured on B200: 53 ms per pass at R = 1141 against 113 ms for the
+    # Cholesky/Newton form, 5 ms against 19 ms at R = 134)
     for _ in range(epc_rounds):                                             # :61
         prev = None
         for _it in range(epc_maxiter):                                      # cp_anc(maxiter, tol)  :63

@@ -69,6 +69,16 @@ def test_parafac_epc_properties():
         assert err <= delta * (1 + 1e-6)                       # the error bound is preserved
         assert cur <= prev * (1 + 1e-9)                        # the intensity never grows
         prev = cur
+    # the Cholesky/Newton multiplier search follows the eigen-decomposition form pass by pass
+    w2, f2 = parafac_als(Y, 12, n_iter_max=40, tol=1e-7, random_state=5, normalize_factors=True)
+    f2[-1] = f2[-1] * w2
+    fa, fb, cache = [f.clone() for f in f2], [f.clone() for f in f2], [None] * 3
+    for _ in range(5):
+        fa = epc_sweep(Y, fa, delta)
+        fb = epc_sweep(Y, fb, delta, mu_cache=cache)
+        for a, b in zip(fa, fb):
+            assert torch.allclose(a, b, rtol=1e-7, atol=1e-9 * float(a.abs().max()))
+    assert all(c is not None and c > 0 for c in cache)
     lam, Us = parafac_epc(W, 12, als_maxiter=15, epc_maxiter=4, epc_rounds=2)
     assert [u.shape for u in Us] == [(14, 12), (10, 12), (6, 12)] and Us[0].dtype == torch.float64
     rel = float(torch.linalg.norm(Y - torch.einsum("ir,jr,kr->ijk", *Us)) / torch.linalg.norm(Y))
