@@ -26,6 +26,13 @@ class LoopReport(ctypes.Structure):
                 ("best_index", ctypes.c_int32), ("absmax", ctypes.c_float), ("phase_ns", ctypes.c_uint64 * 4)]
 
 
+class FactorizeParams(ctypes.Structure):
+    _fields_ = [("max_iter_als", ctypes.c_int32), ("max_iter_admm", ctypes.c_int32), ("eps", ctypes.c_float),
+                ("tol", ctypes.c_float), ("bits", ctypes.c_int32), ("qscheme", ctypes.c_int32),
+                ("num_attempts", ctypes.c_int32), ("solve_precision", ctypes.c_int32),
+                ("mttkrp_precision", ctypes.c_int32), ("max_ctas", ctypes.c_int32), ("init_is_random", ctypes.c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -57,6 +64,11 @@ def _load():
         "admmq_admm_loop_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
                                     vp, vp, vp, c_sz, vp]),
+        "admmq_factorize_workspace_bytes": (c_sz, [c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(FactorizeParams)]),
+        "admmq_factorize_cp3": (c_int, [vp, c_int, c_int, c_int, c_int] + [vp] * 9 +
+                                [ctypes.POINTER(FactorizeParams), vp, vp, ctypes.POINTER(c_int), vp, c_sz, vp]),
+        "admmq_factorize_mat": (c_int, [vp, c_int, c_int, c_int] + [vp] * 6 +
+                                [ctypes.POINTER(FactorizeParams), vp, vp, ctypes.POINTER(c_int), vp, c_sz, vp]),
         "admmq_admm_iteration_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_admm_iteration": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
                                          vp, vp, vp, c_sz, vp]),
@@ -74,7 +86,8 @@ EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count 
            "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp admmq_permute_myx "
            "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
-           "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration").split()
+           "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration "
+           "admmq_factorize_workspace_bytes admmq_factorize_cp3 admmq_factorize_mat").split()
 
 
 def last_error() -> str:
@@ -343,6 +356,43 @@ def admm_loop_inplace(H, U, F, Minv, rho, inv_status, max_iter, eps, bits, qsche
                               float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), int(precision),
                               int(max_ctas), ptr(codes), ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
     return report
+
+
+def factorize(W, factors, duals, bits, qscheme, max_iter_als, max_iter_admm=1000, eps=1e-8, tol=1e-5, num_attempts=200,
+              solve_precision=0, mttkrp_precision=0, max_ctas=0, init_is_random=True, ws=None):
+    """The whole outer loop in one C call (admmq_factorize_cp3 / admmq_factorize_mat; scripts/factorize.py:207-310).
+    `factors` and `duals` (lists of contiguous float32 CUDA tensors) are updated in place.  Returns
+    (loss_hist, loss_quant_hist, sweeps_done, factors_q)."""
+    import numpy as np
+    require_cuda(W, *factors, *duals)
+    Wc = f32c(W)
+    N = Wc.ndim
+    assert N in (2, 3), "Incorrect number of dimentions in weight tensor"
+    for t in list(factors) + list(duals):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    R = factors[0].shape[1]
+    prm = FactorizeParams(int(max_iter_als), int(max_iter_admm), float(eps), float(tol), int(bits), qscheme_id(qscheme),
+                          int(num_attempts), int(solve_precision), int(mttkrp_precision), int(max_ctas),
+                          1 if init_is_random else 0)
+    shape = (ctypes.c_int * N)(*[int(d) for d in Wc.shape])
+    need = int(lib.admmq_factorize_workspace_bytes(N, shape, R, ctypes.byref(prm)))
+    ws = _ws(need, Wc.device, ws)
+    fq = [torch.empty_like(f) for f in factors]
+    hist = np.zeros(int(max_iter_als) + 1, np.float32)
+    histq = np.zeros(int(max_iter_als) + 1, np.float32)
+    done = ctypes.c_int(0)
+    hp, hqp = hist.ctypes.data_as(ctypes.c_void_p), histq.ctypes.data_as(ctypes.c_void_p)
+    if N == 3:
+        rc = lib.admmq_factorize_cp3(ptr(Wc), *[int(d) for d in Wc.shape], R, *[ptr(t) for t in factors],
+                                     *[ptr(t) for t in duals], *[ptr(t) for t in fq], ctypes.byref(prm), hp, hqp,
+                                     ctypes.byref(done), ptr(ws), ws.numel(), stream_ptr(Wc.device))
+    else:
+        rc = lib.admmq_factorize_mat(ptr(Wc), *[int(d) for d in Wc.shape], R, *[ptr(t) for t in factors],
+                                     *[ptr(t) for t in duals], *[ptr(t) for t in fq], ctypes.byref(prm), hp, hqp,
+                                     ctypes.byref(done), ptr(ws), ws.numel(), stream_ptr(Wc.device))
+    check(rc)
+    n = done.value + (0 if init_is_random else 1)
+    return [float(v) for v in hist[:n]], [float(v) for v in histq[:n]], done.value, fq
 
 
 def launch_count() -> int:

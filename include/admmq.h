@@ -186,6 +186,38 @@ ADMMQ_API int admmq_admm_iteration(float* H, float* U, const float* F, const flo
                          int max_ctas, int8_t* codes, admmq_loop_report* report,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ whole outer loop
+ * Replaces the AO-ADMM loop of scripts/factorize.py:207-266 (3-D: admmq_factorize_cp3) and :269-310 (2-D:
+ * admmq_factorize_mat): up to max_iter_als sweeps of { Gram-Hadamard (:215), MTTKRP (:217), admm_iteration (:218),
+ * re-projection (:222) } per mode, the two reconstruction errors (:246-253) and the stop rules (:259-263 / :303-307).
+ *   W              device, (I, J, K) / (I, J) row-major float32
+ *   A, B, C        device factors (I x R), (J x R), (K x R), IN/OUT; UA, UB, UC the scaled duals, IN/OUT (zero for a
+ *                  fresh run, :209-212); Aq, Bq, Cq OUT: the re-projected factors of the last sweep
+ *   loss_hist, loss_quant_hist   HOST float arrays with room for max_iter_als + 1 entries (rec_error, quant_rec_error
+ *                  per sweep; one leading entry for the initial factors unless init_is_random, :192-201)
+ *   sweeps_done    HOST int
+ * Enqueues on `stream` and synchronises it once per sweep to read the errors (the reference synchronises there too).
+ * Returns ADMMQ_E_NOT_PD when a ridge system is not positive definite (torch.linalg.LinAlgError in the reference). */
+typedef struct admmq_factorize_params {
+  int32_t max_iter_als;     /* --max_iter_als  (5000) */
+  int32_t max_iter_admm;    /* --max_iter_admm (1000) */
+  float eps;                /* 1e-8, exit test of admm_iteration  scripts/factorize.py:187 */
+  float tol;                /* 1e-5, stop rule on the error history  :186 */
+  int32_t bits, qscheme, num_attempts;
+  int32_t solve_precision;  /* see admmq_admm_loop */
+  int32_t mttkrp_precision; /* 0 float64-accumulating CUDA-core MTTKRP, 1 3xTF32 tcgen05 */
+  int32_t max_ctas;         /* cooperative-grid budget, 0 = every SM */
+  int32_t init_is_random;   /* non-zero: no leading history entry (:192) */
+} admmq_factorize_params;
+ADMMQ_API size_t admmq_factorize_workspace_bytes(int ndim, const int* shape, int R, const admmq_factorize_params* params);
+ADMMQ_API int admmq_factorize_cp3(const float* W, int I, int J, int K, int R, float* A, float* B, float* C,
+                        float* UA, float* UB, float* UC, float* Aq, float* Bq, float* Cq,
+                        const admmq_factorize_params* params, float* loss_hist, float* loss_quant_hist,
+                        int* sweeps_done, void* workspace, size_t workspace_bytes, void* stream);
+ADMMQ_API int admmq_factorize_mat(const float* W, int I, int J, int R, float* A, float* B, float* UA, float* UB,
+                        float* Aq, float* Bq, const admmq_factorize_params* params, float* loss_hist,
+                        float* loss_quant_hist, int* sweeps_done, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

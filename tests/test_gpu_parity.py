@@ -460,6 +460,42 @@ def test_outer_loop_full_inner_budget_first_sweep(golden_outer, capsys, precisio
     assert all(r.iterations == 999 for r in s.last_reports)  # the exit test never fires
 
 
+def test_c_level_outer_loop_equals_python_orchestration(nat, golden_outer):
+    """admmq_factorize_cp3 / admmq_factorize_mat (the whole loop of scripts/factorize.py:207-310 in one C call) run
+    the same kernels in the same order as source/solver.py::LayerSolver: identical histories and factors, stop rules
+    included; and the first sweep matches the reference's recorded history."""
+    from source import workloads as wl
+    from source.solver import LayerSolver
+    g = torch.Generator().manual_seed(5)
+    for shape, R, sweeps, inner in [((24, 20, 9), 30, 4, 25), ((40, 28), 12, 12, 15)]:
+        W = (torch.randn(*shape, generator=g) * 0.05).cuda()
+        init = wl.random_init(shape, R, 7)
+        for prec in (0, 1):
+            s = LayerSolver(W, [f.cuda() for f in init], 4, MSE, max_iter_admm=inner, solve_precision=prec, mttkrp_precision=prec)
+            n_py = s.run(sweeps)
+            fac = [f.clone().cuda() for f in init]
+            du = [torch.zeros_like(f) for f in fac]
+            hist, histq, n_c, fq = nat.factorize(W, fac, du, 4, MSE, sweeps, inner, solve_precision=prec, mttkrp_precision=prec)
+            assert n_c == n_py and hist == s.loss_hist and histq == s.loss_quant_hist, (shape, prec, hist, s.loss_hist)
+            for a, b in zip(fac + du + fq, s.factors + s.duals + s.factors_q):
+                assert torch.equal(a, b)
+    # non-random init: one leading history entry (scripts/factorize.py:192-201)
+    W = (torch.randn(16, 12, 9, generator=g) * 0.05).cuda()
+    fac = [f.cuda() for f in wl.random_init((16, 12, 9), 10, 3)]
+    hist, histq, n, _ = nat.factorize(W, fac, [torch.zeros_like(f) for f in fac], 4, MSE, 2, 10, init_is_random=False)
+    assert n == 2 and len(hist) == 3 and len(histq) == 3
+    with pytest.raises(ValueError):
+        nat.factorize(W, fac, [torch.zeros_like(f) for f in fac], 9, MSE, 2, 10)
+    # the reference's recorded history (config 1, short budget) through the C entry point
+    go = golden_outer
+    m = go.case("config1_short")
+    fac = [dev(go[f"config1_short/init{k}"]) for k in range(3)]
+    hist, _, n, _ = nat.factorize(dev(go["config1/W"]), fac, [torch.zeros_like(f) for f in fac], m["bits"], m["qscheme"],
+                                  m["sweeps"], m["max_iter_admm"], tol=0.0)
+    ref = go["config1_short/loss"]
+    assert n == m["sweeps"] and abs(hist[0] - ref[0]) <= 1e-3 * ref[0] and abs(hist[1] - ref[1]) <= 1e-3 * ref[1]
+
+
 # ------------------------------------------------------------------ model level (north_star: top-1 on synthetic-calibrated weights)
 class _PrototypeTask:
     """10-class synthetic image task with a real decision margin: class prototype + unit Gaussian noise."""
