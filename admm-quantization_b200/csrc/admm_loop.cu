@@ -46,6 +46,7 @@ struct LoopParams {
   float* H;
   float* U;
   const float* F;
+  const float* H2;  // kDiagP1 only: the other block of the two-block splitting (scripts/factorize_lowrank.py:85)
   int I, R, Rp;
   int max_iter;
   float eps;
@@ -241,6 +242,31 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
   }
 }
 
+// P1 of the two-block splitting W ~ W_q + W_r (scripts/factorize_lowrank.py:80-101): the least-squares step is
+// elementwise, H_ = (rho (H + U) + W - H2) / (1 + rho) with p.F = W, evaluated in the reference's operation order.
+// Every CTA works on the chunk of elements it also owns in P2 / P3 (I = 1, R = number of elements).
+constexpr int kDiagP1 = -1000;
+__device__ void elementwise_phase(const LoopParams& p, float rho, long long e0, long long e1, unsigned int* keys) {
+  const float opr = add_rn(1.0f, rho);
+  unsigned int kmax = 0u, kinv = 0u;
+  for (long long e = e0 + threadIdx.x; e < e1; e += kThreads) {
+    const float u = __ldcg(p.U + e);
+    const float h = div_rn(sub_rn(add_rn(mul_rn(rho, add_rn(p.H[e], u)), p.F[e]), p.H2[e]), opr);   // :85
+    p.Hls[e] = h;
+    const float v = sub_rn(h, u);                                                                  // :88
+    p.V[e] = v;
+    const unsigned int k = float_key(v);
+    kmax = max(kmax, k);
+    kinv = max(kinv, ~k);
+  }
+  kmax = warp_max_u32(kmax);
+  kinv = warp_max_u32(kinv);
+  if ((threadIdx.x & 31) == 0 && (kmax | kinv) != 0u) {
+    atomicMax(&keys[0], kmax);
+    atomicMax(&keys[1], kinv);
+  }
+}
+
 // P1 on the tensor cores: 128 x bn tiles (bn = p.tc_bn <= TCBN) of H_ls = RHS . Minv^T (Minv is symmetric) in 3xTF32;
 // Minv comes pre-split into its tf32 hi / lo parts (constant over the call, made by the kernel's prologue).
 template <int TCBN>
@@ -309,7 +335,7 @@ union LoopSmem {
   GemmSmem<BM, BN> gemm;
   ResidualSmem res;
   unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16), true>::kBytes : 16];
-  SkinnySmem<(TCBN < 0 ? -TCBN : 1)> skinny;
+  SkinnySmem<(TCBN < 0 && TCBN != kDiagP1 ? -TCBN : 1)> skinny;
 };
 
 // sum over the CTA of four per-thread doubles, result valid in every thread
@@ -333,7 +359,8 @@ __device__ __forceinline__ void cta_sum4(double v[4], ResidualSmem& rs) {
 }
 
 // TCBN = 0: P1 as float32 FFMA tiles (BM x BN, TM x TN per thread); TCBN = 16 / 32 / 64: P1 on the tensor cores;
-// TCBN = -MI: P1 for factors with at most MI rows (gemm_phase_skinny).
+// TCBN = -MI: P1 for factors with at most MI rows (gemm_phase_skinny); TCBN = kDiagP1: elementwise P1 of the
+// two-block splitting (elementwise_phase).
 template <int BM, int BN, int TM, int TN, int TCBN>
 __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant__ LoopParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -388,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     }
   }
   // RHS = F + rho * (H + U) for the first iteration (:56)
-  {
+  if constexpr (TCBN != kDiagP1) {
     int i = row0, n = col0;
     for (long long e = e0 + t; e < e1; e += kThreads) {
       p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(p.H[e], p.U[e])));
@@ -406,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
     // ---------------- P1
     if constexpr (TCBN > 0) gemm_phase_tc<TCBN>(p, sm.tc_tiles, pipe, pst, hdr->keys[slot]);
+    else if constexpr (TCBN == kDiagP1) elementwise_phase(p, rho, e0, e1, hdr->keys[slot]);
     else if constexpr (TCBN < 0) gemm_phase_skinny<-TCBN>(p, sm.skinny, hdr->keys[slot]);
     else gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
     if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
@@ -490,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
             f3 = fmaf(un, un, f3);  // sum U^2
             p.H[ee[b]] = hq;
             p.U[ee[b]] = un;
-            p.RHS[(size_t)ii[b] * Rp + nn[b]] = add_rn(fv[b], mul_rn(rho, add_rn(hq, un)));
+            if constexpr (TCBN != kDiagP1) p.RHS[(size_t)ii[b] * Rp + nn[b]] = add_rn(fv[b], mul_rn(rho, add_rn(hq, un)));
             if (p.codes != nullptr) p.codes[ee[b]] = (int8_t)code;
             if (++cnt == 16) {  // float32 partial sums over at most 16 elements, float64 beyond
               sums[0] += (double)f0;
@@ -543,7 +571,7 @@ struct LoopLayout {  // workspace of admmq_admm_loop
   int Rp;
 };
 
-static LoopLayout loop_layout(int I, int R, int grid) {
+static LoopLayout loop_layout(int I, int R, int grid, bool with_minv_parts = true) {
   LoopLayout l;
   l.Rp = (R + 3) / 4 * 4;
   size_t off = 0;
@@ -558,8 +586,8 @@ static LoopLayout loop_layout(int I, int R, int grid) {
   l.rhs = take((size_t)I * l.Rp * sizeof(float));
   l.hls = take((size_t)I * l.Rp * sizeof(float));
   l.v = take((size_t)I * R * sizeof(float));
-  l.minv_hi = take((size_t)R * l.Rp * sizeof(float));
-  l.minv_lo = take((size_t)R * l.Rp * sizeof(float));
+  l.minv_hi = take(with_minv_parts ? (size_t)R * l.Rp * sizeof(float) : 0);
+  l.minv_lo = take(with_minv_parts ? (size_t)R * l.Rp * sizeof(float) : 0);
   l.total = off;
   return l;
 }
@@ -796,6 +824,69 @@ extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* 
                 admmq_admm_loop_workspace_bytes(I, R, num_attempts));
   return launch_loop(H, U, F, Minv, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision, codes,
                      report, (char*)workspace, coop_grid(dp, max_ctas), (cudaStream_t)stream_);
+}
+
+// ---- two-block splitting W ~ W_q + W_r (scripts/factorize_lowrank.py): the quantized block's inner loop
+extern "C" size_t admmq_split_loop_workspace_bytes(int64_t n, int num_attempts) {
+  (void)num_attempts;
+  if (n <= 0 || n >= (1ll << 31)) return 0;
+  return loop_layout(1, (int)n, kMaxGrid, false).total;
+}
+
+extern "C" int admmq_split_loop(float* H, float* U, const float* W, const float* H2, int64_t n, float rho, int max_iter,
+                                float eps, int bits, int qscheme, int num_attempts, int max_ctas, int8_t* codes,
+                                admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n <= 0 || n >= (1ll << 31)) return fail(ADMMQ_E_UNSUPPORTED, "admmq_split_loop: n must be in 1 .. 2^31-1");
+  if (int e = check_loop_args("admmq_split_loop", H, U, W, H2, report, 1, (int)n, bits, qscheme, num_attempts)) return e;
+  if (!(rho > 0.0f)) return fail(ADMMQ_E_BADARG, "admmq_split_loop: rho must be positive");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
+  if (workspace == nullptr || workspace_bytes < admmq_split_loop_workspace_bytes(n, num_attempts) ||
+      ((uintptr_t)workspace & 255) != 0)
+    return fail(ADMMQ_E_WORKSPACE, "admmq_split_loop: workspace needs %zu bytes, 256-byte aligned",
+                admmq_split_loop_workspace_bytes(n, num_attempts));
+  const int grid = coop_grid(dp, max_ctas);
+  char* ws = (char*)workspace;
+  const LoopLayout l = loop_layout(1, (int)n, grid, false);
+  ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, l.slots, stream));
+  // rho lives in the (zeroed) header page: pad[] of LoopHeader is unused by the kernel
+  LoopHeader* hdr = (LoopHeader*)(ws + l.header);
+  ADMMQ_CUDA_OK(cudaMemcpyAsync(&hdr->pad[0], &rho, sizeof(float), cudaMemcpyHostToDevice, stream));
+  LoopParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = H;
+  p.U = U;
+  p.F = W;
+  p.H2 = H2;
+  p.I = 1;
+  p.R = (int)n;
+  p.Rp = l.Rp;
+  p.max_iter = max_iter;
+  p.eps = eps;
+  p.bits = bits;
+  p.scheme = qscheme;
+  p.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
+  p.neg_zero = -0.0f;
+  p.codes = codes;
+  p.report = report;
+  p.rho = reinterpret_cast<const float*>(&hdr->pad[0]);
+  p.inv_status = nullptr;
+  p.hdr = hdr;
+  p.cand = (unsigned long long*)(ws + l.cand);
+  p.slots = (double*)(ws + l.slots);
+  p.Hls = (float*)(ws + l.hls);
+  p.V = (float*)(ws + l.v);
+  p.RHS = nullptr;
+  p.Minv = nullptr;
+  void* args[] = {&p};
+  const void* fn = (const void*)k_admm_loop<16, 32, 1, 2, kDiagP1>;
+  const size_t smem = sizeof(LoopSmem<16, 32, kDiagP1>);
+  ADMMQ_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ADMMQ_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
+  count_launches(1);
+  return ADMMQ_OK;
 }
 
 extern "C" size_t admmq_admm_iteration_workspace_bytes(int I, int R, int num_attempts) {

@@ -64,6 +64,8 @@ def _load():
         "admmq_admm_loop_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
                                     vp, vp, vp, c_sz, vp]),
+        "admmq_split_loop_workspace_bytes": (c_sz, [c_i64, c_int]),
+        "admmq_split_loop": (c_int, [vp, vp, vp, vp, c_i64, c_f, c_int, c_f, c_int, c_int, c_int, c_int, vp, vp, vp, c_sz, vp]),
         "admmq_factorize_workspace_bytes": (c_sz, [c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(FactorizeParams)]),
         "admmq_factorize_cp3": (c_int, [vp, c_int, c_int, c_int, c_int] + [vp] * 9 +
                                 [ctypes.POINTER(FactorizeParams), vp, vp, ctypes.POINTER(c_int), vp, c_sz, vp]),
@@ -87,7 +89,8 @@ EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count 
            "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
            "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration "
-           "admmq_factorize_workspace_bytes admmq_factorize_cp3 admmq_factorize_mat").split()
+           "admmq_factorize_workspace_bytes admmq_factorize_cp3 admmq_factorize_mat "
+           "admmq_split_loop_workspace_bytes admmq_split_loop").split()
 
 
 def last_error() -> str:
@@ -355,6 +358,22 @@ def admm_loop_inplace(H, U, F, Minv, rho, inv_status, max_iter, eps, bits, qsche
     check(lib.admmq_admm_loop(ptr(H), ptr(U), ptr(F), ptr(Minv), ptr(rho), ptr(inv_status), I, R, int(max_iter),
                               float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), int(precision),
                               int(max_ctas), ptr(codes), ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
+    return report
+
+
+def split_loop_inplace(H, U, W, H2, rho, max_iter, eps, bits, qscheme, num_attempts=200, max_ctas=0, codes=None,
+                       report=None, ws=None):
+    """Quantized block of the two-block splitting W ~ W_q + W_r (scripts/factorize_lowrank.py:84-99); H and U
+    (contiguous float32 CUDA tensors) are updated in place."""
+    require_cuda(H, U, W, H2)
+    for t in (H, U, W, H2):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == H.numel()
+    n = H.numel()
+    report = new_report(H.device) if report is None else report
+    ws = _ws(int(lib.admmq_split_loop_workspace_bytes(n, int(num_attempts))), H.device, ws)
+    check(lib.admmq_split_loop(ptr(H), ptr(U), ptr(W), ptr(H2), n, float(rho), int(max_iter), float(eps), int(bits),
+                               qscheme_id(qscheme), int(num_attempts), int(max_ctas), ptr(codes), ptr(report), ptr(ws),
+                               ws.numel(), stream_ptr(H.device)))
     return report
 
 

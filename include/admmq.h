@@ -186,6 +186,18 @@ ADMMQ_API int admmq_admm_iteration(float* H, float* U, const float* F, const flo
                          int max_ctas, int8_t* codes, admmq_loop_report* report,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ two-block splitting  W ~ W_q + W_r
+ * The quantized block's inner loop of scripts/factorize_lowrank.py:80-101 (`admm_iteration(H, U, W, H2, proj_func,
+ * rho, max_iter, eps)` with proj_func = quantize_tensor): max_iter-1 iterations of
+ *   H_ = (rho (H + U) + W - H2) / (1 + rho);  H = Q(H_ - U);  U += H - H_;  exit when r < eps and s < eps
+ * in one persistent cooperative kernel (the least-squares step is elementwise, so there is no ridge product; clip
+ * search, dual update, residuals and barriers are those of admmq_admm_loop).  H, U IN/OUT, W, H2 read-only, all n
+ * floats.  The low-rank block's projection (an SVD truncation, :80-82) stays with the caller. */
+ADMMQ_API size_t admmq_split_loop_workspace_bytes(int64_t n, int num_attempts);
+ADMMQ_API int admmq_split_loop(float* H, float* U, const float* W, const float* H2, int64_t n, float rho, int max_iter,
+                     float eps, int bits, int qscheme, int num_attempts, int max_ctas, int8_t* codes,
+                     admmq_loop_report* report, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ whole outer loop
  * Replaces the AO-ADMM loop of scripts/factorize.py:207-266 (3-D: admmq_factorize_cp3) and :269-310 (2-D:
  * admmq_factorize_mat): up to max_iter_als sweeps of { Gram-Hadamard (:215), MTTKRP (:217), admm_iteration (:218),
