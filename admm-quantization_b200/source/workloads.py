@@ -77,3 +77,68 @@ def lpt_assign(costs, n_bins):
         where[i] = b
         load[b] += costs[i]
     return where
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SM budgets for concurrently running solves.  A layer's persistent kernels run on `g` CTAs (max_ctas); the tensor-core
+# ridge product works in whole waves of 128 x bn tiles, so its time is a STEP function of g (72 tiles of width 64 take 3
+# waves on 24 .. 35 CTAs and 2 on 36), while the clip search / dual update scale like 1/g above a latency floor.  The
+# budgets are chosen from that model, fitted to the phase times the kernels report (admmq_loop_report.phase_ns).
+_TILE_FIXED = 128          # csrc/admm_loop.cu kTileFixed: tile cost that does not depend on its width
+_PHASE_FLOOR_US = 14.0     # P2 + P3 of a factor that is too small to matter: barriers and L2 round trips
+
+
+def product_cost(rows, rank, g, solve_precision=1):
+    """Relative time of one ridge product H_ls = RHS . Minv on g CTAs (mirrors launch_loop in csrc/admm_loop.cu)."""
+    if rows <= 16 or solve_precision != 1 or rows < 64 or rank < 32:
+        return 1.0 / g                                   # column strips / small FFMA tiles: scales with the grid
+    tiles_m = (rows + 127) // 128
+    best = None
+    for bn in (64, 48, 32, 16):
+        tiles = tiles_m * ((rank + bn - 1) // bn)
+        cost = ((tiles + g - 1) // g) * (_TILE_FIXED + bn)
+        best = cost if best is None or cost < best else best
+    return float(best)
+
+
+def predict_sweep_ms(measured_ms, g0, g, modes, solve_precision=1):
+    """Sweep time of one layer on g CTAs from a measurement on g0 CTAs.
+    modes: [(rows, rank, p1_us, p23_us, iterations)] per factor - P1 (ridge product) and P2 + P3 per inner iteration."""
+    loop0 = sum(it * (p1 + p23) for _, _, p1, p23, it in modes) / 1e3
+    rest = max(measured_ms - loop0, 0.0)                 # Gram, MTTKRP, inverse, projection, errors: taken as fixed
+    loop = 0.0
+    for rows, rank, p1, p23, it in modes:
+        p1g = p1 * product_cost(rows, rank, g, solve_precision) / product_cost(rows, rank, g0, solve_precision)
+        floor = min(_PHASE_FLOOR_US, p23)
+        p23g = floor + (p23 - floor) * g0 / g
+        loop += it * (p1g + p23g) / 1e3
+    return rest + loop
+
+
+def allocate_ctas_modelled(layers, sm_count, solve_precision=1):
+    """layers: [(measured_ms, g0, modes)] as for predict_sweep_ms.  Greedy: every layer starts with one CTA, then the
+    layer that is predicted to finish last repeatedly receives the smallest increase of its budget that shortens its
+    predicted time (so budgets move from wave boundary to wave boundary) until the SMs are used up.  Returns the
+    budgets (sum <= sm_count)."""
+    n = len(layers)
+    if n >= sm_count:
+        return [1] * n
+    g = [1] * n
+    t = [predict_sweep_ms(m, g0, 1, modes, solve_precision) for m, g0, modes in layers]
+    free = sm_count - n
+    while free > 0:
+        k = max(range(n), key=lambda i: t[i])
+        m, g0, modes = layers[k]
+        step = None
+        for extra in range(1, free + 1):
+            tn = predict_sweep_ms(m, g0, g[k] + extra, modes, solve_precision)
+            if tn < t[k] * (1.0 - 1e-3):
+                step = (extra, tn)
+                break
+        if step is None:
+            break                                        # the slowest layer cannot be sped up with what is left
+        g[k] += step[0]
+        t[k] = step[1]
+        free -= step[0]
+    # leftovers: hand them out one by one to whoever is slowest and still profits
+    return g

@@ -57,6 +57,9 @@ def parse_args():
                     help="off: layers run one after the other on every SM; prop: every layer gets a share of the SMs "
                          "proportional to its cost and all layers run concurrently on their own streams")
     ap.add_argument("--min-ctas", type=int, default=2)
+    ap.add_argument("--balance", default="model", choices=["model", "prop"],
+                    help="re-balancing of the SM budgets during warm-up: 'model' = wave model of the tensor-core product "
+                         "fitted to the reported phase times (source/workloads.py), 'prop' = proportional to time x CTAs")
     ap.add_argument("--trace-layer", default=None, help="print the per-kernel-group times of this layer's last sweep")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs kept out of the cooperative-grid budgets so that the ordinary kernels between the loops "
@@ -328,10 +331,20 @@ def run_native(args):
         flush.fill_(1)
         step()
         if streams is not None and w < min(2, args.warmup - 1):
-            # re-balance the SM shares from what was just measured: a layer's work is (sweep time) x (its CTAs)
+            # re-balance the SM budgets from what was just measured: per layer the sweep time and, per factor, the
+            # phase times its persistent kernel reported, through the wave model of source/workloads.py
             torch.cuda.synchronize()
-            work = [a.elapsed_time(b) * max(s.max_ctas, 1) for (a, b), s in zip(sweep_events, solvers)]
-            for s, g in zip(solvers, allocate_ctas(work, sm_count - args.reserve_sms, 1)):
+            fitted = []
+            for (a, b), s in zip(sweep_events, solvers):
+                modes = []
+                for f, r in zip(s.factors, s.last_reports):
+                    it = max(r.iterations, 1)
+                    modes.append((f.shape[0], s.R, r.phase_ns[0] / 1e3 / it, (r.phase_ns[1] + r.phase_ns[2]) / 1e3 / it, it))
+                fitted.append((a.elapsed_time(b), max(s.max_ctas, 1), modes))
+            new = wl.allocate_ctas_modelled(fitted, sm_count - args.reserve_sms, args.solve_precision) \
+                if args.balance == "model" else \
+                allocate_ctas([m * g0 for m, g0, _ in fitted], sm_count - args.reserve_sms, 1)
+            for s, g in zip(solvers, new):
                 s.max_ctas = g
             budgets[:] = [s.max_ctas for s in solvers]
     for s in solvers:

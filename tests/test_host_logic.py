@@ -207,3 +207,23 @@ def test_replace_calibrate_and_score_on_synthetic_images():
     bncalibrate_model(model, SyntheticImages(3, 8, image_size=32, seed=1), num_samples=16, device="cpu")
     assert not torch.equal(bn_before, model.bn1.running_mean)            # statistics were re-estimated
     assert not model.training and all(not p.requires_grad for p in model.parameters())
+
+
+def test_modelled_sm_budgets_follow_the_wave_structure():
+    """source/workloads.py: the tensor-core ridge product takes whole waves of tiles, so budgets are moved from wave
+    boundary to wave boundary; the budgets never exceed the SM count and the slowest predicted layer is not starved."""
+    from source import workloads as wl
+    assert wl.product_cost(512, 1141, 36) < wl.product_cost(512, 1141, 35) == wl.product_cost(512, 1141, 24)   # 72 tiles of 64
+    assert wl.product_cost(512, 1141, 32) < wl.product_cost(512, 1141, 31)                                     # 96 tiles of 48
+    assert wl.product_cost(9, 1141, 8) == pytest.approx(2 * wl.product_cost(9, 1141, 16))                      # skinny: 1 / g
+    big = (297.0, 31, [(512, 1141, 61.0, 40.8, 999), (512, 1141, 61.0, 40.8, 999), (9, 1141, 17.0, 20.0, 999)])
+    mid = (270.0, 7, [(256, 566, 40.0, 51.0, 999), (256, 566, 40.0, 51.0, 999), (9, 566, 18.0, 19.0, 999)])
+    small = (112.0, 2, [(64, 134, 17.0, 28.0, 999), (64, 134, 17.0, 28.0, 999), (9, 134, 10.0, 19.0, 999)])
+    assert wl.predict_sweep_ms(*big[:2], 31, big[2]) == pytest.approx(297.0)
+    assert wl.predict_sweep_ms(*big[:2], 36, big[2]) < wl.predict_sweep_ms(*big[:2], 32, big[2]) < 297.0
+    layers = [small] * 4 + [mid] * 4 + [big] * 3
+    g = wl.allocate_ctas_modelled(layers, 148)
+    assert sum(g) <= 148 and min(g) >= 1 and g[-1] > g[4] > g[0]
+    t = [wl.predict_sweep_ms(m, g0, gi, mo) for (m, g0, mo), gi in zip(layers, g)]
+    assert max(t) < 297.0                                   # better than the measured starting point
+    assert wl.allocate_ctas_modelled(layers, 8) == [1] * 11  # more solves than SMs: one CTA each
