@@ -23,6 +23,14 @@ namespace admmq {
 
 constexpr int kKeySlots = 3;
 
+// B operand of the tensor-core ridge product: pre-split hi / lo parts of Minv fetched by TMA straight into the operand
+// stages (1: no conversion work, twice the L2 traffic for B) or the float32 Minv itself, split tile by tile by the
+// converter warps (0).  See DESIGN.md 5 for the measurements behind the default.
+#ifndef ADMMQ_LOOP_PS
+#define ADMMQ_LOOP_PS 1
+#endif
+constexpr bool kLoopPS = ADMMQ_LOOP_PS != 0;
+
 struct LoopHeader {  // start of the workspace; zeroed by cudaMemsetAsync before every call
   unsigned int barrier_loop;
   unsigned int pad[3];
@@ -282,10 +290,10 @@ __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc
     const int i0 = (tile / tilesN) * tc::kTileM, n0 = (tile % tilesN) * bn;
     const int next = tile + (int)gridDim.x;
     const bool has_next = next < tilesM * tilesN;
-    tc::tile_3xtf32<TCBN, true>(&p.tm_rhs, i0, &p.tm_minv_hi, &p.tm_minv_lo, n0, bn, R, smem_tiles, pipe, st,
+    tc::tile_3xtf32<TCBN, kLoopPS>(&p.tm_rhs, i0, &p.tm_minv_hi, &p.tm_minv_lo, n0, bn, R, smem_tiles, pipe, st,
                                 has_next ? (next / tilesN) * tc::kTileM : -1, has_next ? (next % tilesN) * bn : -1);
     // epilogue over row-contiguous float4 groups of the tile parked in shared memory (coalesced global traffic)
-    const float* tile_h = tc::acc_to_smem<TCBN, true>(pipe, smem_tiles);
+    const float* tile_h = tc::acc_to_smem<TCBN, kLoopPS>(pipe, smem_tiles);
     using ET = tc::EpiTile<TCBN>;
 #pragma unroll
     for (int g0 = 0; g0 < ET::kGroups; g0 += kThreads) {
@@ -334,7 +342,7 @@ union LoopSmem {
   SearchSmem search;
   GemmSmem<BM, BN> gemm;
   ResidualSmem res;
-  unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16), true>::kBytes : 16];
+  unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16), kLoopPS>::kBytes : 16];
   SkinnySmem<(TCBN < 0 && TCBN != kDiagP1 ? -TCBN : 1)> skinny;
 };
 
@@ -405,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   const int row0 = (int)((e0 + t) / R), col0 = (int)((e0 + t) - (long long)row0 * R);
   const int drow = kThreads / R, dcol = kThreads - drow * R;
 
-  if constexpr (TCBN > 0) {  // tf32 hi / lo parts of Minv for the tensor-core product (same split as the A operand)
+  if constexpr (TCBN > 0 && kLoopPS) {  // tf32 hi / lo parts of Minv for the tensor-core product (same split as the A operand)
     const long long n4 = (long long)R * Rp / 4;
     for (long long e = (long long)blockIdx.x * kThreads + t; e < n4; e += (long long)gridDim.x * kThreads) {
       float4 hi, lo;
@@ -744,8 +752,8 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     }
     p.tc_bn = tcbn;
     if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
-    if (int e = tc::make_operand_tmap(&p.tm_minv_hi, p.MinvHi, R, R, l.Rp, tcbn)) return e;
-    if (int e = tc::make_operand_tmap(&p.tm_minv_lo, p.MinvLo, R, R, l.Rp, tcbn)) return e;
+    if (int e = tc::make_operand_tmap(&p.tm_minv_hi, kLoopPS ? p.MinvHi : Minv, R, R, l.Rp, tcbn)) return e;
+    if (int e = tc::make_operand_tmap(&p.tm_minv_lo, kLoopPS ? p.MinvLo : Minv, R, R, l.Rp, tcbn)) return e;
     if (tcbn > 32) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, 64>;
       smem = sizeof(LoopSmem<16, 32, 64>);

@@ -32,8 +32,9 @@ namespace tc {
 
 constexpr int kThreadsTC = 512;
 constexpr int kMmaWarp = 15;     // one elected lane issues the MMAs
-constexpr int kTmaWarp = 14;     // one elected lane issues every TMA load
-constexpr int kConverters = 14;  // warps 0 .. 13 convert operands
+constexpr int kTmaWarp = 14;     // one elected lane issues the TMA loads of the raw ring
+constexpr int kTmaWarpB = 13;    // PS: one elected lane issues the TMA loads of B hi / lo into the operand stages
+constexpr int kConverters = 13;  // warps 0 .. 12 convert operands
 constexpr int kAtomK = 32;       // floats per 128-byte swizzle row
 constexpr int kAtoms = 2;        // swizzle atoms along K per K-block
 constexpr int kBlockK = kAtomK * kAtoms;  // 64: halves the per-block synchronisation cost of a 32-deep block
@@ -291,12 +292,12 @@ __device__ __forceinline__ void tmem_store4(unsigned int taddr, const float4 v) 
 // Roles (16 warps):
 //   warp 15  MMA: waits for a stage (A hi/lo in tensor memory from the converters, B hi/lo in shared memory), issues
 //            the 24 MMAs of the K-block, commits them to stage_free
-//   warp 14  TMA: keeps the raw ring (float32 K-blocks of A, and of B without PS) and, with PS, the B hi/lo halves of the
-//            operand stages filled; a slot / stage is refilled as soon as its previous content has been consumed
+//   warp 14  TMA: keeps the raw ring (float32 K-blocks of A, and of B without PS) filled; warp 13 (PS) the B hi/lo halves
+//            of the operand stages; a slot / stage is refilled as soon as its previous content has been consumed
 //            (measured: issuing the TMA loads from the MMA warp or from a converting warp stalls that warp for ~75
 //            cycles per load and makes it the straggler of every K-block)
-//   14 converters (warps 0 .. 13): warp w writes TMEM lanes 32 * (w % 4) .. +31; the 16 chunks (4 k-columns each) of a K-block row are
-//            split 4/4/4/4 over the four warps of quarters 0-1 and 6/5/5 over the three warps of quarters 2-3; without
+//   13 converters (warps 0 .. 12): warp w writes TMEM lanes 32 * (w % 4) .. +31; the 16 chunks (4 k-columns each) of a K-block row are
+//            split 4/4/4/4 over the four warps of quarter 0 and 6/5/5 over the three warps of quarters 1-3; without
 //            PS the B chunks are split over all converters
 // Barrier phases: K-block j of this tile is fill number st.uses[j % kStages] + j / kStages + 1 of its stage (st.uses =
 // fills before this tile, the same in every thread), raw slots likewise with st.raw_uses; nothing is mutated inside
@@ -376,17 +377,7 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
                         &pipe.raw_full[d]);
         }
       };
-      auto fetch_b = [&](int j, int brow) {  // PS: B hi / lo of K-block j into stage j % kNS
-        const int s = j % kNS;
-        const unsigned int sb = tiles_base + (unsigned int)(s * TS::kStageBytes);
-        mbar_expect_tx(&pipe.b_full[s], 2u * (unsigned int)kAtoms * b_atom_tx);
-#pragma unroll
-        for (int a = 0; a < kAtoms; ++a) {
-          tma_load_2d(sb + (unsigned int)(a * TS::kBAtomBytes), tmB, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
-          tma_load_2d(sb + (unsigned int)(TS::kBBytes + a * TS::kBAtomBytes), tmBlo, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
-        }
-      };
-      const int npre_raw = min(kRawDepth, nkb), npre_b = min(kPrefetchB, nkb);
+      const int npre_raw = min(kRawDepth, nkb);
       unsigned int raw_fills[kRawDepth];  // fills of each raw slot so far (previous tiles + this one)
 #pragma unroll
       for (int d = 0; d < kRawDepth; ++d) raw_fills[d] = st.raw_uses[d];
@@ -408,16 +399,33 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
             fetch_raw(j, next_a_row0, next_b_row0);
           }
         }
-        if constexpr (PS) {
+      }
+    }
+    __syncwarp();
+  } else if (warp == kTmaWarpB) {
+    // ---------------- second TMA warp (PS only): B hi / lo straight into the operand stages.  A separate warp, so
+    // that waiting for a stage to be released by the tensor pipe never delays the raw ring (and vice versa)
+    if constexpr (PS) {
+      if (elect_one()) {
+        auto fetch_b = [&](int j, int brow) {
+          const int s = j % kNS;
+          const unsigned int sb = tiles_base + (unsigned int)(s * TS::kStageBytes);
+          mbar_expect_tx(&pipe.b_full[s], 2u * (unsigned int)kAtoms * b_atom_tx);
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a) {
+            tma_load_2d(sb + (unsigned int)(a * TS::kBAtomBytes), tmB, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
+            tma_load_2d(sb + (unsigned int)(TS::kBBytes + a * TS::kBAtomBytes), tmBlo, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
+          }
+        };
+        const int npre_b = min(kPrefetchB, nkb);
+        for (int kb = 0; kb < nkb; ++kb) {
           // stage kb % kNS: free once the MMAs of its previous fill have completed
-          if (cur && !(st.prefetched != 0u && kb < npre_b)) {
+          if (!(st.prefetched != 0u && kb < npre_b)) {
             const unsigned int fb = fills_before(kb);
             if (fb > 0u) mbar_wait(&pipe.stage_free[kb % kNS], (fb - 1u) & 1u);
             fetch_b(kb, b_row0);
           }
         }
-      }
-      if constexpr (PS) {
         // every MMA of this tile has completed => all stages are free: B hi / lo of the next tile's first K-blocks go
         // into stages 0 .. kPrefetchB-1 (the caller's epilogue parks the accumulator in the LAST stage)
         if (next_a_row0 >= 0) {
@@ -431,12 +439,12 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
     // ---------------- converters
     const int q = warp & 3, kgi = warp >> 2;
     const int ar = q * 32 + lane;  // tile row = TMEM lane of this thread
-    // chunks (4 k-columns each) of the row this thread converts: 4/4/4/4 in quarters 0-1, 6/5/5 in quarters 2-3
-    const int c_begin = (q >= 2) ? (kgi == 0 ? 0 : 1 + 5 * kgi) : kgi * (kRowChunks / 4);
-    const int c_count = (q >= 2) ? (kgi == 0 ? 6 : 5) : kRowChunks / 4;
+    // chunks (4 k-columns each) of the row this thread converts: 4/4/4/4 in quarter 0, 6/5/5 in quarters 1-3
+    const int c_begin = (q >= 1) ? (kgi == 0 ? 0 : 1 + 5 * kgi) : kgi * (kRowChunks / 4);
+    const int c_count = (q >= 1) ? (kgi == 0 ? 6 : 5) : kRowChunks / 4;
     const unsigned int lane_addr = tmem + ((unsigned int)(q * 32) << 16);
-    // without PS: B chunk ids handled by this thread: bi0, bi0 + 14 * 32, ...
-    const int cw = (q >= 2) ? 8 + (q - 2) * 3 + kgi : q * 4 + kgi;  // converter index 0 .. 13
+    // without PS: B chunk ids handled by this thread: bi0, bi0 + 13 * 32, ...
+    const int cw = (q >= 1) ? 4 + (q - 1) * 3 + kgi : kgi;  // converter index 0 .. 12
     const int bi0 = cw * 32 + lane;
     for (int kb = 0; kb < nkb; ++kb) {
       const int d = kb % kRawDepth;

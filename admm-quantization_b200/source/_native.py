@@ -7,7 +7,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libadmmq.so")
+LIB_PATH = os.environ.get("ADMMQ_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libadmmq.so")
 
 QSCHEME_IDS = {
     "tensor_mseminmax_symmetric": 0,
