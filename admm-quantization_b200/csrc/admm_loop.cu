@@ -738,10 +738,10 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     const int tilesM = (I + tc::kTileM - 1) / tc::kTileM;
     // tile width (multiple of 16): a tile costs its 128 rows of A (staging, independent of the width) plus bn columns
     // of tensor-core work; minimise waves * (kTileFixed + bn), ties go to the wider tile
-    int tcbn = 64;
+    int tcbn = kLoopPS ? 128 : 64;
     {
       long long best = -1;
-      for (int bn = 64; bn >= 16; bn -= 16) {
+      for (int bn = (kLoopPS ? 128 : 64); bn >= 16; bn -= 16) {
         const long long tiles = (long long)tilesM * ((R + bn - 1) / bn);
         const long long cost = ((tiles + grid - 1) / grid) * (kTileFixed + bn);
         if (best < 0 || cost < best) {
@@ -754,7 +754,10 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
     if (int e = tc::make_operand_tmap(&p.tm_minv_hi, kLoopPS ? p.MinvHi : Minv, R, R, l.Rp, tcbn)) return e;
     if (int e = tc::make_operand_tmap(&p.tm_minv_lo, kLoopPS ? p.MinvLo : Minv, R, R, l.Rp, tcbn)) return e;
-    if (tcbn > 32) {
+    if (tcbn > 64) {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, (kLoopPS ? 128 : 64)>;
+      smem = sizeof(LoopSmem<16, 32, (kLoopPS ? 128 : 64)>);
+    } else if (tcbn > 32) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, 64>;
       smem = sizeof(LoopSmem<16, 32, 64>);
     } else if (tcbn > 16) {

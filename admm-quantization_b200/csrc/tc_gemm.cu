@@ -95,9 +95,21 @@ int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, in
   if (int e = device_props(&dp)) return e;
   if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "admmq_gemm_nt needs an sm_100 device (tcgen05)");
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM;
-  // widest tile that still gives every SM one (a tile's cost is dominated by staging its 128 rows of A)
-  const int bn = ((long long)tilesM * ((N + 63) / 64) >= dp.sm_count) ? 64
-                                                                       : ((long long)tilesM * ((N + 31) / 32) >= dp.sm_count ? 32 : 16);
+  // tile width: a tile costs its 128 rows of A (staging, independent of the width) plus bn columns of tensor-core work;
+  // minimise waves * (128 + bn), ties go to the wider tile (128-wide tiles need the pre-split B operand)
+  int bn = 16;
+  {
+    long long best = -1;
+    const int widths[4] = {128, 64, 32, 16};
+    for (int w = (Blo != nullptr ? 0 : 1); w < 4; ++w) {
+      const long long tiles_w = (long long)tilesM * ((N + widths[w] - 1) / widths[w]);
+      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (128 + widths[w]);
+      if (best < 0 || cost < best) {
+        best = cost;
+        bn = widths[w];
+      }
+    }
+  }
   const int tiles = tilesM * ((N + bn - 1) / bn);
   const int grid = std::min(tiles, dp.sm_count);
   GemmMaps maps;
@@ -106,9 +118,10 @@ int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, in
   if (int e = tc::make_operand_tmap(&maps.blo, Blo != nullptr ? Blo : B, N, K, ldb, bn)) return e;
   int e = ADMMQ_OK;
   if (Blo != nullptr) {
-    e = bn == 64 ? launch_gemm<64, true>(maps, M, N, K, C, ldc, grid, stream)
-                 : (bn == 32 ? launch_gemm<32, true>(maps, M, N, K, C, ldc, grid, stream)
-                             : launch_gemm<16, true>(maps, M, N, K, C, ldc, grid, stream));
+    e = bn == 128 ? launch_gemm<128, true>(maps, M, N, K, C, ldc, grid, stream)
+                  : (bn == 64 ? launch_gemm<64, true>(maps, M, N, K, C, ldc, grid, stream)
+                              : (bn == 32 ? launch_gemm<32, true>(maps, M, N, K, C, ldc, grid, stream)
+                                          : launch_gemm<16, true>(maps, M, N, K, C, ldc, grid, stream)));
   } else {
     e = bn == 64 ? launch_gemm<64, false>(maps, M, N, K, C, ldc, grid, stream)
                  : (bn == 32 ? launch_gemm<32, false>(maps, M, N, K, C, ldc, grid, stream)

@@ -45,17 +45,20 @@ constexpr int kPrefetchB = 2;     // operand stages whose B hi / lo may be reque
 
 constexpr int kMaxRawDepth = 4;  // K-blocks of raw float32 in flight (TMA): TileSmem::kRawDepth = 4 with PS, 3 without
 constexpr int kStageCols = 2 * kBlockK;  // TMEM columns of one A stage: hi [0, 64), lo [64, 128)
-constexpr int kTmemCols = 512;   // 2 accumulators + stages x 128: 64 + 3 x 128 = 448 (BN <= 32), 128 + 3 x 128 = 512 (BN = 64)
+constexpr int kTmemCols = 512;   // 2 accumulators + stages x 128: 64 + 3 x 128 (BN <= 32), 128 + 3 x 128 (BN = 64), 256 + 2 x 128 (BN = 128)
 
 // PS ("pre-split B"): the B operand is given as two tf32-valued float32 matrices hi / lo made once by the caller (the
 // ridge inverse is constant for all inner iterations of an ADMM call), fetched by TMA straight into the operand stage
 // in the layout the MMA reads, so that the producer warps only convert A.
 template <int BN, bool PS = false>
 struct TileSmem {
-  static_assert(BN == 16 || BN == 32 || BN == 64, "BN must be 16, 32 or 64");
-  static constexpr int kStages = (BN == 64 && !PS) ? 2 : 3;      // shared-memory budget (BN = 64 without PS: 2 x 32 + 3 x 48 KB)
-  static constexpr int kRawDepth = PS ? 4 : 3;                   // (BN = 64 with PS: 3 x 32 + 4 x 32 KB)
-  static constexpr int kAccStride = (BN == 64) ? 64 : 32;        // TMEM columns between the two accumulators
+  static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128, "BN must be 16, 32, 64 or 128");
+  static_assert(PS || BN <= 64, "128-wide tiles need the pre-split B operand (shared-memory budget)");
+  // shared-memory / TMEM budgets: BN = 64 without PS: 2 x 32 + 3 x 48 KB; BN = 64 with PS: 3 x 32 + 4 x 32 KB;
+  // BN = 128 (PS): 2 x 64 + 3 x 32 KB and 2 x 128 accumulator + 2 x 128 operand columns of tensor memory
+  static constexpr int kStages = (BN == 128 || (BN == 64 && !PS)) ? 2 : 3;
+  static constexpr int kRawDepth = (BN == 128) ? 3 : (PS ? 4 : 3);
+  static constexpr int kAccStride = (BN == 128) ? 128 : ((BN == 64) ? 64 : 32);  // TMEM columns between the two accumulators
   static constexpr int kAccCols = 2 * kAccStride;                // hi.hi at +0, hi.lo + lo.hi at +stride
   static_assert(kAccCols + kStages * kStageCols <= kTmemCols, "tensor memory budget");
   static constexpr int kAAtomBytes = kTileM * 128;               // one 32-deep atom of A as raw float32
@@ -417,7 +420,7 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
             tma_load_2d(sb + (unsigned int)(TS::kBBytes + a * TS::kBAtomBytes), tmBlo, j * kBlockK + a * kAtomK, brow, &pipe.b_full[s]);
           }
         };
-        const int npre_b = min(kPrefetchB, nkb);
+        const int npre_b = min(min(kPrefetchB, kNS - 1), nkb);
         for (int kb = 0; kb < nkb; ++kb) {
           // stage kb % kNS: free once the MMAs of its previous fill have completed
           if (!(st.prefetched != 0u && kb < npre_b)) {
@@ -531,11 +534,15 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
   row = q * 32 + lane;
   col0 = cgp * (BN / 4);
   const unsigned int taddr = pipe.tmem_base + ((unsigned int)(q * 32) << 16) + (unsigned int)col0;
-  unsigned int hh[BN / 4], cr[BN / 4];
-  tmem_load<BN / 4>(taddr, hh);
-  tmem_load<BN / 4>(taddr + (unsigned int)TileSmem<BN>::kAccStride, cr);
+  constexpr int kW = (BN / 4 > 16) ? 16 : BN / 4;  // columns per tcgen05.ld (register pressure)
 #pragma unroll
-  for (int i = 0; i < BN / 4; ++i) v[i] = __uint_as_float(cr[i]) + __uint_as_float(hh[i]);
+  for (int c0 = 0; c0 < BN / 4; c0 += kW) {
+    unsigned int hh[kW], cr[kW];
+    tmem_load<kW>(taddr + (unsigned int)c0, hh);
+    tmem_load<kW>(taddr + (unsigned int)(TileSmem<BN, true>::kAccStride + c0), cr);
+#pragma unroll
+    for (int i = 0; i < kW; ++i) v[c0 + i] = __uint_as_float(cr[i]) + __uint_as_float(hh[i]);
+  }
 }
 
 // all accumulator reads of this tile are done: the next tile may overwrite TMEM
@@ -555,7 +562,7 @@ template <int BN>
 struct EpiTile {
   static constexpr int kGroupsPerRow = BN / 4;
   static constexpr int kGroups = kTileM * kGroupsPerRow;
-  static_assert(kTileM * BN * 4 <= TileSmem<BN>::kStageBytes, "staging tile must fit in one operand stage");
+  static_assert(kTileM * BN * 4 <= TileSmem<BN, true>::kStageBytes, "staging tile must fit in one operand stage");
   // float offset of float4 group g of `row`: rows of BN floats, groups XOR-swizzled so that both the per-row writes
   // (32 rows per warp) and the row-contiguous reads are bank-conflict free without padding
   __device__ static __forceinline__ int offset(int row, int g) {

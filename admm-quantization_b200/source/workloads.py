@@ -94,7 +94,7 @@ def product_cost(rows, rank, g, solve_precision=1):
         return 1.0 / g                                   # column strips / small FFMA tiles: scales with the grid
     tiles_m = (rows + 127) // 128
     best = None
-    for bn in (64, 48, 32, 16):
+    for bn in range(128, 15, -16):
         tiles = tiles_m * ((rank + bn - 1) // bn)
         cost = ((tiles + g - 1) // g) * (_TILE_FIXED + bn)
         best = cost if best is None or cost < best else best

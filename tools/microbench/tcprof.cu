@@ -61,4 +61,4 @@ template <int BN, bool PS> void run(int M, int N, int K, int gmax = 148, int bn 
   printf("   producer(thread 0): cp.async wait %lld, stage_free wait %lld, convert+issue %lld, tile_done wait %lld, epilogue %lld\n", h[0], h[1], h[2], h[5], h[6]);
   printf("   mma warp (lane 0) : A-full wait %lld, B-full wait %lld, issue %lld, tile_done wait %lld   => per K-block: full-wait %.0f issue %.0f\n", h[8 + 3], h[8 + 0], h[8 + 4], h[8 + 5], (double)h[11] / (tiles_cta0 * nkb), (double)h[12] / (tiles_cta0 * nkb));
 }
-int main(int argc, char** argv) { int c = argc > 1 ? atoi(argv[1]) : 0; if (c == 0) { run<64, true>(512, 1141, 1144, 32, 48); run<64, true>(512, 1141, 1144, 31); } if (c == 1) run<64, true>(256, 566, 568, 7, 64); if (c == 2) run<64, true>(64, 134, 136, 1, 48); if (c == 3) run<64, true>(4096, 4096, 4096); if (c == 4) run<64, false>(4096, 4096, 4096); if (c == 5) run<32, false>(512, 1141, 1144); return 0; }
+int main(int argc, char** argv) { int c = argc > 1 ? atoi(argv[1]) : 0; if (c == 0) { run<64, true>(512, 1141, 1144, 32, 48); run<128, true>(512, 1141, 1144, 36, 128); run<128, true>(512, 1141, 1144, 32, 80); run<128, true>(512, 1141, 1144, 24, 96); } if (c == 1) run<128, true>(256, 566, 568, 7, 96); if (c == 2) run<64, true>(64, 134, 136, 1, 48); if (c == 3) run<128, true>(4096, 4096, 4096, 148, 128); if (c == 4) run<64, false>(4096, 4096, 4096); if (c == 5) run<64, true>(4608, 1141, 512); if (c == 6) run<128, true>(4608, 1141, 512, 148, 128); return 0; }
