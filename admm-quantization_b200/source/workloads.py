@@ -116,29 +116,47 @@ def predict_sweep_ms(measured_ms, g0, g, modes, solve_precision=1):
 
 
 def allocate_ctas_modelled(layers, sm_count, solve_precision=1):
-    """layers: [(measured_ms, g0, modes)] as for predict_sweep_ms.  Greedy: every layer starts with one CTA, then the
-    layer that is predicted to finish last repeatedly receives the smallest increase of its budget that shortens its
-    predicted time (so budgets move from wave boundary to wave boundary) until the SMs are used up.  Returns the
-    budgets (sum <= sm_count)."""
+    """layers: [(measured_ms, g0, modes)] as for predict_sweep_ms.  Minimax over the model: the smallest common
+    deadline T for which every layer has a budget g_l with predicted time <= T and sum g_l <= sm_count (bisection on T;
+    per layer the smallest such g_l, so budgets sit on wave boundaries), then the SMs that are left go, step by step,
+    to whichever layer is predicted to finish last and still profits.  Returns the budgets (sum <= sm_count)."""
     n = len(layers)
     if n >= sm_count:
         return [1] * n
-    g = [1] * n
-    t = [predict_sweep_ms(m, g0, 1, modes, solve_precision) for m, g0, modes in layers]
-    free = sm_count - n
+    table = [[predict_sweep_ms(m, g0, g, modes, solve_precision) for g in range(1, sm_count + 1)] for m, g0, modes in layers]
+
+    def budgets_for(T):
+        out = []
+        for row in table:
+            g = next((k + 1 for k, t in enumerate(row) if t <= T), None)
+            if g is None:
+                return None
+            out.append(g)
+        return out if sum(out) <= sm_count else None
+
+    lo = max(min(row) for row in table)      # nobody can beat its own best time
+    hi = max(row[0] for row in table)        # one CTA each always fits (n < sm_count)
+    best = budgets_for(hi)
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        b = budgets_for(mid)
+        if b is None:
+            lo = mid
+        else:
+            hi, best = mid, b
+    g = list(best)
+    free = sm_count - sum(g)
     while free > 0:
-        k = max(range(n), key=lambda i: t[i])
-        m, g0, modes = layers[k]
-        step = None
-        for extra in range(1, free + 1):
-            tn = predict_sweep_ms(m, g0, g[k] + extra, modes, solve_precision)
-            if tn < t[k] * (1.0 - 1e-3):
-                step = (extra, tn)
+        order = sorted(range(n), key=lambda i: -table[i][g[i] - 1])
+        moved = False
+        for k in order:
+            cur = table[k][g[k] - 1]
+            step = next((e for e in range(1, free + 1) if table[k][g[k] - 1 + e] < cur * (1.0 - 1e-3)), None)
+            if step is not None:
+                g[k] += step
+                free -= step
+                moved = True
                 break
-        if step is None:
-            break                                        # the slowest layer cannot be sped up with what is left
-        g[k] += step[0]
-        t[k] = step[1]
-        free -= step[0]
-    # leftovers: hand them out one by one to whoever is slowest and still profits
+        if not moved:
+            break
     return g
