@@ -392,6 +392,37 @@ def test_admm_full_size_step_against_oracle(precision):
     torch.set_num_threads(1)
 
 
+def test_tensor_core_product_is_independent_of_the_sm_budget(nat):
+    """The 3xTF32 ridge product picks its tile width from the CTA budget (16 .. 128 columns, 1 .. 3 operand stages
+    configurations); every width accumulates over k in the same order, so ten inner iterations at the layer4 size give
+    BIT-IDENTICAL H and U on 148 CTAs (32-wide tiles), 36 (128-wide, one wave), 33 (80-wide), 24 (96-wide) and 7 CTAs -
+    and they agree with the CPU oracle like the full-grid run does."""
+    from oracle import admm_oracle as orc
+    torch.set_num_threads(4)
+    g = torch.Generator().manual_seed(22)
+    I, R = 512, 1141
+    Bf, Cf = torch.randn(512, R, generator=g), torch.randn(9, R, generator=g)
+    G = ((Bf.T @ Bf) * (Cf.T @ Cf)).cuda()
+    F = (torch.randn(I, R, generator=g) * 30).cuda()
+    H0 = torch.randn(I, R, generator=g)
+    U0 = torch.randn(I, R, generator=g) * 0.1
+    outs = []
+    for ctas in (0, 36, 33, 24, 7):
+        H, U = H0.clone().cuda(), U0.clone().cuda()
+        rep = nat.admm_iteration_inplace(H, U, F, G, 11, 1e-8, 4, MSE, precision=1, max_ctas=ctas)
+        assert nat.read_report(rep).iterations == 10
+        outs.append((H.cpu(), U.cpu()))
+    for H, U in outs[1:]:
+        assert torch.equal(H, outs[0][0]) and torch.equal(U, outs[0][1])
+    Uo = U0.clone()
+    Ho, Uo, _ = orc.admm_iteration(H0.clone(), Uo, F.cpu(), G.cpu(), 3, 1e-8, 4, MSE)
+    H, U = H0.clone().cuda(), U0.clone().cuda()
+    nat.admm_iteration_inplace(H, U, F, G, 3, 1e-8, 4, MSE, precision=1, max_ctas=36)
+    agree, dscale = _agreement(H.cpu().numpy(), Ho.numpy())
+    assert agree >= 0.999 and dscale <= 5e-6, (agree, dscale)
+    torch.set_num_threads(1)
+
+
 # ------------------------------------------------------------------ outer loop
 @pytest.mark.parametrize("precision", [0, 1])
 def test_outer_loop_against_reference_history(golden_outer, capsys, precision):
