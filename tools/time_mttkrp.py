@@ -27,3 +27,15 @@ for mode in range(3):
     F0 = nat.mttkrp(unf[mode], X, Y, 0)
     err = ((F1 - F0).abs().max() / F0.abs().max()).item()
     print(f"mode {mode}: f64 CUDA-core {t0 * 1e3:8.1f} us ({flop / t0 / 1e9:6.1f} TFLOP/s)   3xTF32 tcgen05 {t1 * 1e3:8.1f} us ({flop / t1 / 1e9:6.1f} TFLOP/s fp32-equivalent)   max rel diff {err:.2e}")
+
+# 2-D (matrix) MTTKRP of BASELINE config 5: F = W . B (scripts/factorize.py:277), W (out x in), B (in x R)
+for (M, nx, R2) in [(4096, 4096, 1024), (11008, 4096, 1492), (4096, 11008, 1492)]:
+    Wm = (torch.randn(M, nx, generator=g) * 0.02).cuda()
+    X = torch.randn(nx, R2, generator=g).cuda()
+    ws = torch.empty(nat.mttkrp_tc_workspace_bytes(M, nx, 1, R2), dtype=torch.uint8, device="cuda")
+    F1 = torch.empty(M, R2, device="cuda")
+    t1 = T(lambda: nat.mttkrp_tc(Wm, M, X, None, out=F1, ws=ws))
+    ref = (Wm.double() @ X.double())
+    err = ((F1.double() - ref).abs().max() / ref.abs().max()).item()
+    fl = 2.0 * M * nx * R2
+    print(f"matrix {M} x {nx}, R = {R2}: 3xTF32 tcgen05 {t1 * 1e3:8.1f} us ({fl / t1 / 1e9:6.1f} TFLOP/s fp32-equivalent)   max rel err vs float64 {err:.2e}")
