@@ -392,6 +392,30 @@ def test_admm_full_size_step_against_oracle(precision):
     torch.set_num_threads(1)
 
 
+def test_tensor_core_tile_product_random_shapes(nat):
+    """Ragged shapes through both operand paths of the 3xTF32 tile product (pre-split B via mttkrp_tc incl. 128-wide
+    tiles, on-the-fly split via gemm_nt): one- and two-K-block products, many tiles per CTA, single rows; against
+    float64.  (tools/stress_tc.py runs the long version.)"""
+    g = torch.Generator().manual_seed(4)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    shapes = [(1, 1, 1), (5, 3, 2), (129, 17, 64), (130, 129, 65), (700, 1141, 130), (4608, 300, 512)]
+    shapes += [(ri(1, 900), ri(1, 1500), ri(1, 1300)) for _ in range(10)]
+    for M, R, nx in shapes:
+        W = torch.randn(M, nx, generator=g).cuda()
+        X = torch.randn(nx, R, generator=g).cuda()
+        ldv = (nx + 3) // 4 * 4
+        V = torch.zeros(M, ldv, device="cuda")
+        V[:, :nx] = W
+        ref = W.double() @ X.double()
+        scale = float(ref.abs().max().clamp_min(1e-30))
+        F = nat.mttkrp_tc(V, M, X, None)
+        assert float((F.double() - ref).abs().max()) <= 2e-5 * scale, (M, R, nx)
+        Xt = torch.zeros(R, ldv, device="cuda")
+        Xt[:, :nx] = X.t()
+        C = nat.gemm_nt(V, Xt)
+        assert float((C.double() - ref).abs().max()) <= 2e-5 * scale, (M, R, nx)
+
+
 def test_tensor_core_product_is_independent_of_the_sm_budget(nat):
     """The 3xTF32 ridge product picks its tile width from the CTA budget (16 .. 128 columns, 1 .. 3 operand stages
     configurations); every width accumulates over k in the same order, so ten inner iterations at the layer4 size give
