@@ -16,6 +16,8 @@ namespace admmq {
 
 int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, int ldb, int N, int K, float* C, int ldc,
             cudaStream_t stream);  // tc_gemm.cu
+int mttkrp_fold_gemm(const float* V, int ldv, int Mout, int ny, const float* B, const float* Blo, int ldb, int N, int K,
+                     const float* Y, float* F, cudaStream_t stream);  // tc_gemm.cu
 
 constexpr int kTT = 256;
 
@@ -107,6 +109,10 @@ int mttkrp_tc(const float* V, int M, const float* X, int nx, const float* Y, int
   k_transpose_split<<<tg, kTT, 0, stream>>>(X, nx, R, Xt, XtLo, ldx, -0.0f);  // (R x ldx) = X^T, pad columns zero
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);
+  if (ny > 1 && ny <= 128) {
+    // the fold over the small index happens in the GEMM's epilogue: T is never materialised
+    return mttkrp_fold_gemm(V, ldx, M, ny, Xt, XtLo, ldx, R, nx, Y, F, stream);
+  }
   if (int e = gemm_nt(V, ldx, M * ny, Xt, XtLo, ldx, R, nx, T, R, stream)) return e;
   if (ny > 1) {
     const long long n = (long long)M * R;

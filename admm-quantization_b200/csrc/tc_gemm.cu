@@ -75,6 +75,44 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
   tc::pipe_teardown(pipe);
 }
 
+// MTTKRP with the fold of the small tensor index inside the epilogue (mttkrp_tc.cu):
+//   F[m, r] = sum_y Y[y, r] * T[(m, y), r],   T = A . B^T with A rows (m, y) = the (m, y, x)-permuted tensor, B = X^T.
+// A tile takes mg = 128 / ny whole m (rows m0 * ny .. +mg * ny - 1 of A; the TMA box still loads 128 rows, the extra
+// ones belong to the next tile and are ignored), so the fold over y happens on the accumulator parked in shared memory
+// and T never goes to global memory.  float64 accumulation over y like the stand-alone fold kernel.
+template <int BN>
+__global__ void __launch_bounds__(tc::kThreadsTC, 1)
+k_mttkrp_fold_tc(const __grid_constant__ GemmMaps maps, int Mout, int ny, int N, int K, const float* __restrict__ Y,
+                 float* __restrict__ F, float neg_zero) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ tc::Pipe pipe;
+  tc::PipeState st;
+  tc::pipe_setup(pipe, st, neg_zero);
+  const int mg = tc::kTileM / ny;  // m per tile
+  const int tilesM = (Mout + mg - 1) / mg, tilesN = (N + BN - 1) / BN;
+  for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
+    const int m0 = (tile / tilesN) * mg, n0 = (tile % tilesN) * BN;
+    const int next = tile + (int)gridDim.x;
+    const bool has_next = next < tilesM * tilesN;
+    tc::tile_3xtf32<BN, true>(&maps.a, m0 * ny, &maps.b, &maps.blo, n0, BN, K, smem_dyn, pipe, st,
+                              has_next ? (next / tilesN) * mg * ny : -1, has_next ? (next % tilesN) * BN : -1);
+    const float* tile_c = tc::acc_to_smem<BN, true>(pipe, smem_dyn);
+    using ET = tc::EpiTile<BN>;
+    for (int idx = threadIdx.x; idx < mg * BN; idx += tc::kThreadsTC) {
+      const int ml = idx / BN, c = idx - ml * BN;
+      const int m = m0 + ml, n = n0 + c;
+      if (m < Mout && n < N) {
+        double acc = 0.0;
+        for (int y = 0; y < ny; ++y)
+          acc = fma((double)__ldg(Y + (size_t)y * N + n), (double)tile_c[ET::offset(ml * ny + y, c >> 2) + (c & 3)], acc);
+        F[(size_t)m * N + n] = (float)acc;
+      }
+    }
+    __syncthreads();
+  }
+  tc::pipe_teardown(pipe);
+}
+
 template <int BN, bool PS>
 static int launch_gemm(const GemmMaps& maps, int M, int N, int K, float* C, int ldc, int grid, cudaStream_t stream) {
   const int smem = tc::TileSmem<BN, PS>::kBytes;
@@ -128,6 +166,48 @@ int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, in
                              : launch_gemm<16, false>(maps, M, N, K, C, ldc, grid, stream));
   }
   if (e) return e;
+  ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(1);
+  return ADMMQ_OK;
+}
+
+// F (Mout x N) = fold_y( V ((Mout * ny) x K, ld ldv) . Bhi/Blo (N x K, ld ldb)^T , Y (ny x N) ), see k_mttkrp_fold_tc
+int mttkrp_fold_gemm(const float* V, int ldv, int Mout, int ny, const float* B, const float* Blo, int ldb, int N, int K,
+                     const float* Y, float* F, cudaStream_t stream) {
+  if (ny < 1 || ny > tc::kTileM) return fail(ADMMQ_E_UNSUPPORTED, "mttkrp_fold_gemm: ny must be in 1..128");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "the tensor-core MTTKRP needs an sm_100 device (tcgen05)");
+  const int mg = tc::kTileM / ny;
+  const long long tilesM = (Mout + mg - 1) / mg;
+  int bn = 64;
+  {
+    long long best = -1;
+    const int widths[2] = {128, 64};
+    for (int w = 0; w < 2; ++w) {
+      const long long tiles_w = tilesM * ((N + widths[w] - 1) / widths[w]);
+      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (128 + widths[w]);
+      if (best < 0 || cost < best) {
+        best = cost;
+        bn = widths[w];
+      }
+    }
+  }
+  const long long tiles = tilesM * ((N + bn - 1) / bn);
+  const int grid = (int)std::min<long long>(tiles, dp.sm_count);
+  GemmMaps maps;
+  if (int e = tc::make_operand_tmap(&maps.a, V, Mout * ny, K, ldv, tc::kTileM)) return e;
+  if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
+  if (int e = tc::make_operand_tmap(&maps.blo, Blo, N, K, ldb, bn)) return e;
+  if (bn == 128) {
+    const int smem = tc::TileSmem<128, true>::kBytes;
+    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mttkrp_fold_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_mttkrp_fold_tc<128><<<grid, tc::kThreadsTC, smem, stream>>>(maps, Mout, ny, N, K, Y, F, -0.0f);
+  } else {
+    const int smem = tc::TileSmem<64, true>::kBytes;
+    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mttkrp_fold_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_mttkrp_fold_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, Mout, ny, N, K, Y, F, -0.0f);
+  }
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return ADMMQ_OK;
