@@ -33,6 +33,14 @@ class FactorizeParams(ctypes.Structure):
                 ("mttkrp_precision", ctypes.c_int32), ("max_ctas", ctypes.c_int32), ("init_is_random", ctypes.c_int32)]
 
 
+class Problem(ctypes.Structure):
+    _fields_ = [("W", ctypes.c_void_p), ("ndim", ctypes.c_int32), ("shape", ctypes.c_int32 * 3), ("rank", ctypes.c_int32),
+                ("factors", ctypes.c_void_p * 3), ("duals", ctypes.c_void_p * 3), ("factors_q", ctypes.c_void_p * 3),
+                ("params", FactorizeParams), ("loss_hist", ctypes.c_void_p), ("loss_quant_hist", ctypes.c_void_p),
+                ("sweeps_done", ctypes.POINTER(ctypes.c_int32)), ("workspace", ctypes.c_void_p),
+                ("workspace_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -71,6 +79,7 @@ def _load():
                                 [ctypes.POINTER(FactorizeParams), vp, vp, ctypes.POINTER(c_int), vp, c_sz, vp]),
         "admmq_factorize_mat": (c_int, [vp, c_int, c_int, c_int] + [vp] * 6 +
                                 [ctypes.POINTER(FactorizeParams), vp, vp, ctypes.POINTER(c_int), vp, c_sz, vp]),
+        "admmq_factorize_batch": (c_int, [c_int, ctypes.POINTER(Problem)]),
         "admmq_admm_iteration_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_admm_iteration": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
                                          vp, vp, vp, c_sz, vp]),
@@ -89,7 +98,7 @@ EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count 
            "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
            "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration "
-           "admmq_factorize_workspace_bytes admmq_factorize_cp3 admmq_factorize_mat "
+           "admmq_factorize_workspace_bytes admmq_factorize_cp3 admmq_factorize_mat admmq_factorize_batch "
            "admmq_split_loop_workspace_bytes admmq_split_loop").split()
 
 
@@ -412,6 +421,53 @@ def factorize(W, factors, duals, bits, qscheme, max_iter_als, max_iter_admm=1000
     check(rc)
     n = done.value + (0 if init_is_random else 1)
     return [float(v) for v in hist[:n]], [float(v) for v in histq[:n]], done.value, fq
+
+
+def factorize_batch(jobs):
+    """Several independent solves side by side (admmq_factorize_batch).  jobs: list of dicts with W, factors, duals
+    (updated in place), bits, qscheme, max_iter_als and optionally max_iter_admm, eps, tol, num_attempts,
+    solve_precision, mttkrp_precision, max_ctas, init_is_random, stream (torch.cuda.Stream).  Returns one
+    (loss_hist, loss_quant_hist, sweeps_done, factors_q) per job."""
+    import numpy as np
+    n = len(jobs)
+    arr = (Problem * n)()
+    keep = []
+    for k, j in enumerate(jobs):
+        Wc = f32c(j["W"])
+        require_cuda(Wc, *j["factors"], *j["duals"])
+        N = Wc.ndim
+        R = j["factors"][0].shape[1]
+        prm = FactorizeParams(int(j["max_iter_als"]), int(j.get("max_iter_admm", 1000)), float(j.get("eps", 1e-8)),
+                              float(j.get("tol", 1e-5)), int(j["bits"]), qscheme_id(j["qscheme"]),
+                              int(j.get("num_attempts", 200)), int(j.get("solve_precision", 0)),
+                              int(j.get("mttkrp_precision", 0)), int(j.get("max_ctas", 0)),
+                              1 if j.get("init_is_random", True) else 0)
+        shape = (ctypes.c_int * N)(*[int(d) for d in Wc.shape])
+        need = int(lib.admmq_factorize_workspace_bytes(N, shape, R, ctypes.byref(prm)))
+        ws = torch.empty(need, dtype=torch.uint8, device=Wc.device)
+        fq = [torch.empty_like(f) for f in j["factors"]]
+        hist = np.zeros(prm.max_iter_als + 1, np.float32)
+        histq = np.zeros(prm.max_iter_als + 1, np.float32)
+        done = ctypes.c_int32(0)
+        stream = j.get("stream") or torch.cuda.Stream(device=Wc.device)
+        stream.wait_stream(torch.cuda.current_stream(Wc.device))
+        q = arr[k]
+        q.W, q.ndim, q.rank = Wc.data_ptr(), N, R
+        for m in range(N):
+            q.shape[m] = int(Wc.shape[m])
+            q.factors[m], q.duals[m], q.factors_q[m] = j["factors"][m].data_ptr(), j["duals"][m].data_ptr(), fq[m].data_ptr()
+        q.params = prm
+        q.loss_hist, q.loss_quant_hist = hist.ctypes.data, histq.ctypes.data
+        q.sweeps_done = ctypes.pointer(done)
+        q.workspace, q.workspace_bytes, q.stream = ws.data_ptr(), ws.numel(), stream.cuda_stream
+        keep.append((Wc, ws, fq, hist, histq, done, stream, prm))
+    check(lib.admmq_factorize_batch(n, arr))
+    out = []
+    for Wc, ws, fq, hist, histq, done, stream, prm in keep:
+        torch.cuda.current_stream(Wc.device).wait_stream(stream)
+        cnt = done.value + (0 if prm.init_is_random else 1)
+        out.append(([float(v) for v in hist[:cnt]], [float(v) for v in histq[:cnt]], done.value, fq))
+    return out
 
 
 def launch_count() -> int:

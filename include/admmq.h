@@ -230,6 +230,28 @@ ADMMQ_API int admmq_factorize_mat(const float* W, int I, int J, int R, float* A,
                         float* Aq, float* Bq, const admmq_factorize_params* params, float* loss_hist,
                         float* loss_quant_hist, int* sweeps_done, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Independent solves side by side (layers x reduction rates x bit-widths): one descriptor per problem, each with its
+ * own stream, workspace (admmq_factorize_workspace_bytes) and cooperative-grid budget params.max_ctas; the problems
+ * are enqueued round by round (one outer sweep each) and overlap on the GPU.  Same results as one admmq_factorize_*
+ * call per problem. */
+typedef struct admmq_problem {
+  const float* W;          /* device */
+  int32_t ndim;            /* 2 or 3 */
+  int32_t shape[3];
+  int32_t rank;
+  float* factors[3];       /* device, IN/OUT */
+  float* duals[3];         /* device, IN/OUT */
+  float* factors_q[3];     /* device, OUT */
+  admmq_factorize_params params;
+  float* loss_hist;        /* HOST, params.max_iter_als + 1 floats */
+  float* loss_quant_hist;  /* HOST */
+  int32_t* sweeps_done;    /* HOST */
+  void* workspace;         /* device, 256-byte aligned */
+  size_t workspace_bytes;
+  void* stream;            /* cudaStream_t of this problem */
+} admmq_problem;
+ADMMQ_API int admmq_factorize_batch(int n_problems, const admmq_problem* problems);
+
 #ifdef __cplusplus
 }
 #endif

@@ -551,6 +551,30 @@ def test_c_level_outer_loop_equals_python_orchestration(nat, golden_outer):
     assert n == m["sweeps"] and abs(hist[0] - ref[0]) <= 1e-3 * ref[0] and abs(hist[1] - ref[1]) <= 1e-3 * ref[1]
 
 
+def test_batched_solves_equal_individual_calls(nat):
+    """admmq_factorize_batch: independent problems (two tensors, one matrix; different ranks, bit-widths, budgets and
+    stop points) interleaved sweep by sweep on their own streams give exactly what one call per problem gives."""
+    from source import workloads as wl
+    g = torch.Generator().manual_seed(8)
+    specs = [((24, 20, 9), 30, 4, 5, 20, 3), ((32, 16, 9), 17, 3, 3, 15, 2), ((40, 28), 12, 8, 12, 12, 0)]
+    jobs, ref = [], []
+    for shape, R, bits, sweeps, inner, ctas in specs:
+        W = (torch.randn(*shape, generator=g) * 0.05).cuda()
+        init = wl.random_init(shape, R, 11)
+        fa = [f.clone().cuda() for f in init]
+        da = [torch.zeros_like(f) for f in fa]
+        ref.append((nat.factorize(W, fa, da, bits, MSE, sweeps, inner, solve_precision=1, mttkrp_precision=1, max_ctas=ctas), fa, da))
+        fb = [f.clone().cuda() for f in init]
+        jobs.append(dict(W=W, factors=fb, duals=[torch.zeros_like(f) for f in fb], bits=bits, qscheme=MSE, max_iter_als=sweeps,
+                         max_iter_admm=inner, solve_precision=1, mttkrp_precision=1, max_ctas=ctas))
+    out = nat.factorize_batch(jobs)
+    torch.cuda.synchronize()
+    for (hist, histq, n, fq), ((rh, rhq, rn, rfq), fa, da), job in zip(out, ref, jobs):
+        assert n == rn and hist == rh and histq == rhq
+        for a, b in zip(job["factors"] + job["duals"] + fq, fa + da + rfq):
+            assert torch.equal(a, b)
+
+
 def test_two_block_splitting_quantized_block_bit_exact(nat):
     """admmq_split_loop (quantized block of scripts/factorize_lowrank.py:84-101) against the CPU restatement: the
     least-squares step is elementwise in the reference's operation order and the projection is bit-exact, so H and U
