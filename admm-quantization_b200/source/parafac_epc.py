@@ -101,12 +101,13 @@ def _mu_by_eigh(gamma, T, norm_y2, target):
         lo, hi = floor, max(float(sig_c.max()), 1e-300)
         while resid(hi) < target and hi < 1e300:
             hi *= 2.0
-        for _ in range(200):
-            mid = 0.5 * (lo + hi)
-            if resid(mid) < target:
-                lo = mid
-            else:
-                hi = mid
+        # 64-way subdivision instead of plain bisection: 9 vectorised evaluations reach 1e-15 relative width
+        for _ in range(12):
+            grid = lo + (hi - lo) * (np.arange(1, 64) / 64.0)
+            d = sig_c[None, :] + grid[:, None]
+            vals = norm_y2 - np.sum(s_c[None, :] * (d + grid[:, None]) / (d * d), axis=1)
+            k = int(np.searchsorted(vals >= target, True))      # first grid point with residual >= target
+            lo, hi = (grid[k - 1] if k > 0 else lo), (grid[k] if k < 63 else hi)
             if hi - lo <= 1e-15 * hi:
                 break
         mu = 0.5 * (lo + hi)
