@@ -14,10 +14,12 @@
 // State (H, U, F, H_ls, RHS, Minv) stays L2 resident for the whole call: per iteration the
 // algorithmic traffic is 16 B per element of H plus one pass over Minv, all served from L2.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "search.cuh"
 #include "spd_inverse.cuh"
 #include "tc_gemm.cuh"
+#include "admm_loop_resident.cuh"
 
 namespace admmq {
 
@@ -687,6 +689,32 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
                        int I, int R, int max_iter, float eps, int bits, int qscheme, int num_attempts, int precision,
                        int8_t* codes, admmq_loop_report* report, char* ws, int grid, cudaStream_t stream) {
   const LoopLayout l = loop_layout(I, R, grid);
+  static const bool no_resident = getenv("ADMMQ_NO_RESIDENT") != nullptr;  // diagnostics: force the general kernel
+  if (grid == 1 && !no_resident && resident_fits(I, R, l.Rp, num_attempts)) {
+    // a small factor on a single CTA: the shared-memory-resident loop (admm_loop_resident.cuh)
+    ResidentParams rp;
+    rp.H = H;
+    rp.U = U;
+    rp.F = F;
+    rp.Minv = Minv;
+    rp.rho = rho;
+    rp.inv_status = inv_status;
+    rp.I = I;
+    rp.R = R;
+    rp.Rp = l.Rp;
+    rp.max_iter = max_iter;
+    rp.eps = eps;
+    rp.bits = bits;
+    rp.scheme = qscheme;
+    rp.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
+    rp.codes = codes;
+    rp.report = report;
+    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_admm_loop_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResidentSmem)));
+    k_admm_loop_resident<<<1, kThreads, sizeof(ResidentSmem), stream>>>(rp);
+    ADMMQ_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return ADMMQ_OK;
+  }
   // header + candidate accumulators + RHS (its pad columns must be zero)
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, l.slots, stream));
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws + l.rhs, 0, (size_t)I * l.Rp * sizeof(float), stream));

@@ -47,10 +47,6 @@ struct GridBarrier {
   }
   __device__ __forceinline__ void sync() {
     __syncthreads();
-    if (gridDim.x == 1) {  // a single CTA: its own __syncthreads orders everything (global writes included)
-      __threadfence_block();
-      return;
-    }
     target += gridDim.x;
     if (threadIdx.x == 0) {
       __threadfence();

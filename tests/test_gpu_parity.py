@@ -392,6 +392,56 @@ def test_admm_full_size_step_against_oracle(precision):
     torch.set_num_threads(1)
 
 
+def test_shared_memory_resident_loop_for_small_factors(nat):
+    """A factor that fits in shared memory (64 x 134, 9 x 134) on a budget of one CTA runs the resident kernel
+    (csrc/admm_loop_resident.cuh): same float32 recipe as the general kernel up to the summation order of the ridge
+    product, so codes agree with the CPU oracle and with the general kernel; U is updated in place, the exit test and
+    the NaN semantics of a degenerate projection are those of the general kernel."""
+    from oracle import admm_oracle as orc
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(33)
+    for (I, R, bits, qs) in [(64, 134, 4, MSE), (9, 134, 4, MSE), (64, 134, 3, MSE), (48, 100, 8, "tensor_minmax"), (64, 134, 4, "tensor_affine")]:
+        Bf, Cf = torch.randn(64, R, generator=g), torch.randn(9, R, generator=g)
+        G = (Bf.T @ Bf) * (Cf.T @ Cf)
+        F = torch.randn(I, R, generator=g) * 24
+        H0 = torch.randn(I, R, generator=g)
+        U0 = torch.randn(I, R, generator=g) * 0.1
+        def close_frac(a, b, ref):   # share of elements that agree to 1e-4 of the scale of ref
+            return float(((a - b).abs() <= 1e-4 * float(ref.abs().max())).float().mean())
+        for max_iter, need in ((2, 0.9999), (4, 0.999)):
+            Uo = U0.clone()
+            Ho, Uo, _ = orc.admm_iteration(H0.clone(), Uo, F, G, max_iter, 1e-8, bits, qs)
+            outs = []
+            for ctas in (1, 0):
+                H, U = H0.clone().cuda(), U0.clone().cuda()
+                rep = nat.read_report(nat.admm_iteration_inplace(H, U, F.cuda(), G.cuda(), max_iter, 1e-8, bits, qs, precision=0, max_ctas=ctas))
+                assert rep.iterations == max_iter - 1
+                outs.append((H.cpu(), U.cpu()))
+            assert close_frac(outs[0][0], Ho, Ho) >= need, (I, R, bits, qs, max_iter)
+            assert close_frac(outs[0][0], outs[1][0], Ho) >= need, (I, R, bits, qs, max_iter)
+            if max_iter == 2:
+                # one step from identical state: the dual agrees too (later a single flipped code moves a whole row of
+                # the next H_ls, SURVEY App. E; U = u + (H - H_ls) is compared on the scale of H)
+                assert close_frac(outs[0][1], Uo, Ho) >= need and close_frac(outs[0][1], outs[1][1], Ho) >= need, (I, R, bits, qs)
+    # long run: stays on the general kernel's trajectory for dozens of iterations
+    Bf, Cf = torch.randn(64, 134, generator=g), torch.randn(9, 134, generator=g)
+    G = ((Bf.T @ Bf) * (Cf.T @ Cf)).cuda()
+    F = (torch.randn(64, 134, generator=g) * 24).cuda()
+    H0 = torch.randn(64, 134, generator=g).cuda()
+    res = []
+    for ctas in (1, 0):
+        H, U = H0.clone(), torch.zeros_like(H0)
+        nat.admm_iteration_inplace(H, U, F, G, 41, 1e-8, 4, MSE, precision=0, max_ctas=ctas)
+        res.append(H.cpu().numpy())
+    agree, _ = _agreement(res[0], res[1])
+    assert agree >= 0.99, agree
+    # degenerate projection: all-zero state -> NaN everywhere, status NONFINITE (reference: scale 0)
+    Z = torch.zeros(64, 134).cuda()
+    H, U = Z.clone(), Z.clone()
+    rep = nat.read_report(nat.admm_iteration_inplace(H, U, Z.clone(), G, 5, 1e-8, 4, MSE, precision=0, max_ctas=1))
+    assert rep.status & nat.ST_NONFINITE and torch.isnan(H).all()
+
+
 def test_tensor_core_tile_product_random_shapes(nat):
     """Ragged shapes through both operand paths of the 3xTF32 tile product (pre-split B via mttkrp_tc incl. 128-wide
     tiles, on-the-fly split via gemm_nt): one- and two-K-block products, many tiles per CTA, single rows; against
