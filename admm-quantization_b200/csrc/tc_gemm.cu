@@ -133,15 +133,15 @@ int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, in
   if (int e = device_props(&dp)) return e;
   if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "admmq_gemm_nt needs an sm_100 device (tcgen05)");
   const int tilesM = (M + tc::kTileM - 1) / tc::kTileM;
-  // tile width: a tile costs its 128 rows of A (staging, independent of the width) plus bn columns of tensor-core work;
-  // minimise waves * (128 + bn), ties go to the wider tile (128-wide tiles need the pre-split B operand)
+  // tile width: a tile costs a fixed part plus bn columns of tensor-core work (measured 3.3 + 0.225 bn us at K = 1141);
+  // minimise waves * (16 + bn), ties go to the wider tile (128-wide tiles need the pre-split B operand)
   int bn = 16;
   {
     long long best = -1;
     const int widths[4] = {128, 64, 32, 16};
     for (int w = (Blo != nullptr ? 0 : 1); w < 4; ++w) {
       const long long tiles_w = (long long)tilesM * ((N + widths[w] - 1) / widths[w]);
-      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (128 + widths[w]);
+      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (16 + widths[w]);
       if (best < 0 || cost < best) {
         best = cost;
         bn = widths[w];
@@ -186,7 +186,7 @@ int mttkrp_fold_gemm(const float* V, int ldv, int Mout, int ny, const float* B, 
     const int widths[2] = {128, 64};
     for (int w = 0; w < 2; ++w) {
       const long long tiles_w = tilesM * ((N + widths[w] - 1) / widths[w]);
-      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (128 + widths[w]);
+      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (16 + widths[w]);
       if (best < 0 || cost < best) {
         best = cost;
         bn = widths[w];

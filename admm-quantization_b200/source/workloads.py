@@ -84,7 +84,7 @@ def lpt_assign(costs, n_bins):
 # ridge product works in whole waves of 128 x bn tiles, so its time is a STEP function of g (72 tiles of width 64 take 3
 # waves on 24 .. 35 CTAs and 2 on 36), while the clip search / dual update scale like 1/g above a latency floor.  The
 # budgets are chosen from that model, fitted to the phase times the kernels report (admmq_loop_report.phase_ns).
-_TILE_FIXED = 128          # csrc/admm_loop.cu kTileFixed: tile cost that does not depend on its width
+_TILE_FIXED = 16           # csrc/admm_loop.cu kTileFixed: tile cost that does not depend on its width
 _PHASE_FLOOR_US = 14.0     # P2 + P3 of a factor that is too small to matter: barriers and L2 round trips
 
 

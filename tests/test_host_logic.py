@@ -216,7 +216,7 @@ def test_modelled_sm_budgets_follow_the_wave_structure():
     costs = [wl.product_cost(512, 1141, g) for g in range(1, 149)]
     assert all(a >= b for a, b in zip(costs, costs[1:]))                         # more CTAs never hurt ...
     assert len(set(costs)) < 40                                                  # ... but only at wave boundaries
-    assert wl.product_cost(512, 1141, 36) == 256.0 < wl.product_cost(512, 1141, 35)   # 36 tiles of 128: one wave
+    assert wl.product_cost(512, 1141, 36) == 144.0 < wl.product_cost(512, 1141, 35)   # 36 tiles of 128: one wave
     assert wl.product_cost(9, 1141, 8) == pytest.approx(2 * wl.product_cost(9, 1141, 16))                      # skinny: 1 / g
     big = (297.0, 31, [(512, 1141, 61.0, 40.8, 999), (512, 1141, 61.0, 40.8, 999), (9, 1141, 17.0, 20.0, 999)])
     mid = (270.0, 7, [(256, 566, 40.0, 51.0, 999), (256, 566, 40.0, 51.0, 999), (9, 566, 18.0, 19.0, 999)])
