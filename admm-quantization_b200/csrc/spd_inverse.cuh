@@ -23,6 +23,8 @@ struct InvSmem {
   double a[kNB][kNB + 1];
   double b[kNB][kNB + 1];
   double c[kNB][kNB + 1];
+  double a2[kNB][kNB + 1];  // second buffers of the software-pipelined inner loops: step q computes from one pair
+  double b2[kNB][kNB + 1];  // while step q+1 is stashed into the other, so one barrier per step is enough
   double red[kInvThreads];
   int flag;
 };
@@ -41,6 +43,23 @@ struct InvParams {
 
 __device__ __forceinline__ void inv_load_tile(double (*dst)[kNB + 1], const double* src, int ld) {
   for (int i = threadIdx.x; i < kNB * kNB; i += kInvThreads) dst[i >> 5][i & 31] = __ldcg(src + (size_t)(i >> 5) * ld + (i & 31));
+}
+
+// The same tile load split in two halves, so that the L2 round trip of step q+1 overlaps the FMA loop of step q:
+// fetch (global -> registers) before the compute, stash (registers -> shared memory) after the next barrier.
+__device__ __forceinline__ void inv_fetch_tile(double r[4], const double* src, int ld) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int i = threadIdx.x + m * kInvThreads;
+    r[m] = __ldcg(src + (size_t)(i >> 5) * ld + (i & 31));
+  }
+}
+__device__ __forceinline__ void inv_stash_tile(double (*dst)[kNB + 1], const double r[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int i = threadIdx.x + m * kInvThreads;
+    dst[i >> 5][i & 31] = r[m];
+  }
 }
 
 // acc[m] (+/-)= sum_q A[row_m][q] * B[c][q]      (B used transposed)
@@ -139,13 +158,23 @@ __device__ inline int spd_inverse_body(const InvParams& p, InvSmem& sm, GridBarr
         double acc[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) acc[m] = __ldcg(tile + (size_t)(rg + 8 * m) * Rb + c);
+        double ra[4], rb[4];
+        inv_fetch_tile(ra, p.Lw + ((size_t)i * kNB) * Rb, Rb);
+        inv_fetch_tile(rb, p.Lw + ((size_t)k * kNB) * Rb, Rb);
+        __syncthreads();
         for (int q = 0; q < k; ++q) {
+          double (*ta)[kNB + 1] = (q & 1) ? sm.a2 : sm.a;
+          double (*tb)[kNB + 1] = (q & 1) ? sm.b2 : sm.b;
+          inv_stash_tile(ta, ra);
+          inv_stash_tile(tb, rb);
           __syncthreads();
-          inv_load_tile(sm.a, p.Lw + ((size_t)i * kNB) * Rb + (size_t)q * kNB, Rb);
-          inv_load_tile(sm.b, p.Lw + ((size_t)k * kNB) * Rb + (size_t)q * kNB, Rb);
-          __syncthreads();
-          inv_mma_nt(acc, sm.a, sm.b, -1.0);
+          if (q + 1 < k) {
+            inv_fetch_tile(ra, p.Lw + ((size_t)i * kNB) * Rb + (size_t)(q + 1) * kNB, Rb);
+            inv_fetch_tile(rb, p.Lw + ((size_t)k * kNB) * Rb + (size_t)(q + 1) * kNB, Rb);
+          }
+          inv_mma_nt(acc, ta, tb, -1.0);
         }
+        __syncthreads();
 #pragma unroll
         for (int m = 0; m < 4; ++m) tile[(size_t)(rg + 8 * m) * Rb + c] = acc[m];
       }
@@ -184,12 +213,21 @@ __device__ inline int spd_inverse_body(const InvParams& p, InvSmem& sm, GridBarr
     for (int k = blockIdx.x; k < nb - d; k += gridDim.x) {
       const int i = k + d;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      double ra[4], rb[4];
+      inv_fetch_tile(ra, p.Lw + ((size_t)i * kNB) * Rb + (size_t)k * kNB, Rb);
+      inv_fetch_tile(rb, p.Xw + ((size_t)k * kNB) * Rb + (size_t)k * kNB, Rb);
+      __syncthreads();
       for (int j = k; j < i; ++j) {
+        double (*ta)[kNB + 1] = ((j - k) & 1) ? sm.a2 : sm.a;
+        double (*tb)[kNB + 1] = ((j - k) & 1) ? sm.b2 : sm.b;
+        inv_stash_tile(ta, ra);
+        inv_stash_tile(tb, rb);
         __syncthreads();
-        inv_load_tile(sm.a, p.Lw + ((size_t)i * kNB) * Rb + (size_t)j * kNB, Rb);
-        inv_load_tile(sm.b, p.Xw + ((size_t)j * kNB) * Rb + (size_t)k * kNB, Rb);
-        __syncthreads();
-        inv_mma_nn(acc, sm.a, sm.b, 1.0);
+        if (j + 1 < i) {
+          inv_fetch_tile(ra, p.Lw + ((size_t)i * kNB) * Rb + (size_t)(j + 1) * kNB, Rb);
+          inv_fetch_tile(rb, p.Xw + ((size_t)(j + 1) * kNB) * Rb + (size_t)k * kNB, Rb);
+        }
+        inv_mma_nn(acc, ta, tb, 1.0);
       }
       __syncthreads();
 #pragma unroll
@@ -214,13 +252,23 @@ __device__ inline int spd_inverse_body(const InvParams& p, InvSmem& sm, GridBarr
     }
     const int b = rem;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double ra[4], rb[4];
+    inv_fetch_tile(ra, p.Xw + ((size_t)a * kNB) * Rb + (size_t)a * kNB, Rb);
+    inv_fetch_tile(rb, p.Xw + ((size_t)a * kNB) * Rb + (size_t)b * kNB, Rb);
+    __syncthreads();
     for (int q = a; q < nb; ++q) {
+      double (*ta)[kNB + 1] = ((q - a) & 1) ? sm.a2 : sm.a;
+      double (*tb)[kNB + 1] = ((q - a) & 1) ? sm.b2 : sm.b;
+      inv_stash_tile(ta, ra);
+      inv_stash_tile(tb, rb);
       __syncthreads();
-      inv_load_tile(sm.a, p.Xw + ((size_t)q * kNB) * Rb + (size_t)a * kNB, Rb);
-      inv_load_tile(sm.b, p.Xw + ((size_t)q * kNB) * Rb + (size_t)b * kNB, Rb);
-      __syncthreads();
-      inv_mma_tn(acc, sm.a, sm.b);
+      if (q + 1 < nb) {
+        inv_fetch_tile(ra, p.Xw + ((size_t)(q + 1) * kNB) * Rb + (size_t)a * kNB, Rb);
+        inv_fetch_tile(rb, p.Xw + ((size_t)(q + 1) * kNB) * Rb + (size_t)b * kNB, Rb);
+      }
+      inv_mma_tn(acc, ta, tb);
     }
+    __syncthreads();
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const int row = a * kNB + rg + 8 * m, col = b * kNB + c;
