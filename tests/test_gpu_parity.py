@@ -752,3 +752,35 @@ def test_model_top1_with_our_factors_vs_reference_factors(capsys, precision):
     # so a two-sided band only holds to the sampling noise of the evaluation
     assert accs[0] >= accs[1] - 0.1 and abs(accs[0] - accs[1]) <= 0.5
     torch.set_num_threads(1)
+
+
+# ------------------------------------------------------------------ CLI and file contract
+def test_factorize_cli_writes_the_reference_file_set(tmp_path, monkeypatch):
+    """scripts/factorize.py: flags, output directory and file names of the reference (:164-166, 315-318, 345-347) and
+    the consumer side (scripts/calibrate.py) reading exactly those files."""
+    import importlib.util
+    monkeypatch.chdir(tmp_path)
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                         "admm-quantization_b200", "scripts", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    fz = load("factorize")
+    err, errq = fz.main(["--model-name", "resnet18", "--method", "admm", "--init", "random", "--layer", "layer1.0.conv1",
+                         "--reduction-rate", "2", "--bits", "4", "--qscheme", MSE, "--seed", "42",
+                         "--max_iter_als", "2", "--max_iter_admm", "20"])
+    d = tmp_path / f"4bit_{MSE}" / "factors_admm_seed42"
+    names = sorted(p.name for p in d.iterdir())
+    prefix = "layer1.0.conv1_admm_random_rank_134_"
+    assert names == sorted(prefix + s for s in ("losshist.pt", "lossquanthist.pt", "mode_0.pt", "mode_1.pt", "mode_2.pt"))
+    shapes = [tuple(torch.load(d / (prefix + f"mode_{m}.pt")).shape) for m in range(3)]
+    assert shapes == [(64, 134), (64, 134), (9, 134)]
+    assert torch.load(d / (prefix + "mode_0.pt")).dtype == torch.float32
+    hist = torch.load(d / (prefix + "losshist.pt"))
+    assert len(hist) == 2 and 0.5 < hist[-1] < 1.0 and abs(err - hist[-1]) < 1e-3 and abs(errq - err) < 1e-2
+    with pytest.raises(SystemExit):
+        fz.parse_args(["--model-name", "resnet18"])                       # required flags (:38-102)
+    acc = load("calibrate").main(["--bits", "4", "--qscheme", MSE, "--seed", "42", "--layers", "layer1.0.conv1",
+                                  "--eval-batches", "2", "--batch-size", "16", "--calibration-samples", "32"])
+    assert 0.0 <= acc <= 100.0
