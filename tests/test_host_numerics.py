@@ -188,6 +188,28 @@ def test_library_exports_every_declared_symbol():
     assert _native.lib.admmq_admm_iteration_workspace_bytes(64, 134, 200) > 0
 
 
+def test_binding_argument_counts_match_the_header():
+    """Every prototype of include/admmq.h against the ctypes signature of source/_native.py: same number of
+    parameters, pointer parameters bound as pointers (an ABI drift between header and binding corrupts the stack)."""
+    import ctypes
+    import sys
+    sys.path.insert(0, PKG)
+    from source import _native
+    text = open(os.path.join(REPO, "include", "admmq.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"ADMMQ_API\s+[\w\s\*]*?\b(admmq_\w+)\(([^;]*?)\);", text, flags=re.S)
+    assert len(protos) >= 25
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        fn = getattr(_native.lib, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == len(plist), (name, len(fn.argtypes or []), plist)
+        for decl, ct in zip(plist, fn.argtypes):
+            is_ptr = "*" in decl
+            bound_ptr = ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents") or issubclass(ct, ctypes._Pointer)
+            assert is_ptr == bound_ptr, (name, decl, ct)
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     if torch.cuda.is_available():
         pytest.skip("needs a box without CUDA")
