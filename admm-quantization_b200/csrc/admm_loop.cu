@@ -4,7 +4,8 @@
 // One cooperative launch (one CTA per SM) runs ALL max_iter-1 inner iterations; per iteration
 //   P1  H_ls = RHS . Minv            RHS = F + rho (H + U)                                (:56-57)
 //       precision 0: float32 FFMA tile product (parity mode); precision 1: 3xTF32 on tcgen05/TMEM, operands
-//       fetched by TMA (tc_gemm.cuh; throughput mode)
+//       fetched by TMA (tc_gemm.cuh; throughput mode); factors with <= 16 rows: column-strip FMA product;
+//       admmq_split_loop: elementwise (two-block splitting)
 //       epilogue: abs-max key of V = H_ls - U                                          (:59, q.py:129)
 //   --- device-wide barrier
 //   P2  per-candidate squared-error sums of the clip search over V (search.cuh)         (q.py:136-139)
@@ -13,6 +14,7 @@
 //   --- device-wide barrier, then the exit test r < eps && s < eps                       (:64-65)
 // State (H, U, F, H_ls, RHS, Minv) stays L2 resident for the whole call: per iteration the
 // algorithmic traffic is 16 B per element of H plus one pass over Minv, all served from L2.
+// A small factor on a budget of one CTA takes the shared-memory-resident kernel of admm_loop_resident.cuh instead.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>

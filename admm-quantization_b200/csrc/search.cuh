@@ -2,7 +2,12 @@
 // (quantize_tensor_mse, source/quantization.py:118-144), shared by the standalone
 // projection kernels (project.cu) and the persistent ADMM loop (admm_loop.cu).
 //
-// Work split: the CTA's elements are staged through shared memory (cp.async, double buffered); every warp walks its
+// Two forms of the per-candidate squared-error sums (cta_candidate_sums dispatches):
+//   * the THRESHOLD form (cta_candidate_sums_binned, what the product runs): histogram + counting sort of the CTA's
+//     elements, then one exact float32 threshold per (candidate, level) - O(1) work per element, see numerics.cuh;
+//   * the DIRECT form (cta_candidate_sums_direct): every (element, candidate) pair evaluated with the reference's
+//     float32 operations - kept for abs-max outside [2^-40, 2^40] and as the cross-check of the parity tests.
+// Direct form, work split: the CTA's elements are staged through shared memory (cp.async, double buffered); every warp walks its
 // slice of the stage in aligned groups of 8 elements read as warp-wide broadcasts (2 x LDS.128),
 // and each LANE owns kCPL candidates (scale and 1/scale in registers, duplicated into both
 // halves of a packed f32x2 register) -> no per-candidate warp reduction.  One candidate
