@@ -243,8 +243,29 @@ ADMMQ_HD unsigned int ordered_key(float f) {
 }
 ADMMQ_HD float ordered_float(unsigned int k) { return bits_f32((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// smallest float32 x with rint(fl(x / scale)) >= level + 1   (level = -q .. q-2)
+// smallest float32 x with rint(fl(x / scale)) >= level + 1   (level = -q .. q-2), in closed form:
+//   rint(y) >= T  <=>  y >= y*,  y* = T - 0.5 if T is even (the tie rounds up to T), else the next float above it;
+//   fl(z) >= y*   <=>  z > mid or (z == mid and the mantissa of y* is even),  mid = midpoint of pred(y*) and y*;
+//   mid * scale is exact in float64 (25 x 24 significant bits), so theta is the first float above that product
+//   (or the product itself when it is a float and the tie goes to y*).
+// tests/hostcheck pins theta and its predecessor against the exact division for every level of random scales.
 ADMMQ_HD float code_threshold(float scale, float level) {
+  const float target = level + 1.0f;
+  const float b = target - 0.5f;
+  const bool t_even = (((int)target) & 1) == 0;
+  const float ystar = t_even ? b : ordered_float(ordered_key(b) + 1u);
+  const float pred = ordered_float(ordered_key(ystar) - 1u);
+  const double P = (0.5 * ((double)pred + (double)ystar)) * (double)scale;
+  float x = (float)P;                                   // round to nearest
+  if ((double)x < P) x = ordered_float(ordered_key(x) + 1u);
+  const bool ystar_even = (f32_bits(ystar) & 1u) == 0u;
+  if ((double)x == P && !ystar_even) x = ordered_float(ordered_key(x) + 1u);
+  return x;
+}
+
+// the same threshold by stepping through neighbouring floats with the exact division (reference implementation of the
+// definition; used by the host tests)
+ADMMQ_HD float code_threshold_search(float scale, float level) {
   const float target = level + 1.0f;
   unsigned int key = ordered_key(mul_rn(level + 0.5f, scale));
   if (rint_rn(div_rn(ordered_float(key), scale)) >= target) {

@@ -41,12 +41,17 @@ struct DirectSmem {
 constexpr int kBins = 8192;        // linear bins over [-absmax, absmax]
 constexpr int kStageCap = 20480;   // elements sorted by bin in shared memory at a time (40 per thread)
 constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
+#ifndef ADMMQ_PAIRWAYS
+#define ADMMQ_PAIRWAYS 1
+#endif
+constexpr int kPairWays = ADMMQ_PAIRWAYS;  // (candidate, threshold) pairs a thread works on at a time in pass 3
 struct BinnedSmem {
   __align__(16) float sorted[kStageCap];   // the stage's elements grouped by bin
   __align__(16) unsigned int cnt[kBins];   // per-bin counts -> start offsets -> end offsets
   __align__(16) unsigned int slo[kBins];   // per-bin fixed-point sums (low / high word) -> exclusive prefix sums
   __align__(16) unsigned int shi[kBins];
-  unsigned long long acc[kMaxCandidates];  // per-candidate fixed-point totals of this CTA
+  unsigned long long acc[kMaxCandidates];  // per-candidate fixed-point totals of this CTA (folded once per stage)
+  unsigned int part[3][kMaxCandidates];    // the current stage's terms in three 21-bit slices (plain 32-bit adds, no return)
   float scale[kMaxCandidates];
   unsigned long long wsum[kWarps];
   unsigned int wcnt[kWarps];
@@ -257,13 +262,20 @@ __device__ inline void cta_candidate_sums_direct(const float* __restrict__ v, lo
 //   scan    exclusive prefix over the bins
 //   pass 2  counting-sort scatter of the elements into `sorted` (grouped by bin)
 //   pass 3  one (candidate, threshold) pair per thread: exact threshold, its bin, prefix + the bin's elements compared
-//           one by one -> C, P -> float64 term -> fixed point -> per-candidate shared accumulator
+//           one by one -> C, P -> float64 term -> fixed point -> per-candidate shared accumulator (three 21-bit slices)
 // bin(x) is monotone in x, so every element in a lower bin is below the threshold and every element in a higher bin
 // is not; only the threshold's own bin (kStageCap / kBins = 5 elements on average) is inspected.
 __device__ __forceinline__ int bin_of(float x, float bmul) {
   const float t = fma_rn(x, bmul, 12582912.0f + (float)(kBins / 2));  // rne(x * bmul) + kBins / 2 in the low mantissa bits
   const int b = (int)__float_as_uint(t) - 0x4B400000;
   return min(max(b, 0), kBins - 1);
+}
+
+// A 64-bit fixed-point term f is accumulated as three 21-bit slices f = a0 + a1 2^21 + a2 2^42 (a2 signed): at most
+// 2^8 terms per candidate and stage keep every slice inside 32 bits, and 32-bit shared-memory adds need no return
+// value (the 64-bit shared atomic is a compare-and-swap loop).
+__device__ __forceinline__ long long fold_slices(unsigned int a0, unsigned int a1, unsigned int a2) {
+  return (long long)a0 + ((long long)a1 << 21) + (long long)((unsigned long long)(long long)(int)a2 << 42);
 }
 
 __device__ __forceinline__ float4 load_group4(const float* __restrict__ p, int gi, int ngroups, int cnt, bool vec_ok) {
@@ -298,6 +310,7 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
   for (int c = tid; c < Nc; c += kThreads) {
     sm.scale[c] = scale_of(clip_candidate(g, c), L);
     sm.acc[c] = 0ull;
+    sm.part[0][c] = sm.part[1][c] = sm.part[2][c] = 0u;
   }
   double x2 = 0.0;
   for (long long base = e0; base < e1; base += kStageCap) {
@@ -308,6 +321,12 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
       *reinterpret_cast<uint4*>(&sm.cnt[b]) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(&sm.slo[b]) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(&sm.shi[b]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (base != e0) {  // fold the previous stage's slices (its pass 3 ended with a barrier)
+      for (int c = tid; c < Nc; c += kThreads) {
+        sm.acc[c] += (unsigned long long)fold_slices(sm.part[0][c], sm.part[1][c], sm.part[2][c]);
+        sm.part[0][c] = sm.part[1][c] = sm.part[2][c] = 0u;
+      }
     }
     __syncthreads();
     // ---- pass 1: histogram
@@ -408,57 +427,88 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
         if (gi < ngroups) {
           const float xe[4] = {xs[u].x, xs[u].y, xs[u].z, xs[u].w};
           const int nv = min(4, cnt - gi * 4);
+          unsigned int pos[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < nv) {
-              const unsigned int pos = atomicAdd(&sm.cnt[bin_of(xe[q], bmul)], 1u);
-              sm.sorted[pos] = xe[q];
-            }
-          }
+          for (int q = 0; q < 4; ++q)
+            if (q < nv) pos[q] = atomicAdd(&sm.cnt[bin_of(xe[q], bmul)], 1u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nv) sm.sorted[pos[q]] = xe[q];
         }
       }
     }
     __syncthreads();
     // ---- pass 3: thresholds.  pair p = j * Nc + c: neighbouring threads take neighbouring candidates of the same
-    // level, whose thresholds fall into neighbouring bins and whose accumulators are distinct
+    // level, whose thresholds fall into neighbouring bins and whose accumulators are distinct.  A thread has only a
+    // handful of pairs and each is a long dependent chain, so kPairWays pairs are worked on at a time.
     {
       long long ptot = 0ll;
+#pragma unroll
       for (int w = 0; w < kWarps; ++w) ptot += (long long)sm.wsum[w];
-      int j = tid / Nc, c = tid - j * Nc;
-      const int dj = kThreads / Nc, dc = kThreads - dj * Nc;
-      for (int p = tid; p < npairs; p += kThreads) {
-        const float s = sm.scale[c];
-        const float level = L.lo + (float)j;
-        const float theta = code_threshold(s, level);
-        const int b = bin_of(theta, bmul);
-        const unsigned int beg = b ? sm.cnt[b - 1] : 0u, end = sm.cnt[b];
-        long long ps = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);
-        long long cn = (long long)beg;
-        // fix_x() split into its two integer parts, accumulated separately (int32 is enough for 512 elements at a time)
-        for (unsigned int i0 = beg; i0 < end; i0 += 512u) {
-          const unsigned int i1 = min(end, i0 + 512u);
-          int sth = 0, stl = 0, below = 0;
-          for (unsigned int i = i0; i < i1; ++i) {
-            const float x = sm.sorted[i];
-            const float hb = fma_rn(x, fx.p2a, 12582912.0f);
-            const float r = fma_rn(x, fx.p2a, -sub_rn(hb, 12582912.0f));
-            const float lb = fma_rn(r, 1048576.0f, 12582912.0f);
-            const bool in = x < theta;
-            sth += in ? (int)__float_as_uint(hb) - 0x4B400000 : 0;
-            stl += in ? (int)__float_as_uint(lb) - 0x4B400000 : 0;
-            below += in ? 1 : 0;
-          }
-          cn += below;
-          ps += (long long)sth * 1048576ll + (long long)stl;
+      for (int p0 = tid; p0 < npairs; p0 += kPairWays * kThreads) {
+        float s[kPairWays], level[kPairWays], theta[kPairWays];
+        int cand[kPairWays], lev[kPairWays];
+        unsigned int pos[kPairWays], end[kPairWays];
+        long long ps[kPairWays], cn[kPairWays];
+        bool on[kPairWays];
+#pragma unroll
+        for (int u = 0; u < kPairWays; ++u) {
+          const int p = p0 + u * kThreads;
+          on[u] = p < npairs;
+          lev[u] = on[u] ? p / Nc : 0;
+          cand[u] = on[u] ? p - lev[u] * Nc : 0;
+          s[u] = sm.scale[cand[u]];
+          level[u] = L.lo + (float)lev[u];
+          theta[u] = code_threshold(s[u], level[u]);
+          const int b = bin_of(theta[u], bmul);
+          pos[u] = b ? sm.cnt[b - 1] : 0u;
+          end[u] = on[u] ? sm.cnt[b] : pos[u];
+          ps[u] = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);
+          cn[u] = (long long)pos[u];
         }
-        double term = threshold_term(s, level, cn, ps, fx.unit);
-        if (j == nthr - 1) term += closing_term(s, L.hi, (long long)cnt, ptot, fx.unit);
-        atomicAdd(&sm.acc[c], (unsigned long long)__double2ll_rn(term * unit_inv));
-        j += dj;
-        c += dc;
-        if (c >= Nc) {
-          c -= Nc;
-          ++j;
+        // the threshold's own bin, element by element; fix_x() split into its two integer parts, accumulated
+        // separately (int32 is enough for 512 elements at a time)
+        auto any_live = [&]() {
+          bool a = false;
+#pragma unroll
+          for (int u = 0; u < kPairWays; ++u) a = a || pos[u] < end[u];
+          return a;
+        };
+        while (any_live()) {
+          int sth[kPairWays], stl[kPairWays], below[kPairWays];
+#pragma unroll
+          for (int u = 0; u < kPairWays; ++u) sth[u] = stl[u] = below[u] = 0;
+          for (int k = 0; k < 512 && any_live(); ++k) {
+#pragma unroll
+            for (int u = 0; u < kPairWays; ++u) {
+              const bool live = pos[u] < end[u];
+              const float x = sm.sorted[live ? pos[u] : 0u];
+              const float hb = fma_rn(x, fx.p2a, 12582912.0f);
+              const float r = fma_rn(x, fx.p2a, -sub_rn(hb, 12582912.0f));
+              const float lb = fma_rn(r, 1048576.0f, 12582912.0f);
+              const bool in = live && x < theta[u];
+              sth[u] += in ? (int)__float_as_uint(hb) - 0x4B400000 : 0;
+              stl[u] += in ? (int)__float_as_uint(lb) - 0x4B400000 : 0;
+              below[u] += in ? 1 : 0;
+              pos[u] += live ? 1u : 0u;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kPairWays; ++u) {
+            cn[u] += below[u];
+            ps[u] += (long long)sth[u] * 1048576ll + (long long)stl[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kPairWays; ++u) {
+          double term = threshold_term(s[u], level[u], cn[u], ps[u], fx.unit);
+          if (lev[u] == nthr - 1) term += closing_term(s[u], L.hi, (long long)cnt, ptot, fx.unit);
+          if (on[u]) {
+            const long long f = __double2ll_rn(term * unit_inv);
+            atomicAdd(&sm.part[0][cand[u]], (unsigned int)(f & 0x1fffffll));
+            atomicAdd(&sm.part[1][cand[u]], (unsigned int)((f >> 21) & 0x1fffffll));
+            atomicAdd(&sm.part[2][cand[u]], (unsigned int)(int)(f >> 42));
+          }
         }
       }
     }
@@ -473,7 +523,7 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
   for (int w = 0; w < kWarps; ++w) tot += sm.red[w];
   const long long x2f = __double2ll_rn(tot * unit_inv);
   for (int c = tid; c < Nc; c += kThreads) {
-    const long long f = (long long)sm.acc[c] + x2f;  // >= 0 up to rounding
+    const long long f = (long long)sm.acc[c] + fold_slices(sm.part[0][c], sm.part[1][c], sm.part[2][c]) + x2f;  // >= 0 up to rounding
     atomicAdd(cand_sums + c, (unsigned long long)max(f, 0ll));
   }
 }

@@ -110,6 +110,7 @@ long long hc_threshold_violations(float scale, int bits) {
     const float below = ordered_float(ordered_key(theta) - 1u);
     if (!(rint_rn(div_rn(theta, scale)) >= level + 1.0f)) ++bad;
     if (rint_rn(div_rn(below, scale)) >= level + 1.0f) ++bad;
+    if (theta != code_threshold_search(scale, level)) ++bad;   // closed form == search over neighbouring floats
   }
   return bad;
 }
