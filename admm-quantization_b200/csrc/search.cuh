@@ -39,6 +39,7 @@ struct DirectSmem {
 
 // threshold ("binned") form of the search, see numerics.cuh
 constexpr int kBins = 8192;        // linear bins over [-absmax, absmax]
+constexpr int kBinSlots = kBins + kBins / 8;  // see bin_slot()
 constexpr int kStageCap = 20480;   // elements sorted by bin in shared memory at a time (40 per thread)
 constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
 #ifndef ADMMQ_PAIRWAYS
@@ -47,9 +48,10 @@ constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
 constexpr int kPairWays = ADMMQ_PAIRWAYS;  // (candidate, threshold) pairs a thread works on at a time in pass 3
 struct BinnedSmem {
   __align__(16) float sorted[kStageCap];   // the stage's elements grouped by bin
-  __align__(16) unsigned int cnt[kBins];   // per-bin counts -> start offsets -> end offsets
-  __align__(16) unsigned int slo[kBins];   // per-bin fixed-point sums (low / high word) -> exclusive prefix sums
-  __align__(16) unsigned int shi[kBins];
+  // the three per-bin arrays are indexed by bin_slot(bin): four padding words after every 32 bins
+  __align__(16) unsigned int cnt[kBinSlots];   // per-bin counts -> start offsets -> end offsets
+  __align__(16) unsigned int slo[kBinSlots];   // per-bin fixed-point sums (low / high word) -> exclusive prefix sums
+  __align__(16) unsigned int shi[kBinSlots];
   unsigned long long acc[kMaxCandidates];  // per-candidate fixed-point totals of this CTA (folded once per stage)
   unsigned int part[3][kMaxCandidates];    // the current stage's terms in three 21-bit slices (plain 32-bit adds, no return)
   float scale[kMaxCandidates];
@@ -278,6 +280,12 @@ __device__ __forceinline__ long long fold_slices(unsigned int a0, unsigned int a
   return (long long)a0 + ((long long)a1 << 21) + (long long)((unsigned long long)(long long)(int)a2 << 42);
 }
 
+// Position of a bin in the per-bin arrays.  The scan reads 16 consecutive bins per thread as four 16-byte words; with
+// the bins stored densely the threads of a quarter warp start 64 bytes apart and every such access is a 4-way bank
+// conflict (ncu: 16 wavefronts instead of 4).  Four padding words after every 32 bins put the eight threads of a
+// quarter warp on eight different groups of four banks.
+__device__ __forceinline__ int bin_slot(int b) { return b + ((b >> 5) << 2); }
+
 __device__ __forceinline__ float4 load_group4(const float* __restrict__ p, int gi, int ngroups, int cnt, bool vec_ok) {
   float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
   if (gi < ngroups) {
@@ -317,7 +325,7 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
     const int cnt = (int)min((long long)kStageCap, e1 - base);
     const int ngroups = (cnt + 3) >> 2;
     const float* __restrict__ src = v + base;
-    for (int b = tid * 4; b < kBins; b += kThreads * 4) {
+    for (int b = tid * 4; b < kBinSlots; b += kThreads * 4) {
       *reinterpret_cast<uint4*>(&sm.cnt[b]) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(&sm.slo[b]) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(&sm.shi[b]) = make_uint4(0u, 0u, 0u, 0u);
@@ -343,7 +351,7 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (q < nv) {
-              const int b = bin_of(xe[q], bmul);
+              const int b = bin_slot(bin_of(xe[q], bmul));
               atomicAdd(&sm.cnt[b], 1u);
               const long long f = fix_x(xe[q], fx);
               const unsigned int lo = (unsigned int)f, hi = (unsigned int)((unsigned long long)f >> 32);
@@ -361,7 +369,8 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
     {
       constexpr int kPer = kBins / kThreads;
       static_assert(kPer % 4 == 0 && kPer * kThreads == kBins, "bins per thread");
-      const int b0 = tid * kPer;
+      static_assert(kPer <= 32 && 32 % kPer == 0, "a thread's bins share one padded block");
+      const int b0 = bin_slot(tid * kPer);
       unsigned int c[kPer], lo[kPer], hi[kPer];
 #pragma unroll
       for (int i = 0; i < kPer; i += 4) {
@@ -430,7 +439,7 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
           unsigned int pos[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (q < nv) pos[q] = atomicAdd(&sm.cnt[bin_of(xe[q], bmul)], 1u);
+            if (q < nv) pos[q] = atomicAdd(&sm.cnt[bin_slot(bin_of(xe[q], bmul))], 1u);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (q < nv) sm.sorted[pos[q]] = xe[q];
@@ -460,8 +469,8 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
           s[u] = sm.scale[cand[u]];
           level[u] = L.lo + (float)lev[u];
           theta[u] = code_threshold(s[u], level[u]);
-          const int b = bin_of(theta[u], bmul);
-          pos[u] = b ? sm.cnt[b - 1] : 0u;
+          const int bin = bin_of(theta[u], bmul), b = bin_slot(bin);
+          pos[u] = bin ? sm.cnt[bin_slot(bin - 1)] : 0u;
           end[u] = on[u] ? sm.cnt[b] : pos[u];
           ps[u] = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);
           cn[u] = (long long)pos[u];
