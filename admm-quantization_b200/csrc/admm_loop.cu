@@ -199,7 +199,20 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
   unsigned int kmax = 0u, kinv = 0u;
   if (n_begin < R) {  // uniform per CTA
     __syncthreads();
-    for (int e = t * 4; e < I * Rp; e += kThreads * 4) *reinterpret_cast<float4*>(&ss.rhs[e]) = ldcg4(p.RHS + e);
+    // stage RHS, four loads in flight per thread (the phase is a chain of L2 round trips otherwise)
+    for (int e0 = t * 4; e0 < I * Rp; e0 += kThreads * 16) {
+      float4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads * 4;
+        if (e < I * Rp) r[u] = ldcg4(p.RHS + e);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads * 4;
+        if (e < I * Rp) *reinterpret_cast<float4*>(&ss.rhs[e]) = r[u];
+      }
+    }
     __syncthreads();
     for (int s0 = n_begin; s0 < n_end; s0 += 128) {
       const int w = min(128, n_end - s0);
@@ -211,17 +224,40 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
       for (int i = 0; i < MI; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
       if (s < ks) {
         const float* mp = p.Minv + s0 + 4 * c;
-#pragma unroll 4
-        for (int k = s; k < R; k += ks) {
-          const float4 m = __ldg(reinterpret_cast<const float4*>(mp + (size_t)k * Rp));
+        // a thread takes groups of four consecutive rows of Minv (k = 4 g .. 4 g + 3, g = s, s + ks, ...): the four RHS
+        // values of a factor row come as ONE 16-byte shared-memory load for 16 FMAs (one 4-byte load per 4 FMAs made
+        // the loop issue and shared-memory-latency bound: ncu showed 140 instructions per row of Minv); kG groups in
+        // flight.  Rows >= R of Minv do not exist (read as zero); the pad columns of RHS are zero.
+        constexpr int kG = MI <= 9 ? 2 : 1;
+        const int ngroups = (R + 3) >> 2;
+        for (int g0 = s; g0 < ngroups; g0 += ks * kG) {
+          float4 m[kG][4];
 #pragma unroll
-          for (int i = 0; i < MI; ++i) {
-            if (i < I) {
-              const float r = ss.rhs[i * Rp + k];
-              acc[i][0] = fmaf(r, m.x, acc[i][0]);
-              acc[i][1] = fmaf(r, m.y, acc[i][1]);
-              acc[i][2] = fmaf(r, m.z, acc[i][2]);
-              acc[i][3] = fmaf(r, m.w, acc[i][3]);
+          for (int u = 0; u < kG; ++u) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int k = 4 * (g0 + u * ks) + q;
+              m[u][q] = (k < R) ? __ldcg(reinterpret_cast<const float4*>(mp + (size_t)k * Rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kG; ++u) {
+            const int g = g0 + u * ks;
+            if (g < ngroups) {
+#pragma unroll
+              for (int i = 0; i < MI; ++i) {
+                if (i < I) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(&ss.rhs[i * Rp + 4 * g]);
+                  const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    acc[i][0] = fmaf(r[q], m[u][q].x, acc[i][0]);
+                    acc[i][1] = fmaf(r[q], m[u][q].y, acc[i][1]);
+                    acc[i][2] = fmaf(r[q], m[u][q].z, acc[i][2]);
+                    acc[i][3] = fmaf(r[q], m[u][q].w, acc[i][3]);
+                  }
+                }
+              }
             }
           }
         }
@@ -233,11 +269,20 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
       for (int o = t; o < I * w; o += kThreads) {
         const int i = o / w, nn = o - i * w;
         const int cc = nn >> 2, q = nn & 3;
-        float h = 0.0f;
-        for (int sl = 0; sl < ks; ++sl) h = add_rn(h, ss.red[(size_t)(sl * cg + cc) * (MI * 4) + i * 4 + q]);
         const int n = s0 + nn;
+        const float u = __ldcg(p.U + (size_t)i * R + n);  // requested before the (long) sum over the slices
+        // fixed order: four interleaved partial sums over the k-slices, then ((h0 + h1) + (h2 + h3))
+        float h4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float* rp = &ss.red[(size_t)cc * (MI * 4) + i * 4 + q];
+        int sl = 0;
+        for (; sl + 3 < ks; sl += 4) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) h4[a] = add_rn(h4[a], rp[(size_t)((sl + a) * cg) * (MI * 4)]);
+        }
+        for (; sl < ks; ++sl) h4[sl & 3] = add_rn(h4[sl & 3], rp[(size_t)(sl * cg) * (MI * 4)]);
+        const float h = add_rn(add_rn(h4[0], h4[1]), add_rn(h4[2], h4[3]));
         p.Hls[(size_t)i * Rp + n] = h;
-        const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + n));  // V = H_ls - U (:59)
+        const float v = sub_rn(h, u);  // V = H_ls - U (:59)
         p.V[(size_t)i * R + n] = v;
         const unsigned int k = float_key(v);
         kmax = max(kmax, k);
