@@ -44,7 +44,7 @@ __device__ __forceinline__ void read_minmax(const ProjectHeader* hdr, float& tmi
 
 __global__ void __launch_bounds__(kThreads) k_mse_sums(const float* x, long long n, int bits, int Nc,
                                                       const ProjectHeader* hdr, unsigned long long* cand_sums,
-                                                      float neg_zero, int direct) {
+                                                      float neg_zero, int form) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchSmem& sm = *reinterpret_cast<SearchSmem*>(smem_raw);
   float tmin, tmax, absmax;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) k_mse_sums(const float* x, long long
   const Levels L = make_levels(bits);
   const long long cs = chunk_size(n, gridDim.x);
   const long long e0 = min(n, (long long)blockIdx.x * cs), e1 = min(n, e0 + cs);
-  cta_candidate_sums(x, e0, e1, absmax, Nc, L, bits, (double)n, cand_sums, sm, neg_zero, direct != 0);
+  cta_candidate_sums(x, e0, e1, absmax, Nc, L, bits, (double)n, cand_sums, sm, neg_zero, form);
 }
 
 __global__ void __launch_bounds__(kThreads) k_apply(const float* x, long long n, int bits, int scheme, int Nc,
@@ -126,13 +126,13 @@ extern "C" size_t admmq_project_workspace_bytes(int64_t n, int num_attempts) {
 }
 
 static int launch_mse_sums(const float* x, int64_t n, int bits, int num_attempts, ProjectHeader* hdr,
-                           unsigned long long* cand, int direct, int max_ctas, const DeviceProps& dp, cudaStream_t stream) {
+                           unsigned long long* cand, int form, int max_ctas, const DeviceProps& dp, cudaStream_t stream) {
   // one chunk of >= 512 elements per CTA, at most one CTA per SM
   const long long want = (n + 511) / 512;
   int g = (int)std::max<long long>(1, std::min<long long>((long long)dp.sm_count, want));
   if (max_ctas > 0) g = std::min(g, max_ctas);
   ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mse_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem)));
-  k_mse_sums<<<g, kThreads, sizeof(SearchSmem), stream>>>(x, n, bits, num_attempts, hdr, cand, -0.0f, direct);
+  k_mse_sums<<<g, kThreads, sizeof(SearchSmem), stream>>>(x, n, bits, num_attempts, hdr, cand, -0.0f, form);
   return ADMMQ_OK;
 }
 
@@ -154,7 +154,7 @@ extern "C" int admmq_clip_search_sums(const float* x, int64_t n, int bits, int n
   ADMMQ_CUDA_OK(cudaMemsetAsync(workspace, 0, admmq_project_workspace_bytes(n, num_attempts), stream));
   const int g_stream = (int)std::min<long long>((long long)dp.sm_count * 4, (n + kThreads * 4 - 1) / (kThreads * 4));
   k_minmax_keys<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, hdr);
-  if (int e = launch_mse_sums(x, n, bits, num_attempts, hdr, cand, method == 0 ? 1 : 0, max_ctas, dp, stream)) return e;
+  if (int e = launch_mse_sums(x, n, bits, num_attempts, hdr, cand, method == 0 ? kFormDirect : kFormThresholds, max_ctas, dp, stream)) return e;
   k_sums_to_double<<<(num_attempts + 255) / 256, 256, 0, stream>>>(cand, hdr, n, num_attempts, sums);
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(3);
@@ -182,7 +182,7 @@ extern "C" int admmq_project(const float* x, int64_t n, int bits, int qscheme, i
   const int g_stream = (int)std::min<long long>(max_ctas, (n + kThreads * 4 - 1) / (kThreads * 4));
   k_minmax_keys<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, hdr);
   if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) {
-    if (int e = launch_mse_sums(x, n, bits, num_attempts, hdr, cand, 0, 0, dp, stream)) return e;
+    if (int e = launch_mse_sums(x, n, bits, num_attempts, hdr, cand, kFormAuto, 0, dp, stream)) return e;
   }
   k_apply<<<std::max(g_stream, 1), kThreads, 0, stream>>>(x, n, bits, qscheme, num_attempts, hdr, cand, tmin, tmax,
                                                             xq, codes, info);

@@ -537,12 +537,27 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
   }
 }
 
-// Dispatch: threshold form whenever absmax is in its supported range, direct evaluation otherwise (and on request)
+// Dispatch: threshold form when absmax is in its supported range and the form is the cheaper one, direct evaluation
+// otherwise (and on request)
+constexpr int kFormAuto = 0, kFormDirect = 1, kFormThresholds = 2;
+// cost of one (candidate, threshold) pair in (element, candidate) evaluations of the direct form: measured ~1.1 ns against
+// ~69 ps on B200 (tools/time_search.py crossover: break-even near 5 k elements per CTA with 8 bits, 1.3 k with 6, and
+// no difference below 1 k with 4)
+constexpr int kPairsPerElement = 18;
 __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long e0, long long e1, float absmax, int Nc,
                                           const Levels L, int bits, double n_total, unsigned long long* cand_sums,
-                                          SearchSmem& sm, float opaque_neg_zero, bool force_direct = false) {
-  if (!force_direct && binned_range_ok(absmax)) cta_candidate_sums_binned(v, e0, e1, absmax, Nc, L, bits, n_total, cand_sums, sm.binned);
-  else cta_candidate_sums_direct(v, e0, e1, absmax, Nc, L, n_total, cand_sums, sm.direct, opaque_neg_zero);
+                                          SearchSmem& sm, float opaque_neg_zero, int form = kFormAuto) {
+  // Both forms give the same sums up to the last fixed-point unit, so each CTA may take the cheaper one for its chunk: the threshold form
+  // pays per (candidate, threshold) pair and stage on top of O(1) per element, the direct form per (element, candidate);
+  // with 8 bits (255 thresholds) the direct form wins below ~4.6 k elements per stage, with 4 bits never in practice.
+  const long long elems = e1 - e0;
+  const long long stages = (elems + kStageCap - 1) / kStageCap;
+  const bool direct_is_cheaper = (long long)((1 << bits) - 1) * stages * kPairsPerElement > elems;
+  const bool want_direct = form == kFormDirect || (form == kFormAuto && direct_is_cheaper);
+  if (!want_direct && binned_range_ok(absmax))
+    cta_candidate_sums_binned(v, e0, e1, absmax, Nc, L, bits, n_total, cand_sums, sm.binned);
+  else
+    cta_candidate_sums_direct(v, e0, e1, absmax, Nc, L, n_total, cand_sums, sm.direct, opaque_neg_zero);
 }
 
 // First index of the smallest MSE (torch.argmin, source/quantization.py:141), evaluated

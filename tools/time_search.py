@@ -5,8 +5,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [REPO, os.path.join(REPO, "admm-quantization_b200")]
 from source import _native as nat
 g = torch.Generator().manual_seed(0)
-for shape, bits, nc, ctas in [((512, 1141), 4, 200, 0), ((512, 1141), 4, 200, 31), ((512, 1141), 8, 200, 31), ((64, 134), 4, 200, 1),
-                              ((256, 566), 4, 200, 8), ((4096, 1024), 4, 200, 0), ((512, 1141), 4, 1000, 0), ((512, 1141), 8, 1000, 0)]:
+cases = [((512, 1141), 4, 200, 0), ((512, 1141), 4, 200, 31), ((512, 1141), 8, 200, 31), ((64, 134), 4, 200, 1),
+         ((256, 566), 4, 200, 8), ((4096, 1024), 4, 200, 0), ((512, 1141), 4, 1000, 0), ((512, 1141), 8, 1000, 0)]
+if len(sys.argv) > 1 and sys.argv[1] == "crossover":   # elements per CTA x bits: where does the direct form win?
+    cases = [((rows, 1141), bits, 200, 36) for bits in (4, 6, 8) for rows in (9, 32, 64, 128, 256, 512)]
+for shape, bits, nc, ctas in cases:
     x = (torch.randn(*shape, generator=g) * 0.05).cuda()
     for method in (0, 1):
         for _ in range(3):
