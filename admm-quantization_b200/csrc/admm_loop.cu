@@ -529,25 +529,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
       qp = params_from_minmax(p.scheme, p.bits, tmin, tmax, L);
     }
     rep.scale = qp.scale;
+    // clip-search scheme: the code comes from x * (1 / scale) + magic-number rounding (numerics.cuh dev_fast, the
+    // shortcut the direct search uses); the rare quotient too close to a rounding boundary is redone with the exact
+    // division, so the codes stay those of rint(fl(x / scale))
+    const bool fast_code = p.scheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC && !degenerate;
+    const float rcp_scale = fast_code ? div_rn(1.0f, qp.scale) : 0.0f;
     float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f, f3 = 0.0f;
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     {
       // batches of 4 elements per thread: all 16 loads of a batch are issued before the first dependent use, so the
       // phase runs at L2 bandwidth instead of one L2 round trip per element
       constexpr int kBatch = 4;
+      // 32-bit element offsets (check_loop_args: I * Rp < 2^31): one IMAD.WIDE per address instead of 64-bit shifts and
+      // carries - the phase is issue bound
       int i = row0, n = col0, cnt = 0;
-      long long e = e0 + t;
-      while (e < e1) {
-        long long ee[kBatch];
-        int ii[kBatch], nn[kBatch];
+      unsigned int e = (unsigned int)e0 + (unsigned int)t;
+      const unsigned int e1u = (unsigned int)e1;
+      while (e < e1u) {
+        unsigned int ee[kBatch], hh[kBatch];
         float hls[kBatch], u[kBatch], hp[kBatch], fv[kBatch];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
           ee[b] = e;
-          ii[b] = i;
-          nn[b] = n;
-          if (e < e1) {
-            hls[b] = __ldcg(p.Hls + (size_t)i * Rp + n);
+          hh[b] = (unsigned int)i * (unsigned int)Rp + (unsigned int)n;
+          if (e < e1u) {
+            hls[b] = __ldcg(p.Hls + hh[b]);
             u[b] = __ldcg(p.U + e);
             hp[b] = p.H[e];
             fv[b] = p.F[e];
@@ -562,10 +568,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
         }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-          if (ee[b] < e1) {
+          if (ee[b] < e1u) {
             const float v = sub_rn(hls[b], u[b]);
-            float code = 0.0f;
-            const float hq = degenerate ? qnan : quantize_value(v, qp, L, code);   // H = Q(H_ls - U)   (:59)
+            float code = 0.0f, hq;                                               // H = Q(H_ls - U)   (:59)
+            if (fast_code) {
+              const float tq = fminf(fmaxf(mul_rn(v, rcp_scale), L.fast_lo), L.fast_hi);
+              code = sub_rn(add_rn(tq, 12582912.0f), 12582912.0f);
+              const bool near_tie = !(fabsf(sub_rn(tq, code)) <= L.fast_thr);
+              code = copysignf(code, tq);  // rint keeps the sign of a quotient in (-0.5, 0); the magic sum returns +0
+              if (near_tie) code = code_exact(v, qp.scale, L);
+              hq = mul_rn(code, qp.scale);
+            } else {
+              hq = degenerate ? qnan : quantize_value(v, qp, L, code);
+            }
             const float d1 = sub_rn(hq, hls[b]);
             const float un = add_rn(u[b], d1);                                     // U += H - H_ls     (:60)
             const float d2 = sub_rn(hq, hp[b]);
@@ -575,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
             f3 = fmaf(un, un, f3);  // sum U^2
             p.H[ee[b]] = hq;
             p.U[ee[b]] = un;
-            if constexpr (TCBN != kDiagP1) p.RHS[(size_t)ii[b] * Rp + nn[b]] = add_rn(fv[b], mul_rn(rho, add_rn(hq, un)));
+            if constexpr (TCBN != kDiagP1) p.RHS[hh[b]] = add_rn(fv[b], mul_rn(rho, add_rn(hq, un)));
             if (p.codes != nullptr) p.codes[ee[b]] = (int8_t)code;
             if (++cnt == 16) {  // float32 partial sums over at most 16 elements, float64 beyond
               sums[0] += (double)f0;
@@ -729,7 +744,7 @@ static int check_loop_args(const char* who, const void* H, const void* U, const 
   if (qscheme < 0 || qscheme > 3) return fail(ADMMQ_E_BADARG, "%s: unknown qscheme %d", who, qscheme);
   if (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC && (num_attempts < 1 || num_attempts > kMaxCandidates))
     return fail(ADMMQ_E_BADARG, "%s: num_attempts must be in 1..%d", who, kMaxCandidates);
-  if ((long long)I * R >= (1ll << 31)) return fail(ADMMQ_E_UNSUPPORTED, "%s: I*R must be < 2^31", who);
+  if ((long long)I * ((R + 3) / 4 * 4) >= (1ll << 31)) return fail(ADMMQ_E_UNSUPPORTED, "%s: I * (R rounded up to 4) must be < 2^31", who);
   return ADMMQ_OK;
 }
 
