@@ -344,27 +344,42 @@ __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc
     // epilogue over row-contiguous float4 groups of the tile parked in shared memory (coalesced global traffic)
     const float* tile_h = tc::acc_to_smem<TCBN, kLoopPS>(pipe, smem_tiles);
     using ET = tc::EpiTile<TCBN>;
+    // U is dense (row pitch R, not 16-byte aligned in general) and comes from L2: the loads of up to four groups per
+    // thread are issued before the first use, so the epilogue pays two L2 round trips per tile instead of eight
+    constexpr int kIt = (ET::kGroups + kThreads - 1) / kThreads;
+    constexpr int kChunk = kIt < 4 ? kIt : 4;
 #pragma unroll
-    for (int g0 = 0; g0 < ET::kGroups; g0 += kThreads) {
-      const int g = g0 + (int)threadIdx.x;
-      const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
-      const int i = i0 + row, n = n0 + c4;
-      if (g < ET::kGroups && c4 < bn && i < I && n < R) {
-        const float4 h4 = *reinterpret_cast<const float4*>(tile_h + ET::offset(row, c4 >> 2));
-        const float h[4] = {h4.x, h4.y, h4.z, h4.w};
-        *reinterpret_cast<float4*>(p.Hls + (size_t)i * Rp + n) = h4;  // n + 3 < Rp: pad columns hold the zero-filled product
-        const size_t e = (size_t)i * R + n;
-        float u[4];
+    for (int c0 = 0; c0 < kIt; c0 += kChunk) {
+      float u[kChunk][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) u[q] = (n + q < R) ? __ldcg(p.U + e + q) : 0.0f;
+      for (int j = 0; j < kChunk; ++j) {
+        const int g = (c0 + j) * kThreads + (int)threadIdx.x;
+        const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
+        const int i = i0 + row, n = n0 + c4;
+        const unsigned int e = (unsigned int)i * (unsigned int)R + (unsigned int)n;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (n + q < R) {
-            const float d = sub_rn(h[q], u[q]);  // V = H_ls - U (:59)
-            p.V[e + q] = d;
-            const unsigned int k = float_key(d);
-            kmax = max(kmax, k);
-            kinv = max(kinv, ~k);
+        for (int q = 0; q < 4; ++q)
+          u[j][q] = (c0 + j < kIt && g < ET::kGroups && c4 < bn && i < I && n + q < R) ? __ldcg(p.U + e + q) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) {
+        const int g = (c0 + j) * kThreads + (int)threadIdx.x;
+        const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
+        const int i = i0 + row, n = n0 + c4;
+        if (c0 + j < kIt && g < ET::kGroups && c4 < bn && i < I && n < R) {
+          const float4 h4 = *reinterpret_cast<const float4*>(tile_h + ET::offset(row, c4 >> 2));
+          const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+          *reinterpret_cast<float4*>(p.Hls + (unsigned int)i * (unsigned int)Rp + (unsigned int)n) = h4;  // n + 3 < Rp: pad columns hold the zero-filled product
+          const unsigned int e = (unsigned int)i * (unsigned int)R + (unsigned int)n;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n + q < R) {
+              const float d = sub_rn(h[q], u[j][q]);  // V = H_ls - U (:59)
+              p.V[e + q] = d;
+              const unsigned int k = float_key(d);
+              kmax = max(kmax, k);
+              kinv = max(kinv, ~k);
+            }
           }
         }
       }

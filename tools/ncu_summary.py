@@ -63,9 +63,51 @@ def full(rep_path, out_path, title, top=25, kernel=""):
                 f.write(f"| {r[S]} | {r[idx['Instructions Executed']]} | `{r[1][:80]}` |\n")
 
 
+def regions(rep_path, out_path, title, warps_per_pass=0):
+    """Splits the SASS of the (single) profiled kernel at its BAR.SYNC instructions and lists, per region, the static
+    and executed instruction counts, the share of the stall samples and the top stall reasons - the view that showed
+    which phases of the persistent kernel are issue bound (executed instructions per element) and which wait."""
+    src = subprocess.run(["ncu", "-i", rep_path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    hdr, data = rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    regs, cur = [], None
+    for r in data:
+        if len(r) != len(hdr):
+            continue
+        if cur is None:
+            cur = {"samples": 0, "st": collections.Counter(), "instr": 0, "exec": 0, "wf": 0, "ideal": 0}
+        cur["samples"] += int(r[col["# Samples"]] or 0)
+        cur["instr"] += 1
+        cur["exec"] += int(r[col["Instructions Executed"]] or 0)
+        cur["wf"] += int(r[col["L1 Wavefronts Shared"]] or 0)
+        cur["ideal"] += int(r[col["L1 Wavefronts Shared Ideal"]] or 0)
+        for h in stalls:
+            v = int(r[col[h]] or 0)
+            if v:
+                cur["st"][h[6:]] += v
+        if "BAR.SYNC" in r[col["Source"]]:
+            regs.append(cur)
+            cur = None
+    if cur:
+        regs.append(cur)
+    tot = sum(x["samples"] for x in regs) or 1
+    with open(out_path, "w") as f:
+        f.write(f"# {title}\n\nRegions = stretches of SASS between two BAR.SYNC instructions, in program order; regions with < 0.5 % of the samples omitted.\n\n")
+        f.write("| region | SASS instr | executed (warp-level) | samples | share | shared wavefronts / ideal | top stall reasons |\n|---:|---:|---:|---:|---:|---|---|\n")
+        for i, x in enumerate(regs):
+            if x["samples"] < 0.005 * tot:
+                continue
+            top = ", ".join(f"{k} {v}" for k, v in x["st"].most_common(4))
+            f.write(f"| {i} | {x['instr']} | {x['exec']} | {x['samples']} | {100 * x['samples'] / tot:.1f} % | {x['wf']} / {x['ideal']} | {top} |\n")
+
+
 if __name__ == "__main__":
     kind = sys.argv[1]
     if kind == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif kind == "regions":
+        regions(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4], kernel=sys.argv[5] if len(sys.argv) > 5 else "")
