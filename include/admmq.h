@@ -78,7 +78,8 @@ ADMMQ_API int admmq_project(const float* x, int64_t n, int bits, int qscheme, in
                   void* workspace, size_t workspace_bytes, void* stream);
 /* The per-candidate sums behind the argmin of source/quantization.py:136-141, sums[c] = sum((x - Q_c(x))**2) as
  * float64, for the parity tests: method 0 = direct evaluation of every (element, candidate) pair with the
- * reference's float32 operations, method 1 = the threshold form the product uses (csrc/numerics.cuh).  max_ctas > 0
+ * reference's float32 operations, method 1 = the threshold form (csrc/numerics.cuh); the product lets every CTA take
+ * whichever of the two is cheaper for its chunk (csrc/search.cuh, cta_candidate_sums).  max_ctas > 0
  * limits the grid (the result must not depend on it).  Workspace: admmq_project_workspace_bytes(n, num_attempts). */
 ADMMQ_API int admmq_clip_search_sums(const float* x, int64_t n, int bits, int num_attempts, int method, int max_ctas,
                   double* sums, void* workspace, size_t workspace_bytes, void* stream);
@@ -170,6 +171,8 @@ typedef struct admmq_loop_report {
  * precision (both loop entry points): how the per-iteration ridge product H_ls = (F + rho (H + U)) . Minv is formed
  *   0  float32 FFMA tiles on the CUDA cores (parity mode: what the bit-level comparisons against the reference use)
  *   1  3xTF32 on tcgen05 / tensor memory with TMA-fed operands (throughput mode; factors with < 64 rows fall back to 0)
+ *
+ * Shapes: I * admmq_padded_ld(R) < 2^31 (ADMMQ_E_UNSUPPORTED otherwise; the kernels index elements with 32 bits).
  *
  * The loop alone, for callers that keep (Minv, rho) of a ridge system around (admmq_spd_inverse):
  *   Minv  R x admmq_padded_ld(R) float32, rho / inv_status device scalars written by admmq_spd_inverse
