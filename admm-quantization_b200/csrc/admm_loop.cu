@@ -706,7 +706,7 @@ static IterationLayout iteration_layout(int I, int R, int grid) {
 }
 
 constexpr int kTileFixed = 16;   // cost of a tensor-core tile that does not depend on its width, in columns of width
-                                 // (measured per tile: 10.5 / 15.3 / 23 / 32 us at 32 / 48 / 80 / 128 columns = 3.3 + 0.225 bn)
+                                 // (measured per tile at K = 1141: 10.5 / 15.3 / 23 / 32 us at 32 / 48 / 80 / 128 columns)
 constexpr int kMaxGrid = 1024;  // workspaces are sized for any cooperative grid up to this many CTAs
 
 static int coop_grid(const DeviceProps& dp, int max_ctas) {
