@@ -102,6 +102,12 @@ def test_code_thresholds_are_exact(hc):
         for trial in range(200):
             scale = np.float32(float(torch.rand(1, generator=g) + 0.01) * 10 ** float(torch.randint(-9, 9, (1,), generator=g)))
             assert hc.hc_threshold_violations(ctypes.c_float(scale), bits) == 0, (bits, scale)
+        # scales where the quotient is exact or the rounding boundary itself is a float: powers of two, mantissas of all
+        # ones / one bit, and the ends of the range the threshold form accepts (abs-max in [2^-40, 2^40])
+        for e in (-46, -40, -23, -1, 0, 1, 7, 24, 37):
+            for mant in (1.0, 1.5, 1.0 + 2.0 ** -23, 2.0 - 2.0 ** -23, 1.25, 1.0 + 2.0 ** -12):
+                scale = np.float32(mant * 2.0 ** e)
+                assert hc.hc_threshold_violations(ctypes.c_float(scale), bits) == 0, (bits, scale)
 
 
 def test_threshold_form_matches_oracle_argmin_on_random_tensors(hc):
