@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--balance", default="model", choices=["model", "prop"],
                     help="re-balancing of the SM budgets during warm-up: 'model' = wave model of the tensor-core product "
                          "fitted to the reported phase times (source/workloads.py), 'prop' = proportional to time x CTAs")
+    ap.add_argument("--budgets", default=None,
+                    help="experiment knob: comma-separated SM budgets, one per layer in workload order; fixes the budgets "
+                         "(no re-balancing during warm-up)")
     ap.add_argument("--trace-layer", default=None, help="print the per-kernel-group times of this layer's last sweep")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs kept out of the cooperative-grid budgets so that the ordinary kernels between the loops "
@@ -263,6 +266,9 @@ def run_native(args):
     budgets = allocate_ctas([wl.solve_cost(W.shape, rnk) for _, W, rnk, _ in problems], sm_count - args.reserve_sms,
                             args.min_ctas) \
         if args.concurrency == "prop" else [0] * len(problems)
+    if args.budgets and args.concurrency == "prop":
+        budgets = [int(x) for x in args.budgets.split(",")]
+        assert len(budgets) == len(problems) and sum(budgets) <= sm_count, (len(problems), sum(budgets), sm_count)
     streams = [torch.cuda.Stream(device=dev) for _ in problems] if args.concurrency == "prop" else None
     for (name, W, rnk, init), g in zip(problems, budgets):
         solvers.append(LayerSolver(W.to(dev), [f.to(dev) for f in init], args.bits, QSCHEME,
@@ -338,7 +344,7 @@ def run_native(args):
         w1.record()
         torch.cuda.synchronize()
         tried.append((w0.elapsed_time(w1), [s.max_ctas for s in solvers]))
-        if streams is not None and w < args.warmup - 1:
+        if streams is not None and w < args.warmup - 1 and not args.budgets:
             # re-balance the SM budgets from what was just measured: per layer the sweep time and, per factor, the
             # phase times its persistent kernel reported, through the wave model of source/workloads.py
             fitted = []
