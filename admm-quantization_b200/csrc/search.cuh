@@ -42,10 +42,6 @@ constexpr int kBins = 8192;        // linear bins over [-absmax, absmax]
 constexpr int kBinSlots = kBins + kBins / 8;  // see bin_slot()
 constexpr int kStageCap = 20480;   // elements sorted by bin in shared memory at a time (40 per thread)
 constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
-#ifndef ADMMQ_PAIRWAYS
-#define ADMMQ_PAIRWAYS 1
-#endif
-constexpr int kPairWays = ADMMQ_PAIRWAYS;  // (candidate, threshold) pairs a thread works on at a time in pass 3
 struct BinnedSmem {
   __align__(16) float sorted[kStageCap];   // the stage's elements grouped by bin
   // the three per-bin arrays are indexed by bin_slot(bin): four padding words after every 32 bins
@@ -448,77 +444,51 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
     }
     __syncthreads();
     // ---- pass 3: thresholds.  pair p = j * Nc + c: neighbouring threads take neighbouring candidates of the same
-    // level, whose thresholds fall into neighbouring bins and whose accumulators are distinct.  A thread has only a
-    // handful of pairs and each is a long dependent chain, so kPairWays pairs are worked on at a time.
+    // level, whose thresholds fall into neighbouring bins and whose accumulators are distinct.  (Working on two pairs
+    // at a time to hide the dependent chain was measured: no gain, the phase is issue bound.)
     {
       long long ptot = 0ll;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) ptot += (long long)sm.wsum[w];
-      for (int p0 = tid; p0 < npairs; p0 += kPairWays * kThreads) {
-        float s[kPairWays], level[kPairWays], theta[kPairWays];
-        int cand[kPairWays], lev[kPairWays];
-        unsigned int pos[kPairWays], end[kPairWays];
-        long long ps[kPairWays], cn[kPairWays];
-        bool on[kPairWays];
-#pragma unroll
-        for (int u = 0; u < kPairWays; ++u) {
-          const int p = p0 + u * kThreads;
-          on[u] = p < npairs;
-          lev[u] = on[u] ? p / Nc : 0;
-          cand[u] = on[u] ? p - lev[u] * Nc : 0;
-          s[u] = sm.scale[cand[u]];
-          level[u] = L.lo + (float)lev[u];
-          theta[u] = code_threshold(s[u], level[u]);
-          const int bin = bin_of(theta[u], bmul), b = bin_slot(bin);
-          pos[u] = bin ? sm.cnt[bin_slot(bin - 1)] : 0u;
-          end[u] = on[u] ? sm.cnt[b] : pos[u];
-          ps[u] = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);
-          cn[u] = (long long)pos[u];
-        }
-        // the threshold's own bin, element by element; fix_x() split into its two integer parts, accumulated
-        // separately (int32 is enough for 512 elements at a time)
-        auto any_live = [&]() {
-          bool a = false;
-#pragma unroll
-          for (int u = 0; u < kPairWays; ++u) a = a || pos[u] < end[u];
-          return a;
-        };
-        while (any_live()) {
-          int sth[kPairWays], stl[kPairWays], below[kPairWays];
-#pragma unroll
-          for (int u = 0; u < kPairWays; ++u) sth[u] = stl[u] = below[u] = 0;
-          for (int k = 0; k < 512 && any_live(); ++k) {
-#pragma unroll
-            for (int u = 0; u < kPairWays; ++u) {
-              const bool live = pos[u] < end[u];
-              const float x = sm.sorted[live ? pos[u] : 0u];
-              const float hb = fma_rn(x, fx.p2a, 12582912.0f);
-              const float r = fma_rn(x, fx.p2a, -sub_rn(hb, 12582912.0f));
-              const float lb = fma_rn(r, 1048576.0f, 12582912.0f);
-              const bool in = live && x < theta[u];
-              sth[u] += in ? (int)__float_as_uint(hb) - 0x4B400000 : 0;
-              stl[u] += in ? (int)__float_as_uint(lb) - 0x4B400000 : 0;
-              below[u] += in ? 1 : 0;
-              pos[u] += live ? 1u : 0u;
-            }
+      // fix_x() split into its two integer parts, accumulated separately (int32 is enough for 512 elements at a time)
+      auto take = [&](float x, float theta, int& sth, int& stl, int& below) {
+        const float hb = fma_rn(x, fx.p2a, 12582912.0f);
+        const float r = fma_rn(x, fx.p2a, -sub_rn(hb, 12582912.0f));
+        const float lb = fma_rn(r, 1048576.0f, 12582912.0f);
+        const bool in = x < theta;
+        sth += in ? (int)__float_as_uint(hb) - 0x4B400000 : 0;
+        stl += in ? (int)__float_as_uint(lb) - 0x4B400000 : 0;
+        below += in ? 1 : 0;
+      };
+      for (int p = tid; p < npairs; p += kThreads) {
+        const int j = p / Nc, c = p - j * Nc;
+        const float s = sm.scale[c];
+        const float level = L.lo + (float)j;
+        const float theta = code_threshold(s, level);
+        const int bin = bin_of(theta, bmul), b = bin_slot(bin);
+        const unsigned int beg = bin ? sm.cnt[bin_slot(bin - 1)] : 0u, end = sm.cnt[b];
+        long long ps = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);
+        long long cn = (long long)beg;
+        // the threshold's own bin, two elements per step
+        for (unsigned int i0 = beg; i0 < end; i0 += 512u) {
+          const unsigned int i1 = min(end, i0 + 512u);
+          int sth = 0, stl = 0, below = 0;
+          unsigned int i = i0;
+          for (; i + 1u < i1; i += 2u) {
+            const float x0 = sm.sorted[i], x1 = sm.sorted[i + 1u];
+            take(x0, theta, sth, stl, below);
+            take(x1, theta, sth, stl, below);
           }
-#pragma unroll
-          for (int u = 0; u < kPairWays; ++u) {
-            cn[u] += below[u];
-            ps[u] += (long long)sth[u] * 1048576ll + (long long)stl[u];
-          }
+          if (i < i1) take(sm.sorted[i], theta, sth, stl, below);
+          cn += below;
+          ps += (long long)sth * 1048576ll + (long long)stl;
         }
-#pragma unroll
-        for (int u = 0; u < kPairWays; ++u) {
-          double term = threshold_term(s[u], level[u], cn[u], ps[u], fx.unit);
-          if (lev[u] == nthr - 1) term += closing_term(s[u], L.hi, (long long)cnt, ptot, fx.unit);
-          if (on[u]) {
-            const long long f = __double2ll_rn(term * unit_inv);
-            atomicAdd(&sm.part[0][cand[u]], (unsigned int)(f & 0x1fffffll));
-            atomicAdd(&sm.part[1][cand[u]], (unsigned int)((f >> 21) & 0x1fffffll));
-            atomicAdd(&sm.part[2][cand[u]], (unsigned int)(int)(f >> 42));
-          }
-        }
+        double term = threshold_term(s, level, cn, ps, fx.unit);
+        if (j == nthr - 1) term += closing_term(s, L.hi, (long long)cnt, ptot, fx.unit);
+        const long long f = __double2ll_rn(term * unit_inv);
+        atomicAdd(&sm.part[0][c], (unsigned int)(f & 0x1fffffll));
+        atomicAdd(&sm.part[1][c], (unsigned int)((f >> 21) & 0x1fffffll));
+        atomicAdd(&sm.part[2][c], (unsigned int)(int)(f >> 42));
       }
     }
     __syncthreads();
