@@ -40,7 +40,9 @@ struct DirectSmem {
 // threshold ("binned") form of the search, see numerics.cuh
 constexpr int kBins = 8192;        // linear bins over [-absmax, absmax]
 constexpr int kBinSlots = kBins + kBins / 8;  // see bin_slot()
-constexpr int kStageCap = 20480;   // elements sorted by bin in shared memory at a time (40 per thread)
+// elements sorted by bin in shared memory at a time: as many as fit next to the bin arrays in the 227 KB of a CTA (every
+// further stage repeats the fixed costs of the scan and the threshold pass: a 20.7 k chunk took 27 us as two stages)
+constexpr int kStageCap = 24064;
 constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
 struct BinnedSmem {
   __align__(16) float sorted[kStageCap];   // the stage's elements grouped by bin
@@ -60,6 +62,7 @@ union SearchSmem {
   DirectSmem direct;
   BinnedSmem binned;
 };
+static_assert(sizeof(SearchSmem) + 512 <= 227 * 1024, "the search scratch must fit the dynamic shared memory of one CTA");
 
 // ---- packed pairs of float32 (two independent IEEE round-to-nearest operations per instruction).
 // NOTE: ptxas fuses a single-use mul.rn.f32x2 feeding an add/sub.rn.f32x2 into one FFMA2 (unlike the
@@ -262,7 +265,7 @@ __device__ inline void cta_candidate_sums_direct(const float* __restrict__ v, lo
 //   pass 3  one (candidate, threshold) pair per thread: exact threshold, its bin, prefix + the bin's elements compared
 //           one by one -> C, P -> float64 term -> fixed point -> per-candidate shared accumulator (three 21-bit slices)
 // bin(x) is monotone in x, so every element in a lower bin is below the threshold and every element in a higher bin
-// is not; only the threshold's own bin (kStageCap / kBins = 5 elements on average) is inspected.
+// is not; only the threshold's own bin (kStageCap / kBins = 3 elements on average, ~7 in the central bins of bell-shaped data) is inspected.
 __device__ __forceinline__ int bin_of(float x, float bmul) {
   const float t = fma_rn(x, bmul, 12582912.0f + (float)(kBins / 2));  // rne(x * bmul) + kBins / 2 in the low mantissa bits
   const int b = (int)__float_as_uint(t) - 0x4B400000;
