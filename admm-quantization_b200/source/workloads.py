@@ -88,6 +88,17 @@ _TILE_FIXED = 16           # csrc/admm_loop.cu kTileFixed: tile cost that does n
 _PHASE_FLOOR_US = 14.0     # P2 + P3 of a factor that is too small to matter: barriers and L2 round trips
 
 
+_STAGE_CAP = 24064         # csrc/search.cuh kStageCap
+_STAGE_FIXED_US = 7.0      # scan + threshold pass of one more stage (measured: 20.7 k elements as two stages 27 us, as one 20 us)
+
+
+def search_stages(rows, rank, g):
+    """Stages of the clip search per CTA when rows x rank elements are split over g CTAs (chunks are multiples of 64)."""
+    chunk = -(-(rows * rank) // g)
+    chunk = -(-chunk // 64) * 64
+    return max(1, -(-chunk // _STAGE_CAP))
+
+
 def product_cost(rows, rank, g, solve_precision=1):
     """Relative time of one ridge product H_ls = RHS . Minv on g CTAs (mirrors launch_loop in csrc/admm_loop.cu)."""
     if rows <= 16 or solve_precision != 1 or rows < 64 or rank < 32:
@@ -111,7 +122,9 @@ def predict_sweep_ms(measured_ms, g0, g, modes, solve_precision=1):
         p1g = p1 * product_cost(rows, rank, g, solve_precision) / product_cost(rows, rank, g0, solve_precision)
         floor = min(_PHASE_FLOOR_US, p23)
         p23g = floor + (p23 - floor) * g0 / g
-        loop += it * (p1g + p23g) / 1e3
+        # the clip search works in stages of _STAGE_CAP elements per CTA; every further stage repeats its fixed costs
+        p23g += _STAGE_FIXED_US * (search_stages(rows, rank, g) - search_stages(rows, rank, g0))
+        loop += it * (p1g + max(p23g, floor)) / 1e3
     return rest + loop
 
 
