@@ -371,6 +371,10 @@ def run_native(args):
         sampler.start()
     launches0 = _native.launch_count()
     step_ms = []
+    # inner iterations actually executed in the timed steps, per layer and factor, from the kernels' device reports (the
+    # loop may leave early: r < eps and s < eps, source/admm.py:64-65) - the metric counts these, not the nominal 999
+    done = [[0] * s.N for s in solvers]
+    early = nonfinite = 0
     barrier()
     for _ in range(args.steps):
         flush.fill_(1)                      # L2 flush between timed steps (outside the event pair)
@@ -380,28 +384,39 @@ def run_native(args):
         e1.record()
         torch.cuda.synchronize()
         step_ms.append(e0.elapsed_time(e1))
+        for k, sv in enumerate(solvers):
+            for m, r in enumerate(sv.last_reports):
+                done[k][m] += int(r.iterations)
+                early += int(r.iterations) < sv.max_iter_admm - 1
+                nonfinite += bool(int(r.status) & _native.ST_NONFINITE)
     barrier()
+    done_total = sum(sum(d) for d in done)
     launches = _native.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    value = world * inner_per_step * args.steps / (total_ms / 1e3)
+    done_all = torch.tensor([done_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(done_all, op=dist.ReduceOp.SUM)
+    value = float(done_all.item()) / (total_ms / 1e3)
 
     # ---- the dominant kernel (persistent ADMM loop), timed with CUDA events on its own stream.  In concurrent mode a
     # launch holds only its share g of the SMs, so its duration is weighted by g / SMs: the sum is the time the whole
     # GPU would have been busy with these launches (equals the plain sum when every launch uses every SM).
     loop_ms, loop_gpu_ms, per_layer = 0.0, 0.0, {}
-    for (name, _, _, _), s in zip(problems, solvers):
+    for k, ((name, _, _, _), s) in enumerate(zip(problems, solvers)):
         ms = sum(a.elapsed_time(b) for _, a, b in s.loop_events)
         loop_ms += ms
         loop_gpu_ms += ms * ((s.max_ctas or sm_count) / sm_count)
-        per_layer[name] = round(s.inner_iterations_per_sweep() * args.steps / (ms / 1e3), 1)
+        per_layer[name] = round(sum(done[k]) / (ms / 1e3), 1)
     n_loop = sum(len(s.loop_events) for s in solvers)
-    alg_bytes = sum(s.loop_algorithmic_bytes_per_sweep() for s in solvers) * args.steps
-    evals = sum(s.candidate_evaluations_per_sweep() for s in solvers) * args.steps
-    flops = sum(s.solve_flops_per_sweep() for s in solvers) * args.steps
+    # algorithmic work of the iterations that ran
+    alg_bytes = sum(it * (16 * f.shape[0] * s.R + 4 * s.R * s.R) for s, d in zip(solvers, done) for f, it in zip(s.factors, d))
+    evals = sum(it * (s.num_attempts if s.qscheme == QSCHEME else 0) * f.shape[0] * s.R
+                for s, d in zip(solvers, done) for f, it in zip(s.factors, d))
+    flops = sum(it * 2 * f.shape[0] * s.R * s.R for s, d in zip(solvers, done) for f, it in zip(s.factors, d))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -445,6 +460,7 @@ def run_native(args):
         barrier()
         t_e2e = []
         h2d = d2h = 0
+        done_e2e = 0
         for _ in range(args.steps):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -453,11 +469,14 @@ def run_native(args):
             e1.record()
             torch.cuda.synchronize()
             t_e2e.append(e0.elapsed_time(e1))
+            done_e2e += sum(int(_native.read_report(r).iterations) for sv in solvers for r in sv.reports_dev)
         barrier()
         tot = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([done_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * inner_per_step * args.steps / (float(tot.item()) / 1e3), "unit": UNIT,
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(cnt.item()) / (float(tot.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(tot.item()) / args.steps}
 
     # ---- final factor gather over NCCL (once per job, outside the timed region)
@@ -488,7 +507,11 @@ def run_native(args):
                                                    "concurrency": args.concurrency,
                                                    "ctas_per_layer": dict(zip([p[0] for p in problems], budgets)),
                                                    "parallelism": f"{world} independent seeds, one per GPU; no data-path collective",
-                                                   "inner_iterations_per_step_per_gpu": inner_per_step}),
+                                                   "inner_iterations_per_step_per_gpu": done_total / args.steps,
+                                                   "inner_iterations_nominal_per_step": inner_per_step,
+                                                   "loops_left_early": f"{early} of {args.steps * sum(sv.N for sv in solvers)} "
+                                                                       "(exit test r < eps and s < eps, eps = 1e-8)",
+                                                   "loops_nonfinite": nonfinite}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "per_layer_inner_iter_per_s": per_layer,
                 "per_layer_sweep_ms_last_step": {p[0]: round(a.elapsed_time(b), 1) for p, (a, b) in zip(problems, sweep_events)},
