@@ -3,8 +3,9 @@
 //
 // One cooperative launch (one CTA per SM) runs ALL max_iter-1 inner iterations; per iteration
 //   P1  H_ls = RHS . Minv            RHS = F + rho (H + U)                                (:56-57)
-//       precision 0: float32 FFMA tile product (parity mode); precision 1: 3xTF32 on tcgen05/TMEM, operands
-//       fetched by TMA (tc_gemm.cuh; throughput mode); factors with <= 16 rows: column-strip FMA product;
+//       precision 0: float64-accumulating tiles against the float64 inverse (parity mode: the correctly rounded
+//       solve); precision 1: 3xTF32 on tcgen05/TMEM, operands fetched by TMA (tc_gemm.cuh; throughput mode);
+//       precision 2 and shapes that do not fill a tensor-core tile: float32 FFMA tiles, column strips for <= 16 rows;
 //       admmq_split_loop: elementwise (two-block splitting)
 //       epilogue: abs-max key of V = H_ls - U                                          (:59, q.py:129)
 //   --- device-wide barrier
@@ -75,6 +76,7 @@ struct LoopParams {
   float* V;                  // I x R flat: H_ls - U, the projection input of this iteration (source/admm.py:59)
   float* RHS;                // I x Rp (pad columns stay zero)
   const float* Minv;         // R x Rp
+  const double* Minv64;      // R x Rp float64 inverse (parity mode, kF64P1) or nullptr
 };
 
 // P1 shared memory: two K-groups (256 threads each) work on alternating 16-deep slabs of the same
@@ -161,6 +163,93 @@ __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned i
           const int i = i0 + ty * TM + m, c = n0 + tx * TN + n;
           if (i < I && c < R) {
             const float h = add_rn(acc[m][n], gs.red[(ty * TM + m) * BN + tx * TN + n]);
+            p.Hls[(size_t)i * Rp + c] = h;
+            const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
+            p.V[(size_t)i * R + c] = v;
+            const unsigned int k = float_key(v);
+            kmax = max(kmax, k);
+            kinv = max(kinv, ~k);
+          }
+        }
+    }
+  }
+  kmax = warp_max_u32(kmax);
+  kinv = warp_max_u32(kinv);
+  if ((threadIdx.x & 31) == 0 && (kmax | kinv) != 0u) {
+    atomicMax(&keys[0], kmax);
+    atomicMax(&keys[1], kinv);
+  }
+}
+
+// P1 of the PARITY mode (precision 0): H_ls = fl32( RHS . Minv64 ) with the inverse kept in float64 and every product
+// and sum formed in float64, i.e. the correctly rounded solution of the ridge system (up to one double rounding) -
+// what LAPACK's float32 potrs (source/admm.py:56) approximates to 3e-7.  Same tiling as gemm_phase: two K-groups on
+// alternating 16-deep slabs, summed in fixed order.  FP64 FMAs run at half the FP32 rate on B200; this mode exists for
+// the bit-level comparisons, not for throughput.
+template <int BM, int BN>
+struct __align__(16) GemmSmem64 {
+  float a[2][16][BM + 4];
+  double b[2][16][BN + 2];
+  double red[BM * BN];
+};
+
+template <int BM, int BN, int TM, int TN>
+__device__ void gemm_phase_f64(const LoopParams& p, GemmSmem64<BM, BN>& gs, unsigned int* keys) {
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == 256, "thread tiling must cover the tile with one K-group");
+  const int kg = threadIdx.x >> 8, t = threadIdx.x & 255, tx = t % TX, ty = t / TX;
+  const int I = p.I, R = p.R, Rp = p.Rp;
+  const int tilesN = (R + BN - 1) / BN, tilesM = (I + BM - 1) / BM;
+  const int nslab = (R + 15) / 16, nstep = (nslab + 1) / 2;   // slab = 2 * step + kg
+  unsigned int kmax = 0u, kinv = 0u;
+  for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
+    const int i0 = (tile / tilesN) * BM, n0 = (tile % tilesN) * BN;
+    double acc[TM][TN];
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+      for (int n = 0; n < TN; ++n) acc[m][n] = 0.0;
+    for (int step = 0; step < nstep; ++step) {
+      const int k0 = (2 * step + kg) * 16;
+      __syncthreads();
+      for (int idx = t; idx < BM * 16; idx += 256) {  // A slab, transposed into [k][row]
+        const int row = idx >> 4, kk = idx & 15;
+        gs.a[kg][kk][row] = (i0 + row < I && k0 + kk < R) ? __ldcg(p.RHS + (size_t)(i0 + row) * Rp + k0 + kk) : 0.0f;
+      }
+      for (int idx = t; idx < 16 * BN; idx += 256) {  // B slab
+        const int kk = idx / BN, c = idx - kk * BN;
+        gs.b[kg][kk][c] = (k0 + kk < R && n0 + c < R) ? __ldg(p.Minv64 + (size_t)(k0 + kk) * Rp + n0 + c) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int kk = 0; kk < 16; ++kk) {
+        double av[TM], bv[TN];
+#pragma unroll
+        for (int m = 0; m < TM; ++m) av[m] = (double)gs.a[kg][kk][ty * TM + m];
+#pragma unroll
+        for (int n = 0; n < TN; ++n) bv[n] = gs.b[kg][kk][tx * TN + n];
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+          for (int n = 0; n < TN; ++n) acc[m][n] = fma(av[m], bv[n], acc[m][n]);
+      }
+    }
+    __syncthreads();
+    if (kg == 1) {
+#pragma unroll
+      for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) gs.red[(ty * TM + m) * BN + tx * TN + n] = acc[m][n];
+    }
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) {
+          const int i = i0 + ty * TM + m, c = n0 + tx * TN + n;
+          if (i < I && c < R) {
+            const float h = (float)(acc[m][n] + gs.red[(ty * TM + m) * BN + tx * TN + n]);
             p.Hls[(size_t)i * Rp + c] = h;
             const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
             p.V[(size_t)i * R + c] = v;
@@ -303,6 +392,7 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
 // elementwise, H_ = (rho (H + U) + W - H2) / (1 + rho) with p.F = W, evaluated in the reference's operation order.
 // Every CTA works on the chunk of elements it also owns in P2 / P3 (I = 1, R = number of elements).
 constexpr int kDiagP1 = -1000;
+constexpr int kF64P1 = -2000;  // TCBN value of the parity mode: float64-accumulating tiles against Minv64
 __device__ void elementwise_phase(const LoopParams& p, float rho, long long e0, long long e1, unsigned int* keys) {
   const float opr = add_rn(1.0f, rho);
   unsigned int kmax = 0u, kinv = 0u;
@@ -405,9 +495,10 @@ template <int BM, int BN, int TCBN>
 union LoopSmem {
   SearchSmem search;
   GemmSmem<BM, BN> gemm;
+  GemmSmem64<BM, BN> gemm64;
   ResidualSmem res;
   unsigned char tc_tiles[TCBN > 0 ? tc::TileSmem<(TCBN > 0 ? TCBN : 16), kLoopPS>::kBytes : 16];
-  SkinnySmem<(TCBN < 0 && TCBN != kDiagP1 ? -TCBN : 1)> skinny;
+  SkinnySmem<(TCBN < 0 && TCBN != kDiagP1 && TCBN != kF64P1 ? -TCBN : 1)> skinny;
 };
 
 // sum over the CTA of four per-thread doubles, result valid in every thread
@@ -432,7 +523,8 @@ __device__ __forceinline__ void cta_sum4(double v[4], ResidualSmem& rs) {
 
 // TCBN = 0: P1 as float32 FFMA tiles (BM x BN, TM x TN per thread); TCBN = 16 / 32 / 64: P1 on the tensor cores;
 // TCBN = -MI: P1 for factors with at most MI rows (gemm_phase_skinny); TCBN = kDiagP1: elementwise P1 of the
-// two-block splitting (elementwise_phase).
+// two-block splitting (elementwise_phase); TCBN = kF64P1: float64-accumulating tiles against the float64 inverse
+// (parity mode, gemm_phase_f64).
 template <int BM, int BN, int TM, int TN, int TCBN>
 __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant__ LoopParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -506,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     // ---------------- P1
     if constexpr (TCBN > 0) gemm_phase_tc<TCBN>(p, sm.tc_tiles, pipe, pst, hdr->keys[slot]);
     else if constexpr (TCBN == kDiagP1) elementwise_phase(p, rho, e0, e1, hdr->keys[slot]);
+    else if constexpr (TCBN == kF64P1) gemm_phase_f64<BM, BN, TM, TN>(p, sm.gemm64, hdr->keys[slot]);
     else if constexpr (TCBN < 0) gemm_phase_skinny<-TCBN>(p, sm.skinny, hdr->keys[slot]);
     else gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
     if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
@@ -680,7 +773,7 @@ static LoopLayout loop_layout(int I, int R, int grid, bool with_minv_parts = tru
 }
 
 struct IterationLayout {  // workspace of admmq_admm_iteration = scalars + Minv + inverse scratch + loop workspace
-  size_t header, minv, inv_ws, loop_ws, total;
+  size_t header, minv, minv64, inv_ws, loop_ws, total;
 };
 
 static size_t spd_scratch_bytes(int R) {
@@ -699,6 +792,7 @@ static IterationLayout iteration_layout(int I, int R, int grid) {
   };
   l.header = take(sizeof(IterationHeader));
   l.minv = take((size_t)R * Rp * sizeof(float));
+  l.minv64 = take((size_t)R * Rp * sizeof(double));
   l.inv_ws = take(spd_scratch_bytes(R));
   l.loop_ws = take(loop_layout(I, R, grid).total);
   l.total = off;
@@ -713,7 +807,7 @@ static int coop_grid(const DeviceProps& dp, int max_ctas) {
   return (max_ctas > 0 && max_ctas < dp.sm_count) ? max_ctas : dp.sm_count;
 }
 
-static int launch_spd_inverse(const float* G, int R, float* Minv, int ldm, float* rho_out, int* status,
+static int launch_spd_inverse(const float* G, int R, float* Minv, double* Minv64, int ldm, float* rho_out, int* status,
                               unsigned int* barrier, double* Lw, double* Xw, int grid, cudaStream_t stream) {
   InvParams ip;
   ip.G = G;
@@ -724,6 +818,7 @@ static int launch_spd_inverse(const float* G, int R, float* Minv, int ldm, float
   ip.Lw = Lw;
   ip.Xw = Xw;
   ip.Minv = Minv;
+  ip.Minv64 = Minv64;
   ip.rho_out = rho_out;
   ip.status = status;
   ip.barrier = barrier;
@@ -763,12 +858,12 @@ static int check_loop_args(const char* who, const void* H, const void* U, const 
   return ADMMQ_OK;
 }
 
-static int launch_loop(float* H, float* U, const float* F, const float* Minv, const float* rho, const int* inv_status,
-                       int I, int R, int max_iter, float eps, int bits, int qscheme, int num_attempts, int precision,
+static int launch_loop(float* H, float* U, const float* F, const float* Minv, const double* Minv64, const float* rho,
+                       const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme, int num_attempts, int precision,
                        int8_t* codes, admmq_loop_report* report, char* ws, int grid, cudaStream_t stream) {
   const LoopLayout l = loop_layout(I, R, grid);
   static const bool no_resident = getenv("ADMMQ_NO_RESIDENT") != nullptr;  // diagnostics: force the general kernel
-  if (grid == 1 && !no_resident && resident_fits(I, R, l.Rp, num_attempts)) {
+  if (grid == 1 && precision != 0 && !no_resident && resident_fits(I, R, l.Rp, num_attempts)) {
     // a small factor on a single CTA: the shared-memory-resident loop (admm_loop_resident.cuh)
     ResidentParams rp;
     rp.H = H;
@@ -820,6 +915,7 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.V = (float*)(ws + l.v);
   p.RHS = (float*)(ws + l.rhs);
   p.Minv = Minv;
+  p.Minv64 = Minv64;
   p.MinvHi = (float*)(ws + l.minv_hi);
   p.MinvLo = (float*)(ws + l.minv_lo);
   p.tc_bn = 0;
@@ -828,8 +924,19 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   size_t smem = 0;
   // tensor-core P1 only pays off when the factor has enough rows to fill a good part of a 128-row tile
   const bool use_tc = precision == 1 && I >= 64 && R >= 32;
-  const bool use_skinny = I <= 16 && (long long)I * l.Rp <= SkinnySmem<16>::kRhsFloats;
-  if (use_skinny) {
+  const bool use_skinny = precision != 0 && I <= 16 && (long long)I * l.Rp <= SkinnySmem<16>::kRhsFloats;
+  if (precision == 0) {  // parity mode: float64-accumulating tiles against the float64 inverse
+    memset(&p.tm_rhs, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv_hi, 0, sizeof(CUtensorMap));
+    memset(&p.tm_minv_lo, 0, sizeof(CUtensorMap));
+    if (pick_tile(I, R, grid) == 0) {
+      fn = (const void*)k_admm_loop<64, 64, 4, 4, kF64P1>;
+      smem = sizeof(LoopSmem<64, 64, kF64P1>);
+    } else {
+      fn = (const void*)k_admm_loop<32, 32, 2, 2, kF64P1>;
+      smem = sizeof(LoopSmem<32, 32, kF64P1>);
+    }
+  } else if (use_skinny) {
     memset(&p.tm_rhs, 0, sizeof(CUtensorMap));
     memset(&p.tm_minv_hi, 0, sizeof(CUtensorMap));
     memset(&p.tm_minv_lo, 0, sizeof(CUtensorMap));
@@ -900,8 +1007,8 @@ extern "C" size_t admmq_spd_inverse_workspace_bytes(int R) {
   return 256 + spd_scratch_bytes(R);
 }
 
-extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, int max_ctas,
-                                 void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, double* Minv64, float* rho_out, int* status,
+                                 int max_ctas, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (G == nullptr || Minv == nullptr || rho_out == nullptr || status == nullptr || R <= 0)
     return fail(ADMMQ_E_BADARG, "admmq_spd_inverse: bad argument");
@@ -915,7 +1022,7 @@ extern "C" int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_
   ADMMQ_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), stream));
   double* Lw = (double*)(ws + 256);
   double* Xw = (double*)(ws + 256 + spd_scratch_bytes(R) / 2);
-  return launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp, max_ctas), stream);
+  return launch_spd_inverse(G, R, Minv, Minv64, admmq_padded_ld(R), rho_out, status, (unsigned int*)ws, Lw, Xw, coop_grid(dp, max_ctas), stream);
 }
 
 extern "C" size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts) {
@@ -924,13 +1031,15 @@ extern "C" size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts
   return loop_layout(I, R, kMaxGrid).total;
 }
 
-extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
-                               const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
+extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const double* Minv64,
+                               const float* rho, const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
                                int num_attempts, int precision, int max_ctas, int8_t* codes, admmq_loop_report* report,
                                void* workspace, size_t workspace_bytes, void* stream_) {
   if (int e = check_loop_args("admmq_admm_loop", H, U, F, Minv, report, I, R, bits, qscheme, num_attempts)) return e;
   if (rho == nullptr) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: rho is null");
-  if (precision != 0 && precision != 1) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: precision must be 0 or 1");
+  if (precision < 0 || precision > 2) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: precision must be 0, 1 or 2");
+  if (precision == 0 && Minv64 == nullptr)
+    return fail(ADMMQ_E_BADARG, "admmq_admm_loop: precision 0 (parity mode) needs the float64 inverse Minv64 of admmq_spd_inverse");
   if (((uintptr_t)Minv & 15) != 0) return fail(ADMMQ_E_BADARG, "admmq_admm_loop: Minv must be 16-byte aligned");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;
@@ -939,8 +1048,8 @@ extern "C" int admmq_admm_loop(float* H, float* U, const float* F, const float* 
       ((uintptr_t)workspace & 255) != 0)
     return fail(ADMMQ_E_WORKSPACE, "admmq_admm_loop: workspace needs %zu bytes, 256-byte aligned",
                 admmq_admm_loop_workspace_bytes(I, R, num_attempts));
-  return launch_loop(H, U, F, Minv, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision, codes,
-                     report, (char*)workspace, coop_grid(dp, max_ctas), (cudaStream_t)stream_);
+  return launch_loop(H, U, F, Minv, Minv64, rho, inv_status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision,
+                     codes, report, (char*)workspace, coop_grid(dp, max_ctas), (cudaStream_t)stream_);
 }
 
 // ---- two-block splitting W ~ W_q + W_r (scripts/factorize_lowrank.py): the quantized block's inner loop
@@ -1018,7 +1127,7 @@ extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const fl
                                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_loop_args("admmq_admm_iteration", H, U, F, G, report, I, R, bits, qscheme, num_attempts)) return e;
-  if (precision != 0 && precision != 1) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: precision must be 0 or 1");
+  if (precision < 0 || precision > 2) return fail(ADMMQ_E_BADARG, "admmq_admm_iteration: precision must be 0, 1 or 2");
   DeviceProps dp;
   if (int e = device_props(&dp)) return e;
   if (!dp.coop) return fail(ADMMQ_E_UNSUPPORTED, "device does not support cooperative launch");
@@ -1030,9 +1139,10 @@ extern "C" int admmq_admm_iteration(float* H, float* U, const float* F, const fl
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws + l.header, 0, 256, stream));
   IterationHeader* ih = (IterationHeader*)(ws + l.header);
   float* Minv = (float*)(ws + l.minv);
-  if (int e = launch_spd_inverse(G, R, Minv, admmq_padded_ld(R), &ih->rho, &ih->status, &ih->barrier_inv,
+  double* Minv64 = precision == 0 ? (double*)(ws + l.minv64) : nullptr;
+  if (int e = launch_spd_inverse(G, R, Minv, Minv64, admmq_padded_ld(R), &ih->rho, &ih->status, &ih->barrier_inv,
                                  (double*)(ws + l.inv_ws), (double*)(ws + l.inv_ws + spd_scratch_bytes(R) / 2), grid, stream))
     return e;
-  return launch_loop(H, U, F, Minv, &ih->rho, &ih->status, I, R, max_iter, eps, bits, qscheme, num_attempts, precision,
-                     codes, report, ws + l.loop_ws, grid, stream);
+  return launch_loop(H, U, F, Minv, Minv64, &ih->rho, &ih->status, I, R, max_iter, eps, bits, qscheme, num_attempts,
+                     precision, codes, report, ws + l.loop_ws, grid, stream);
 }

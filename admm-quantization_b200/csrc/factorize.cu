@@ -22,7 +22,7 @@ struct Carve {
 };
 
 struct FactorizeLayout {
-  size_t unf[3], perm[3], G, F, Minv, scalars, reports, err, ws_inv, ws_loop, ws_proj, ws_mttkrp, ws_err, total;
+  size_t unf[3], perm[3], G, F, Minv, Minv64, scalars, reports, err, ws_inv, ws_loop, ws_proj, ws_mttkrp, ws_err, total;
   size_t n_inv, n_loop, n_proj, n_mttkrp, n_err;
   int nx[3], ny[3];
 };
@@ -50,6 +50,7 @@ static FactorizeLayout factorize_layout(int ndim, const int* shape, int R, const
   l.G = c.take((size_t)R * R * sizeof(float));
   l.F = c.take((size_t)maxd * R * sizeof(float));
   l.Minv = c.take((size_t)R * admmq_padded_ld(R) * sizeof(float));
+  l.Minv64 = c.take(p->solve_precision == 0 ? (size_t)R * admmq_padded_ld(R) * sizeof(double) : 0);
   l.scalars = c.take(64);
   l.reports = c.take(3 * sizeof(admmq_loop_report));
   l.err = c.take(4 * sizeof(double));
@@ -79,8 +80,8 @@ static int check_params(const char* who, int ndim, const int* shape, int R, cons
   if (p->max_iter_als < 1 || p->max_iter_admm < 1) return fail(ADMMQ_E_BADARG, "%s: iteration budgets must be >= 1", who);
   if (p->bits < 1 || p->bits > 8) return fail(ADMMQ_E_BADARG, "%s: bits must be in 1..8", who);
   if (p->qscheme < 0 || p->qscheme > 3) return fail(ADMMQ_E_BADARG, "%s: unknown qscheme %d", who, p->qscheme);
-  if (p->solve_precision < 0 || p->solve_precision > 1 || p->mttkrp_precision < 0 || p->mttkrp_precision > 1)
-    return fail(ADMMQ_E_BADARG, "%s: precision flags must be 0 or 1", who);
+  if (p->solve_precision < 0 || p->solve_precision > 2 || p->mttkrp_precision < 0 || p->mttkrp_precision > 1)
+    return fail(ADMMQ_E_BADARG, "%s: solve_precision must be 0..2, mttkrp_precision 0 or 1", who);
   return ADMMQ_OK;
 }
 
@@ -116,6 +117,7 @@ struct Run {
   float* G() { return (float*)(ws + l.G); }
   float* F() { return (float*)(ws + l.F); }
   float* Minv() { return (float*)(ws + l.Minv); }
+  double* Minv64() { return prm.solve_precision == 0 ? (double*)(ws + l.Minv64) : nullptr; }
   float* rho() { return (float*)(ws + l.scalars); }
   int* inv_status() { return (int*)(ws + l.scalars + 16); }
   admmq_loop_report* reports() { return (admmq_loop_report*)(ws + l.reports); }
@@ -201,8 +203,8 @@ struct Run {
       } else if (int e = admmq_mttkrp(unf[m], shape[m], X, l.nx[m], Y, l.ny[m], R, F(), 0, ws + l.ws_mttkrp, l.n_mttkrp, st)) {
         return e;                                                                                              // :217
       }
-      if (int e = admmq_spd_inverse(G(), R, Minv(), rho(), inv_status(), prm.max_ctas, ws + l.ws_inv, l.n_inv, st)) return e;
-      if (int e = admmq_admm_loop(factors[m], duals[m], F(), Minv(), rho(), inv_status(), shape[m], R, prm.max_iter_admm,
+      if (int e = admmq_spd_inverse(G(), R, Minv(), Minv64(), rho(), inv_status(), prm.max_ctas, ws + l.ws_inv, l.n_inv, st)) return e;
+      if (int e = admmq_admm_loop(factors[m], duals[m], F(), Minv(), Minv64(), rho(), inv_status(), shape[m], R, prm.max_iter_admm,
                                   prm.eps, prm.bits, prm.qscheme, prm.num_attempts, prm.solve_precision, prm.max_ctas,
                                   nullptr, reports() + m, ws + l.ws_loop, l.n_loop, st))
         return e;                                                                                              // :218
@@ -232,7 +234,7 @@ struct Run {
     ++sweep;
     *sweeps_done = sweep;
     const size_t n = hist.size();
-    if (n > 1 && std::fabs((double)hist[n - 2] - (double)hist[n - 1]) < (double)prm.tol) active = false;
+    if (n > 1 && std::fabs((double)hist[n - 2] - (double)hist[n - 1]) < prm.tol) active = false;
     const size_t back = ndim == 3 ? 5 : 10;
     if (n > 10 && (double)hist[n - 1] - (double)hist[n - back] > 1e-3) active = false;
     if (sweep >= prm.max_iter_als) active = false;

@@ -36,6 +36,7 @@ struct InvParams {
   double* Lw;           // Rb x Rb  (in: A, out: L in the lower tiles)
   double* Xw;           // Rb x Rb  (L^-1 in the lower tiles)
   float* Minv;          // R x ldm
+  double* Minv64;       // R x ldm or nullptr: the same inverse before its rounding to float32 (parity mode of the loop)
   float* rho_out;       // device float
   int* status;          // device int: 0 or ADMMQ_E_NOT_PD
   unsigned int* barrier;
@@ -274,6 +275,10 @@ __device__ inline int spd_inverse_body(const InvParams& p, InvSmem& sm, GridBarr
       const int row = a * kNB + rg + 8 * m, col = b * kNB + c;
       if (row < R && col < p.ldm) p.Minv[(size_t)row * p.ldm + col] = (col < R) ? (float)acc[m] : 0.0f;
       if (a != b && col < R && row < p.ldm) p.Minv[(size_t)col * p.ldm + row] = (row < R) ? (float)acc[m] : 0.0f;
+      if (p.Minv64 != nullptr) {
+        if (row < R && col < p.ldm) p.Minv64[(size_t)row * p.ldm + col] = (col < R) ? acc[m] : 0.0;
+        if (a != b && col < R && row < p.ldm) p.Minv64[(size_t)col * p.ldm + row] = (row < R) ? acc[m] : 0.0;
+      }
     }
   }
   bar.sync();

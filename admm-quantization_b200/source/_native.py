@@ -28,7 +28,7 @@ class LoopReport(ctypes.Structure):
 
 class FactorizeParams(ctypes.Structure):
     _fields_ = [("max_iter_als", ctypes.c_int32), ("max_iter_admm", ctypes.c_int32), ("eps", ctypes.c_float),
-                ("tol", ctypes.c_float), ("bits", ctypes.c_int32), ("qscheme", ctypes.c_int32),
+                ("tol", ctypes.c_double), ("bits", ctypes.c_int32), ("qscheme", ctypes.c_int32),
                 ("num_attempts", ctypes.c_int32), ("solve_precision", ctypes.c_int32),
                 ("mttkrp_precision", ctypes.c_int32), ("max_ctas", ctypes.c_int32), ("init_is_random", ctypes.c_int32)]
 
@@ -68,9 +68,9 @@ def _load():
         "admmq_gemm_nt": (c_int, [vp, c_int, c_int, vp, c_int, c_int, c_int, vp, c_int, vp]),
         "admmq_padded_ld": (c_int, [c_int]),
         "admmq_spd_inverse_workspace_bytes": (c_sz, [c_int]),
-        "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, c_int, vp, c_sz, vp]),
+        "admmq_spd_inverse": (c_int, [vp, c_int, vp, vp, vp, vp, c_int, vp, c_sz, vp]),
         "admmq_admm_loop_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
-        "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
+        "admmq_admm_loop": (c_int, [vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, c_int, c_int, c_int, c_int,
                                     vp, vp, vp, c_sz, vp]),
         "admmq_split_loop_workspace_bytes": (c_sz, [c_i64, c_int]),
         "admmq_split_loop": (c_int, [vp, vp, vp, vp, c_i64, c_f, c_int, c_f, c_int, c_int, c_int, c_int, vp, vp, vp, c_sz, vp]),
@@ -127,10 +127,28 @@ def qscheme_id(qscheme: str) -> int:
 
 
 def require_cuda(*tensors):
+    """Every tensor of a call must live on ONE CUDA device (the library launches on a single device and stream)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("libadmmq kernels need CUDA tensors (there is no CPU fallback); got device "
                                f"{t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"libadmmq: all tensors of a call must share one device, got {dev} and {t.device}")
+
+
+def call(device, fn, *args):
+    """Run a library entry point with `device` made current: the C side resolves the device (SM count, cooperative
+    launch, kernel launches, memsets) with cudaGetDevice(), and the stream passed in belongs to `device`."""
+    device = torch.device(device)
+    if torch.cuda.current_device() == device.index:
+        return check(fn(*args))
+    with torch.cuda.device(device):
+        return check(fn(*args))
 
 
 def ptr(t):
@@ -145,14 +163,22 @@ _tls = threading.local()
 
 
 def workspace(nbytes: int, device, tag: str = "main") -> torch.Tensor:
-    """Caller-owned scratch (the library never allocates).  One growing buffer per (device, tag)."""
+    """Caller-owned scratch (the library never allocates).  One growing buffer per (thread, device, STREAM, tag): the
+    scratch holds barrier counters and accumulators of persistent kernels, so two calls that may run concurrently
+    (different streams) must never share it.  A buffer that has to grow is replaced; the old one is handed back to
+    the caching allocator with `record_stream`, so kernels still using it on that stream finish first."""
     cache = getattr(_tls, "ws", None)
     if cache is None:
         cache = _tls.ws = {}
-    key = (torch.device(device).index, tag)
+    device = torch.device(device)
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream, tag)
     buf = cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        if buf is not None:
+            buf.record_stream(stream)
+        with torch.cuda.device(device):
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         cache[key] = buf
     return buf
 
@@ -188,8 +214,8 @@ def project(x, bits, qscheme, num_attempts=200, tmin=None, tmax=None, want_codes
     ws = _ws(project_workspace_bytes(n, num_attempts), xc.device, ws)
     tmin_t = None if tmin is None else torch.as_tensor(tmin, dtype=torch.float32, device=xc.device).reshape(1)
     tmax_t = None if tmax is None else torch.as_tensor(tmax, dtype=torch.float32, device=xc.device).reshape(1)
-    check(lib.admmq_project(ptr(xc), n, int(bits), qscheme_id(qscheme), int(num_attempts), ptr(tmin_t), ptr(tmax_t),
-                            ptr(out), ptr(codes), ptr(info), ptr(ws), ws.numel(), stream_ptr(xc.device)))
+    call(xc.device, lib.admmq_project, ptr(xc), n, int(bits), qscheme_id(qscheme), int(num_attempts), ptr(tmin_t), ptr(tmax_t),
+                            ptr(out), ptr(codes), ptr(info), ptr(ws), ws.numel(), stream_ptr(xc.device))
     return out, codes, info
 
 
@@ -200,8 +226,8 @@ def clip_search_sums(x, bits, num_attempts=200, method=1, max_ctas=0):
     n = xc.numel()
     sums = torch.empty(int(num_attempts), dtype=torch.float64, device=xc.device)
     ws = _ws(project_workspace_bytes(n, num_attempts), xc.device, None)
-    check(lib.admmq_clip_search_sums(ptr(xc), n, int(bits), int(num_attempts), int(method), int(max_ctas), ptr(sums),
-                                     ptr(ws), ws.numel(), stream_ptr(xc.device)))
+    call(xc.device, lib.admmq_clip_search_sums, ptr(xc), n, int(bits), int(num_attempts), int(method), int(max_ctas), ptr(sums),
+                                     ptr(ws), ws.numel(), stream_ptr(xc.device))
     return sums
 
 
@@ -211,8 +237,8 @@ def gram_hadamard(U1, U2=None, out=None):
     U2 = None if U2 is None else f32c(U2)
     R = U1.shape[1]
     G = torch.empty(R, R, dtype=torch.float32, device=U1.device) if out is None else out
-    check(lib.admmq_gram_hadamard(ptr(U1), U1.shape[0], ptr(U2), 0 if U2 is None else U2.shape[0], R, ptr(G),
-                                  stream_ptr(U1.device)))
+    call(U1.device, lib.admmq_gram_hadamard, ptr(U1), U1.shape[0], ptr(U2), 0 if U2 is None else U2.shape[0], R, ptr(G),
+                                  stream_ptr(U1.device))
     return G
 
 
@@ -222,7 +248,7 @@ def unfold3(W, mode, out=None):
     I, J, K = W.shape
     shape = [(I, J * K), (J, I * K), (K, I * J)][mode]
     out = torch.empty(shape, dtype=torch.float32, device=W.device) if out is None else out
-    check(lib.admmq_unfold3(ptr(W), I, J, K, int(mode), ptr(out), stream_ptr(W.device)))
+    call(W.device, lib.admmq_unfold3, ptr(W), I, J, K, int(mode), ptr(out), stream_ptr(W.device))
     return out
 
 
@@ -240,8 +266,8 @@ def mttkrp(Wn, X, Y=None, precision=0, out=None, ws=None):
     assert Wn.shape[1] == nx * ny, (Wn.shape, nx, ny)
     F = torch.empty(M, R, dtype=torch.float32, device=Wn.device) if out is None else out
     ws = _ws(mttkrp_workspace_bytes(M, nx, ny, R, precision), Wn.device, ws)
-    check(lib.admmq_mttkrp(ptr(Wn), M, ptr(X), nx, ptr(Y), ny, R, ptr(F), int(precision), ptr(ws), ws.numel(),
-                           stream_ptr(Wn.device)))
+    call(Wn.device, lib.admmq_mttkrp, ptr(Wn), M, ptr(X), nx, ptr(Y), ny, R, ptr(F), int(precision), ptr(ws), ws.numel(),
+                           stream_ptr(Wn.device))
     return F
 
 
@@ -253,7 +279,7 @@ def permute_myx(Wn, nx, ny):
     assert Wn.shape[1] == nx * ny
     ldv = (nx + 3) // 4 * 4
     V = torch.empty(M * ny, ldv, dtype=torch.float32, device=Wn.device)
-    check(lib.admmq_permute_myx(ptr(Wn), M, int(nx), int(ny), ptr(V), stream_ptr(Wn.device)))
+    call(Wn.device, lib.admmq_permute_myx, ptr(Wn), M, int(nx), int(ny), ptr(V), stream_ptr(Wn.device))
     return V
 
 
@@ -271,7 +297,7 @@ def mttkrp_tc(V, M, X, Y=None, out=None, ws=None):
     assert V.dtype == torch.float32 and V.is_contiguous() and V.shape == (M * ny, (nx + 3) // 4 * 4)
     F = torch.empty(M, R, dtype=torch.float32, device=V.device) if out is None else out
     ws = _ws(mttkrp_tc_workspace_bytes(M, nx, ny, R), V.device, ws)
-    check(lib.admmq_mttkrp_tc(ptr(V), int(M), ptr(X), nx, ptr(Y), ny, R, ptr(F), ptr(ws), ws.numel(), stream_ptr(V.device)))
+    call(V.device, lib.admmq_mttkrp_tc, ptr(V), int(M), ptr(X), nx, ptr(Y), ny, R, ptr(F), ptr(ws), ws.numel(), stream_ptr(V.device))
     return F
 
 
@@ -289,8 +315,8 @@ def recon_error_sums(W0, A, X, Y=None, out=None, ws=None):
     assert W0.shape == (M, nx * ny)
     out = torch.empty(2, dtype=torch.float64, device=W0.device) if out is None else out
     ws = _ws(recon_error_workspace_bytes(M, nx, ny), W0.device, ws)
-    check(lib.admmq_recon_error(ptr(W0), M, ptr(A), ptr(X), nx, ptr(Y), ny, R, ptr(out), ptr(ws), ws.numel(),
-                                stream_ptr(W0.device)))
+    call(W0.device, lib.admmq_recon_error, ptr(W0), M, ptr(A), ptr(X), nx, ptr(Y), ny, R, ptr(out), ptr(ws), ws.numel(),
+                                stream_ptr(W0.device))
     return out
 
 
@@ -302,7 +328,7 @@ def gemm_nt(A, B, out=None):
     N = B.shape[0]
     assert B.shape[1] == K
     C = torch.empty(M, N, dtype=torch.float32, device=A.device) if out is None else out
-    check(lib.admmq_gemm_nt(ptr(A), A.stride(0), M, ptr(B), B.stride(0), N, K, ptr(C), C.stride(0), stream_ptr(A.device)))
+    call(A.device, lib.admmq_gemm_nt, ptr(A), A.stride(0), M, ptr(B), B.stride(0), N, K, ptr(C), C.stride(0), stream_ptr(A.device))
     return C
 
 
@@ -310,8 +336,10 @@ def spd_inverse_workspace_bytes(R):
     return int(lib.admmq_spd_inverse_workspace_bytes(int(R)))
 
 
-def spd_inverse(G, out=None, ws=None, max_ctas=0):
-    """(Minv [R, ld], rho [1], status [1]) of G + trace(G)/R * I.  `out` = preallocated (Minv, rho, status)."""
+def spd_inverse(G, out=None, ws=None, max_ctas=0, minv64=None):
+    """(Minv [R, ld], rho [1], status [1]) of G + trace(G)/R * I.  `out` = preallocated (Minv, rho, status);
+    `minv64` = preallocated float64 [R, ld] that also receives the inverse before its rounding to float32 (the
+    operand of the loop's parity mode), or True to allocate it (it is then returned as a fourth element)."""
     require_cuda(G)
     G = f32c(G)
     R = G.shape[0]
@@ -322,10 +350,16 @@ def spd_inverse(G, out=None, ws=None, max_ctas=0):
         status = torch.empty(1, dtype=torch.int32, device=G.device)
     else:
         Minv, rho, status = out
+    made = minv64 is True
+    if made:
+        minv64 = torch.empty(R, ld, dtype=torch.float64, device=G.device)
+    if minv64 is not None:
+        assert minv64.dtype == torch.float64 and minv64.is_contiguous() and minv64.shape == (R, ld)
+    require_cuda(G, Minv, rho, status, minv64)
     ws = _ws(spd_inverse_workspace_bytes(R), G.device, ws)
-    check(lib.admmq_spd_inverse(ptr(G), R, ptr(Minv), ptr(rho), ptr(status), int(max_ctas), ptr(ws), ws.numel(),
-                                stream_ptr(G.device)))
-    return Minv, rho, status
+    call(G.device, lib.admmq_spd_inverse, ptr(G), R, ptr(Minv), ptr(minv64), ptr(rho), ptr(status), int(max_ctas), ptr(ws),
+         ws.numel(), stream_ptr(G.device))
+    return (Minv, rho, status, minv64) if made else (Minv, rho, status)
 
 
 def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempts=200, codes=None, precision=0,
@@ -340,9 +374,9 @@ def admm_iteration_inplace(H, U, F, G, max_iter, eps, bits, qscheme, num_attempt
     report = torch.empty(ctypes.sizeof(LoopReport), dtype=torch.uint8, device=H.device)
     nbytes = lib.admmq_admm_iteration_workspace_bytes(I, R, int(num_attempts))
     ws = workspace(nbytes, H.device)
-    check(lib.admmq_admm_iteration(ptr(H), ptr(U), ptr(F), ptr(G), I, R, int(max_iter), float(eps), int(bits),
+    call(H.device, lib.admmq_admm_iteration, ptr(H), ptr(U), ptr(F), ptr(G), I, R, int(max_iter), float(eps), int(bits),
                                    qscheme_id(qscheme), int(num_attempts), int(precision), int(max_ctas), ptr(codes),
-                                   ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
+                                   ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device))
     return report
 
 
@@ -355,18 +389,23 @@ def new_report(device):
 
 
 def admm_loop_inplace(H, U, F, Minv, rho, inv_status, max_iter, eps, bits, qscheme, num_attempts=200, codes=None,
-                      report=None, ws=None, precision=0, max_ctas=0):
-    """The persistent loop alone, given (Minv, rho, status) from `spd_inverse`; H and U are updated in place."""
-    require_cuda(H, U, F, Minv, rho)
+                      report=None, ws=None, precision=0, max_ctas=0, minv64=None):
+    """The persistent loop alone, given (Minv, rho, status[, Minv64]) from `spd_inverse`; H and U are updated in place.
+    precision 0 (parity mode) needs `minv64`."""
+    require_cuda(H, U, F, Minv, rho, inv_status, minv64, codes, report, ws)
     for t in (H, U, F, Minv):
         assert t.dtype == torch.float32 and t.is_contiguous()
     I, R = H.shape
     assert U.shape == H.shape and F.shape == H.shape and Minv.shape == (R, lib.admmq_padded_ld(R))
+    if int(precision) == 0 and minv64 is None:
+        raise ValueError("admm_loop_inplace: precision 0 (parity mode) needs minv64 from spd_inverse(..., minv64=...)")
+    if minv64 is not None:
+        assert minv64.dtype == torch.float64 and minv64.is_contiguous() and minv64.shape == Minv.shape
     report = new_report(H.device) if report is None else report
     ws = _ws(admm_loop_workspace_bytes(I, R, num_attempts), H.device, ws)
-    check(lib.admmq_admm_loop(ptr(H), ptr(U), ptr(F), ptr(Minv), ptr(rho), ptr(inv_status), I, R, int(max_iter),
-                              float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), int(precision),
-                              int(max_ctas), ptr(codes), ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device)))
+    call(H.device, lib.admmq_admm_loop, ptr(H), ptr(U), ptr(F), ptr(Minv), ptr(minv64), ptr(rho), ptr(inv_status), I, R,
+         int(max_iter), float(eps), int(bits), qscheme_id(qscheme), int(num_attempts), int(precision), int(max_ctas),
+         ptr(codes), ptr(report), ptr(ws), ws.numel(), stream_ptr(H.device))
     return report
 
 
@@ -380,9 +419,9 @@ def split_loop_inplace(H, U, W, H2, rho, max_iter, eps, bits, qscheme, num_attem
     n = H.numel()
     report = new_report(H.device) if report is None else report
     ws = _ws(int(lib.admmq_split_loop_workspace_bytes(n, int(num_attempts))), H.device, ws)
-    check(lib.admmq_split_loop(ptr(H), ptr(U), ptr(W), ptr(H2), n, float(rho), int(max_iter), float(eps), int(bits),
+    call(H.device, lib.admmq_split_loop, ptr(H), ptr(U), ptr(W), ptr(H2), n, float(rho), int(max_iter), float(eps), int(bits),
                                qscheme_id(qscheme), int(num_attempts), int(max_ctas), ptr(codes), ptr(report), ptr(ws),
-                               ws.numel(), stream_ptr(H.device)))
+                               ws.numel(), stream_ptr(H.device))
     return report
 
 
@@ -411,14 +450,13 @@ def factorize(W, factors, duals, bits, qscheme, max_iter_als, max_iter_admm=1000
     done = ctypes.c_int(0)
     hp, hqp = hist.ctypes.data_as(ctypes.c_void_p), histq.ctypes.data_as(ctypes.c_void_p)
     if N == 3:
-        rc = lib.admmq_factorize_cp3(ptr(Wc), *[int(d) for d in Wc.shape], R, *[ptr(t) for t in factors],
-                                     *[ptr(t) for t in duals], *[ptr(t) for t in fq], ctypes.byref(prm), hp, hqp,
-                                     ctypes.byref(done), ptr(ws), ws.numel(), stream_ptr(Wc.device))
+        call(Wc.device, lib.admmq_factorize_cp3, ptr(Wc), *[int(d) for d in Wc.shape], R, *[ptr(t) for t in factors],
+             *[ptr(t) for t in duals], *[ptr(t) for t in fq], ctypes.byref(prm), hp, hqp,
+             ctypes.byref(done), ptr(ws), ws.numel(), stream_ptr(Wc.device))
     else:
-        rc = lib.admmq_factorize_mat(ptr(Wc), *[int(d) for d in Wc.shape], R, *[ptr(t) for t in factors],
-                                     *[ptr(t) for t in duals], *[ptr(t) for t in fq], ctypes.byref(prm), hp, hqp,
-                                     ctypes.byref(done), ptr(ws), ws.numel(), stream_ptr(Wc.device))
-    check(rc)
+        call(Wc.device, lib.admmq_factorize_mat, ptr(Wc), *[int(d) for d in Wc.shape], R, *[ptr(t) for t in factors],
+             *[ptr(t) for t in duals], *[ptr(t) for t in fq], ctypes.byref(prm), hp, hqp,
+             ctypes.byref(done), ptr(ws), ws.numel(), stream_ptr(Wc.device))
     n = done.value + (0 if init_is_random else 1)
     return [float(v) for v in hist[:n]], [float(v) for v in histq[:n]], done.value, fq
 
@@ -435,6 +473,8 @@ def factorize_batch(jobs):
     for k, j in enumerate(jobs):
         Wc = f32c(j["W"])
         require_cuda(Wc, *j["factors"], *j["duals"])
+        if keep and keep[0][0].device != Wc.device:
+            raise RuntimeError("factorize_batch: all problems of one batch must live on one device")
         N = Wc.ndim
         R = j["factors"][0].shape[1]
         prm = FactorizeParams(int(j["max_iter_als"]), int(j.get("max_iter_admm", 1000)), float(j.get("eps", 1e-8)),
@@ -444,7 +484,10 @@ def factorize_batch(jobs):
                               1 if j.get("init_is_random", True) else 0)
         shape = (ctypes.c_int * N)(*[int(d) for d in Wc.shape])
         need = int(lib.admmq_factorize_workspace_bytes(N, shape, R, ctypes.byref(prm)))
-        ws = torch.empty(need, dtype=torch.uint8, device=Wc.device)
+        ws = j.get("ws")
+        if ws is None:
+            ws = torch.empty(need, dtype=torch.uint8, device=Wc.device)
+        assert ws.numel() >= need
         fq = [torch.empty_like(f) for f in j["factors"]]
         hist = np.zeros(prm.max_iter_als + 1, np.float32)
         histq = np.zeros(prm.max_iter_als + 1, np.float32)
@@ -461,7 +504,7 @@ def factorize_batch(jobs):
         q.sweeps_done = ctypes.pointer(done)
         q.workspace, q.workspace_bytes, q.stream = ws.data_ptr(), ws.numel(), stream.cuda_stream
         keep.append((Wc, ws, fq, hist, histq, done, stream, prm))
-    check(lib.admmq_factorize_batch(n, arr))
+    call(keep[0][0].device, lib.admmq_factorize_batch, n, arr)   # all problems of a batch live on one device
     out = []
     for Wc, ws, fq, hist, histq, done, stream, prm in keep:
         torch.cuda.current_stream(Wc.device).wait_stream(stream)
@@ -474,9 +517,12 @@ def launch_count() -> int:
     return int(lib.admmq_launch_count())
 
 
-def read_report(report: torch.Tensor) -> LoopReport:
-    raw = bytes(report.cpu().numpy().tobytes())
+def decode_report(raw: bytes) -> LoopReport:
     rep = LoopReport.from_buffer_copy(raw)
     if rep.status == E_NOT_PD:
         raise torch.linalg.LinAlgError("admm_iteration: G + rho*I is not positive-definite (Cholesky failed)")
     return rep
+
+
+def read_report(report: torch.Tensor) -> LoopReport:
+    return decode_report(bytes(report.cpu().numpy().tobytes()))

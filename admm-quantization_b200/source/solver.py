@@ -49,6 +49,8 @@ class LayerSolver:
         self.G = torch.empty(R, R, dtype=torch.float32, device=dev)
         self.F = [torch.empty(d, R, dtype=torch.float32, device=dev) for d in dims]
         self.Minv = torch.empty(R, ld, dtype=torch.float32, device=dev)
+        # parity mode (solve_precision 0): the loop multiplies by the float64 inverse and accumulates in float64
+        self.Minv64 = torch.empty(R, ld, dtype=torch.float64, device=dev) if self.solve_precision == 0 else None
         self.rho = torch.empty(1, dtype=torch.float32, device=dev)
         self.inv_status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.reports_dev = [_native.new_report(dev) for _ in range(self.N)]
@@ -106,7 +108,7 @@ class LayerSolver:
             _native.mttkrp(self.unfoldings[mode], X, Y, 0, out=self.F[mode], ws=self.ws_mttkrp)  # :217
         self._mark(f"m{mode}:mttkrp")
         _native.spd_inverse(self.G, out=(self.Minv, self.rho, self.inv_status), ws=self.ws_inv,
-                            max_ctas=self.max_ctas)  # source/admm.py:52-54
+                            max_ctas=self.max_ctas, minv64=self.Minv64)  # source/admm.py:52-54
         self._mark(f"m{mode}:inverse")
         if self.time_loops:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -114,7 +116,7 @@ class LayerSolver:
         _native.admm_loop_inplace(self.factors[mode], self.duals[mode], self.F[mode], self.Minv, self.rho,
                                   self.inv_status, self.max_iter_admm, self.eps, self.bits, self.qscheme,
                                   self.num_attempts, codes, report=self.reports_dev[mode], ws=self.ws_loop,
-                                  precision=self.solve_precision, max_ctas=self.max_ctas)  # :218
+                                  precision=self.solve_precision, max_ctas=self.max_ctas, minv64=self.Minv64)  # :218
         if self.time_loops:
             ev1.record()
             self.loop_events.append((mode, ev0, ev1))
@@ -176,25 +178,42 @@ class LayerSolver:
             dims = [f.shape[0] for f in self.factors]
             for m in range(self.N):
                 o = self._others[m]
-                _native.check(_native.lib.admmq_permute_myx(_native.ptr(self.unfoldings[m]), dims[m], dims[o[0]],
-                                                            dims[o[1]] if self.N == 3 else 1,
-                                                            _native.ptr(self.permuted[m]),
-                                                            _native.stream_ptr(self.W.device)))
+                _native.call(self.W.device, _native.lib.admmq_permute_myx, _native.ptr(self.unfoldings[m]), dims[m],
+                             dims[o[0]], dims[o[1]] if self.N == 3 else 1, _native.ptr(self.permuted[m]),
+                             _native.stream_ptr(self.W.device))
         for dst, src in zip(self.factors + self.duals, list(factors) + list(duals)):
             dst.copy_(src, non_blocking=True)
             n += dst.numel() * 4
         return n
 
-    def store_to_host(self, factors, duals, factors_q, err_sums):
+    def store_to_host(self, factors, duals, factors_q, err_sums, reports=None):
         """Device -> host copy of the sweep's results into (pinned) host tensors; asynchronous - synchronise
-        the stream before reading them.  Returns the number of bytes copied."""
+        the stream, then call `check_host_reports(reports)`, before reading them.  `reports` is a pinned uint8 tensor
+        of N * sizeof(LoopReport) bytes that receives the loop reports: a ridge system that was not positive definite
+        (loop skipped, factors untouched) or a non-finite loop must not go unnoticed on this path either.  Without
+        `reports` the sweep stays pending and `collect()` must still be called.  Returns the number of bytes copied."""
         n = 0
         for dst, src in zip(list(factors) + list(duals) + list(factors_q), self.factors + self.duals + self.factors_q):
             dst.copy_(src, non_blocking=True)
             n += src.numel() * 4
         err_sums.copy_(self.err_sums, non_blocking=True)
-        self._pending = False
-        return n + self.err_sums.numel() * 8
+        n += self.err_sums.numel() * 8
+        if reports is not None:
+            size = self.reports_dev[0].numel()
+            for m, r in enumerate(self.reports_dev):
+                reports[m * size:(m + 1) * size].copy_(r, non_blocking=True)
+            n += self.N * size
+            self._pending = False
+        return n
+
+    def check_host_reports(self, reports):
+        """Decode the loop reports `store_to_host` copied (after the stream was synchronised): raises
+        torch.linalg.LinAlgError for a non-positive-definite ridge system like `collect()` and the reference's
+        torch.linalg.cholesky; returns the reports."""
+        size = self.reports_dev[0].numel()
+        self.last_reports = [_native.decode_report(bytes(reports[m * size:(m + 1) * size].numpy().tobytes()))
+                             for m in range(self.N)]
+        return self.last_reports
 
     def should_stop(self):
         """Stop rules of scripts/factorize.py:259-263 (3-D) and :303-307 (2-D)."""

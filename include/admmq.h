@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ADMMQ_VERSION 100 /* 0.1.0 */
+#define ADMMQ_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define ADMMQ_API __attribute__((visibility("default")))
@@ -134,11 +134,12 @@ ADMMQ_API int admmq_gemm_nt(const float* A, int lda, int M, const float* B, int 
  * rho = trace(G)/R and Minv = (G + rho I)^-1  (replaces torch.linalg.cholesky at source/admm.py:52-54;
  * the per-iteration cholesky_solve of :56 becomes a product with Minv).  Blocked float64 Cholesky +
  * triangular inverse run by one cooperative kernel; Minv is (R x ldm) float32, ldm = admmq_padded_ld(R).
- * status (device int): 0 or ADMMQ_E_NOT_PD.  rho_out: device float. */
+ * Minv64 (R x ldm float64, or NULL): the same inverse before its rounding to float32 - the operand of the loop's
+ * parity mode (precision 0).  status (device int): 0 or ADMMQ_E_NOT_PD.  rho_out: device float. */
 ADMMQ_API int admmq_padded_ld(int R);
 ADMMQ_API size_t admmq_spd_inverse_workspace_bytes(int R);
-ADMMQ_API int admmq_spd_inverse(const float* G, int R, float* Minv, float* rho_out, int* status, int max_ctas,
-                      void* workspace, size_t workspace_bytes, void* stream);
+ADMMQ_API int admmq_spd_inverse(const float* G, int R, float* Minv, double* Minv64, float* rho_out, int* status,
+                      int max_ctas, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ ADMM inner loop
  * Replaces admm_iteration(H, U, F, G, max_iter, eps, bits, qscheme)  source/admm.py:51-67.
@@ -169,17 +170,22 @@ typedef struct admmq_loop_report {
  *   launches are gang scheduled, a grid that does not fit yet simply waits for SMs to free up.
  *
  * precision (both loop entry points): how the per-iteration ridge product H_ls = (F + rho (H + U)) . Minv is formed
- *   0  float32 FFMA tiles on the CUDA cores (parity mode: what the bit-level comparisons against the reference use)
- *   1  3xTF32 on tcgen05 / tensor memory with TMA-fed operands (throughput mode; factors with < 64 rows fall back to 0)
+ *   0  parity mode: float64 products and sums against the float64 inverse Minv64, rounded once to float32 - the
+ *      correctly rounded solution of the ridge system, which LAPACK's float32 potrs in the reference approximates to
+ *      ~3e-7; what the bit-level comparisons against the reference use (general kernel only, FP64 pipe)
+ *   1  throughput mode: 3xTF32 on tcgen05 / tensor memory with TMA-fed operands; factors with < 64 rows take 2
+ *   2  float32 FFMA on the CUDA cores (tiles; column strips for <= 16 rows; the shared-memory-resident kernel for a
+ *      small factor on a budget of one CTA)
  *
  * Shapes: I * admmq_padded_ld(R) < 2^31 (ADMMQ_E_UNSUPPORTED otherwise; the kernels index elements with 32 bits).
  *
  * The loop alone, for callers that keep (Minv, rho) of a ridge system around (admmq_spd_inverse):
  *   Minv  R x admmq_padded_ld(R) float32, rho / inv_status device scalars written by admmq_spd_inverse
- *         (inv_status may be NULL; a non-zero value makes the loop return it in report->status untouched). */
+ *         (inv_status may be NULL; a non-zero value makes the loop return it in report->status untouched).
+ *   Minv64  the float64 inverse (same shape) - required for precision 0, NULL otherwise. */
 ADMMQ_API size_t admmq_admm_loop_workspace_bytes(int I, int R, int num_attempts);
-ADMMQ_API int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const float* rho,
-                    const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
+ADMMQ_API int admmq_admm_loop(float* H, float* U, const float* F, const float* Minv, const double* Minv64,
+                    const float* rho, const int* inv_status, int I, int R, int max_iter, float eps, int bits, int qscheme,
                     int num_attempts, int precision, int max_ctas, int8_t* codes, admmq_loop_report* report,
                     void* workspace, size_t workspace_bytes, void* stream);
 
@@ -216,8 +222,9 @@ ADMMQ_API int admmq_split_loop(float* H, float* U, const float* W, const float* 
 typedef struct admmq_factorize_params {
   int32_t max_iter_als;     /* --max_iter_als  (5000) */
   int32_t max_iter_admm;    /* --max_iter_admm (1000) */
-  float eps;                /* 1e-8, exit test of admm_iteration  scripts/factorize.py:187 */
-  float tol;                /* 1e-5, stop rule on the error history  :186 */
+  float eps;                /* 1e-8, exit test of admm_iteration  scripts/factorize.py:187 (compared in float32 like the
+                               reference's 0-dim float32 tensors r, s against the Python float) */
+  double tol;               /* 1e-5, stop rule on the error history  :186 - a Python float (double) in the reference */
   int32_t bits, qscheme, num_attempts;
   int32_t solve_precision;  /* see admmq_admm_loop */
   int32_t mttkrp_precision; /* 0 float64-accumulating CUDA-core MTTKRP, 1 3xTF32 tcgen05 */

@@ -1,0 +1,167 @@
+"""Round-2 parity tests on the B200: the whole 999-iteration budget, late sweeps, the large shapes of
+BASELINE configs 4 / 5, early exits.  Everything goes through the C ABI (`libadmmq.so`); the checker is
+`oracle/admm_oracle.py` (CPU restatement, pinned to the unmodified reference) and the reference-made fixtures of
+`tests/golden/long_run.npz` / `solve_divergence.npz` (generator: `oracle/make_golden.py --only long_run,solve_divergence`).
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MSE = "tensor_mseminmax_symmetric"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def long_run():
+    z = np.load(os.path.join(GOLDEN, "long_run.npz"))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from source import _native
+    return _native
+
+
+# ------------------------------------------------------------------ first N over the whole inner budget
+@pytest.mark.parametrize("precision", [0, 1])
+def test_first_n_over_the_whole_inner_budget(long_run, capsys, precision):
+    """north_star: "integer quantized factor codes must be bit-exact for the first N iterations".  From the reference's
+    own (H0, U = 0, F, G) of each mode of sweep 0 of BASELINE config 1, free-running for all 999 inner iterations (one
+    iteration per call, state carried in H and U exactly like one long call), the int8 codes of EVERY iteration are
+    compared with the reference's through a CRC32, and element-wise at every 10th iteration.  N = the first iteration
+    with any differing code.  (a correctly rounded float32-level solve stays bit-identical for hundreds
+    of iterations, an emulated 3xTF32 solve first deviates near iteration 127.)"""
+    from source.admm import admm_iteration
+    z, meta = long_run
+    report = []
+    for m in range(3):
+        H = dev(z[f"sweep0/m{m}/k1/Hin"])
+        U = torch.zeros_like(H)
+        F, G = dev(z[f"sweep0/m{m}/F"]), dev(z[f"sweep0/m{m}/G"])
+        crc_ref = z[f"sweep0/m{m}/crc"]
+        dense = z[f"sweep0/m{m}/codes_every10"]
+        first, agree10 = None, []
+        for k in range(1, 1000):
+            H, U, codes = admm_iteration(H, U, F, G, 2, 1e-8, 4, MSE, return_codes=True, precision=precision)
+            c = codes.cpu().numpy()
+            if first is None and zlib.crc32(c.tobytes()) != int(crc_ref[k - 1]):
+                first = k
+            if k % 10 == 0:
+                agree10.append(float(np.mean(c == dense[k // 10 - 1])))
+        n_str = "none in 999" if first is None else str(first)
+        report.append((m, n_str, min(agree10), agree10[-1]))
+        # bit-exact over the first iterations; high agreement while the trajectories have not separated
+        assert first is None or first > (20 if precision == 0 else 5), (m, first)
+        assert agree10[0] >= 0.999, (m, agree10[:3])
+    with capsys.disabled():
+        for m, n_str, worst, last in report:
+            print(f"\n[first-N/999] precision {precision} mode {m}: first inner iteration with any differing code: {n_str}; "
+                  f"code agreement at every 10th iteration: min {worst:.4f}, at iteration 990 {last:.4f}")
+
+
+# ------------------------------------------------------------------ teacher-forced steps deep into the run
+@pytest.mark.parametrize("precision", [0, 1])
+def test_teacher_forced_steps_in_late_sweeps(long_run, capsys, precision):
+    """from the reference's state at inner iteration k (H, U entering the iteration, F, G of that mode and
+    sweep) one step must land on the reference's codes - sampled at k in {1, 500, 999} of every mode in sweep 1, in a
+    middle sweep and in the LAST sweep of the reference's run to its stop rule (north_star: "final code agreement
+    >= 99.9 %")."""
+    from source.admm import admm_iteration
+    z, meta = long_run
+    worst, n_exact, n = 1.0, 0, 0
+    for tag in ("sweep1", "sweep30", "last"):
+        if f"{tag}/m0/F" not in z.files:
+            continue
+        for m in range(3):
+            F, G = dev(z[f"{tag}/m{m}/F"]), dev(z[f"{tag}/m{m}/G"])
+            for k in meta["keep_k"]:
+                key = f"{tag}/m{m}/k{k}"
+                Hin = dev(z[key + "/Hin_codes"].astype(np.float32) * np.float32(z[key + "/Hin_scale"][0]))
+                U = dev(z[key + "/Uin"])
+                _, _, codes = admm_iteration(Hin, U, F, G, 2, 1e-8, 4, MSE, return_codes=True, precision=precision)
+                agree = float(np.mean(codes.cpu().numpy() == z[key + "/codes"]))
+                worst = min(worst, agree)
+                n += 1
+                n_exact += agree == 1.0
+                assert agree >= 0.999, (tag, m, k, agree)
+    assert n >= 18
+    with capsys.disabled():
+        print(f"\n[teacher-forced late] precision {precision}: {n} steps from sweeps 1 / 30 / last ({meta['last_sweep']}), "
+              f"{n_exact} bit-exact, worst code agreement {worst:.5f}")
+
+
+def test_reference_run_never_left_the_inner_loop_early(long_run):
+    """The reference's own record for config 1: every admm_iteration call of the run to the stop rule ran all 999
+    inner iterations."""
+    z, meta = long_run
+    assert (z["iters_run"] == 999).all() and z["iters_run"].shape == (meta["sweeps"], 3)
+
+
+# ------------------------------------------------------------------ large shapes of configs 4 and 5
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("shape", [(2048, 204, 512), (4096, 1024, 4096)])
+def test_loop_step_at_config4_and_config5_shapes(shape, precision):
+    """Two inner iterations of the 2-D branch (scripts/factorize.py:269-310: G = B^T B, F = W B) at the ResNet-50 1x1
+    shape 2048 x 512 (R = 204) and the Llama shape 4096 x 4096 (R = 1024) against the CPU oracle."""
+    from oracle import admm_oracle as orc
+    from source.admm import admm_iteration
+    I, R, J = shape
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    try:
+        g = torch.Generator().manual_seed(31)
+        Bf = torch.randn(J, R, generator=g)
+        G = Bf.T @ Bf
+        F = torch.randn(I, R, generator=g) * (J ** 0.5) * 0.02
+        H0 = torch.randn(I, R, generator=g)
+        U0 = torch.randn(I, R, generator=g) * 0.1
+        Uo = U0.clone()
+        Ho, Uo, _ = orc.admm_iteration(H0.clone(), Uo, F, G, 3, 1e-8, 4, MSE)
+        Ud = U0.clone().cuda()
+        Hd, _, codes = admm_iteration(H0.cuda(), Ud, F.cuda(), G.cuda(), 3, 1e-8, 4, MSE, precision=precision,
+                                      return_codes=True)
+        from source import admm as A
+        scale = A.last_report.scale
+        codes_o = torch.round(Ho / Ho.abs()[Ho != 0].min()).to(torch.int8)
+        agree = float((codes.cpu() == codes_o).float().mean())
+        assert agree >= 0.999, (shape, precision, agree)
+        assert abs(scale - float(Ho.abs()[Ho != 0].min())) <= 5e-6 * scale
+    finally:
+        torch.set_num_threads(1)
+
+
+# ------------------------------------------------------------------ history against the reference's own spread
+@pytest.mark.parametrize("precision", [0, 1])
+def test_full_budget_history_within_the_references_own_spread(capsys, precision):
+    """BASELINE config 1, max_iter_admm = 1000, two free-running sweeps.  Yardstick (tests/golden/solve_divergence.npz):
+    the UNMODIFIED reference with the output of its ridge solve jittered by +-3e-7 relative per inner iteration -
+    LAPACK's own distance from the exact solution - drifts 3e-4 .. 6e-4 from itself in sweep 0 and 5e-4 .. 3.5e-3 in
+    sweep 1.  Sweep 0 must be within north_star's 1e-3; sweep 1 within twice the reference's own worst drift."""
+    from source.solver import LayerSolver
+    go = np.load(os.path.join(GOLDEN, "outer_loop.npz"))
+    sd = np.load(os.path.join(GOLDEN, "solve_divergence.npz"))
+    meta = json.loads(bytes(sd["meta"]).decode())
+    ref = go["config1_full/loss"]
+    drift = np.array([np.abs(sd[f"{m['name']}/loss"] - ref) / ref for m in meta if abs(m["eps"] - 3e-7) < 1e-12])
+    W = dev(go["config1/W"])
+    init = [dev(go[f"config1_full/init{k}"]) for k in range(3)]
+    s = LayerSolver(W, init, 4, MSE, max_iter_admm=1000, solve_precision=precision)
+    for _ in range(2):
+        s.sweep()
+    rel = np.abs(np.array(s.loss_hist) - ref) / ref
+    with capsys.disabled():
+        print(f"\n[outer-full-2] precision {precision}: rec_error {s.loss_hist} vs reference {ref.tolist()} -> rel {rel}; "
+              f"reference vs itself under +-3e-7 solve jitter: sweep 0 {drift[:, 0].min():.1e}..{drift[:, 0].max():.1e}, "
+              f"sweep 1 {drift[:, 1].min():.1e}..{drift[:, 1].max():.1e}")
+    assert rel[0] <= 1e-3
+    assert rel[1] <= max(1e-3, 2.0 * drift[:, 1].max())

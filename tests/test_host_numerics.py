@@ -189,7 +189,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_native.lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert _native.lib.admmq_version() == 100
+    assert _native.lib.admmq_version() == 200
     assert _native.lib.admmq_padded_ld(134) == 136
     assert _native.lib.admmq_admm_iteration_workspace_bytes(64, 134, 200) > 0
 
