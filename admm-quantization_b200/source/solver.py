@@ -76,6 +76,8 @@ class LayerSolver:
         self.part_events = None    # set to [] to record an event after every kernel group of a sweep (diagnostics)
         self.last_reports = []
         self._pending = False
+        self.snapshot_inputs = False   # diagnostics: keep clones of (H, U, F, G) entering every loop call of a sweep
+        self.snapshots = {}
         if not init_is_random:                                          # :192-201
             fq = [_native.project(f, self.bits, qscheme, self.num_attempts)[0] for f in self.factors]
             self.loss_hist.append(self._error(self.factors))
@@ -110,6 +112,8 @@ class LayerSolver:
         _native.spd_inverse(self.G, out=(self.Minv, self.rho, self.inv_status), ws=self.ws_inv,
                             max_ctas=self.max_ctas, minv64=self.Minv64)  # source/admm.py:52-54
         self._mark(f"m{mode}:inverse")
+        if self.snapshot_inputs:
+            self.snapshots[mode] = (self.factors[mode].clone(), self.duals[mode].clone(), self.F[mode].clone(), self.G.clone())
         if self.time_loops:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()

