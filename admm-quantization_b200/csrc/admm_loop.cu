@@ -56,15 +56,19 @@ struct LoopParams {
   float* MinvHi;           // R x Rp each, made from Minv by the kernel's prologue (tensor-core variant)
   float* MinvLo;
   int tc_bn;               // tile width of the tensor-core variant (multiple of 16, <= TCBN)
-  float* H;
+  float* H;         // the caller's dense I x R arrays: read by the prologue, written back after the last iteration
   float* U;
   const float* F;
+  float* Hp;        // working copies with row pitch Rp (pad columns zero): every array of the loop then shares ONE element
+  float* Up;        // index and is accessed in aligned 16-byte groups
+  float* Fp;
   const float* H2;  // kDiagP1 only: the other block of the two-block splitting (scripts/factorize_lowrank.py:85)
   int I, R, Rp;
   int max_iter;
   float eps;
   int bits, scheme, Nc;
   float neg_zero;  // -0.0f as a run-time value (see search.cuh)
+  int direct_below;  // chunks of at most this many elements per CTA take the direct form of the clip search
   int8_t* codes;
   admmq_loop_report* report;
   const float* rho;       // device scalar: trace(G)/R
@@ -164,7 +168,7 @@ __device__ void gemm_phase(const LoopParams& p, GemmSmem<BM, BN>& gs, unsigned i
           if (i < I && c < R) {
             const float h = add_rn(acc[m][n], gs.red[(ty * TM + m) * BN + tx * TN + n]);
             p.Hls[(size_t)i * Rp + c] = h;
-            const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
+            const float v = sub_rn(h, __ldcg(p.Up + (size_t)i * Rp + c));  // V = H_ls - U (:59)
             p.V[(size_t)i * R + c] = v;
             const unsigned int k = float_key(v);
             kmax = max(kmax, k);
@@ -251,7 +255,7 @@ __device__ void gemm_phase_f64(const LoopParams& p, GemmSmem64<BM, BN>& gs, unsi
           if (i < I && c < R) {
             const float h = (float)(acc[m][n] + gs.red[(ty * TM + m) * BN + tx * TN + n]);
             p.Hls[(size_t)i * Rp + c] = h;
-            const float v = sub_rn(h, __ldcg(p.U + (size_t)i * R + c));  // V = H_ls - U (:59)
+            const float v = sub_rn(h, __ldcg(p.Up + (size_t)i * Rp + c));  // V = H_ls - U (:59)
             p.V[(size_t)i * R + c] = v;
             const unsigned int k = float_key(v);
             kmax = max(kmax, k);
@@ -359,7 +363,7 @@ __device__ void gemm_phase_skinny(const LoopParams& p, SkinnySmem<MI>& ss, unsig
         const int i = o / w, nn = o - i * w;
         const int cc = nn >> 2, q = nn & 3;
         const int n = s0 + nn;
-        const float u = __ldcg(p.U + (size_t)i * R + n);  // requested before the (long) sum over the slices
+        const float u = __ldcg(p.Up + (size_t)i * Rp + n);  // requested before the (long) sum over the slices
         // fixed order: four interleaved partial sums over the k-slices, then ((h0 + h1) + (h2 + h3))
         float h4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const float* rp = &ss.red[(size_t)cc * (MI * 4) + i * 4 + q];
@@ -397,8 +401,8 @@ __device__ void elementwise_phase(const LoopParams& p, float rho, long long e0, 
   const float opr = add_rn(1.0f, rho);
   unsigned int kmax = 0u, kinv = 0u;
   for (long long e = e0 + threadIdx.x; e < e1; e += kThreads) {
-    const float u = __ldcg(p.U + e);
-    const float h = div_rn(sub_rn(add_rn(mul_rn(rho, add_rn(p.H[e], u)), p.F[e]), p.H2[e]), opr);   // :85
+    const float u = __ldcg(p.Up + e);   // I = 1: padded and dense indices coincide
+    const float h = div_rn(sub_rn(add_rn(mul_rn(rho, add_rn(__ldcg(p.Hp + e), u)), p.F[e]), p.H2[e]), opr);   // :85
     p.Hls[e] = h;
     const float v = sub_rn(h, u);                                                                  // :88
     p.V[e] = v;
@@ -434,22 +438,20 @@ __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc
     // epilogue over row-contiguous float4 groups of the tile parked in shared memory (coalesced global traffic)
     const float* tile_h = tc::acc_to_smem<TCBN, kLoopPS>(pipe, smem_tiles);
     using ET = tc::EpiTile<TCBN>;
-    // U is dense (row pitch R, not 16-byte aligned in general) and comes from L2: the loads of up to four groups per
-    // thread are issued before the first use, so the epilogue pays two L2 round trips per tile instead of eight
+    // U comes from L2 (working copy, row pitch Rp: one aligned 16-byte load per group): the loads of up to four groups
+    // per thread are issued before the first use, so the epilogue pays two L2 round trips per tile instead of eight
     constexpr int kIt = (ET::kGroups + kThreads - 1) / kThreads;
     constexpr int kChunk = kIt < 4 ? kIt : 4;
 #pragma unroll
     for (int c0 = 0; c0 < kIt; c0 += kChunk) {
-      float u[kChunk][4];
+      float4 u[kChunk];
 #pragma unroll
       for (int j = 0; j < kChunk; ++j) {
         const int g = (c0 + j) * kThreads + (int)threadIdx.x;
         const int row = g / ET::kGroupsPerRow, c4 = (g - row * ET::kGroupsPerRow) * 4;
         const int i = i0 + row, n = n0 + c4;
-        const unsigned int e = (unsigned int)i * (unsigned int)R + (unsigned int)n;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          u[j][q] = (c0 + j < kIt && g < ET::kGroups && c4 < bn && i < I && n + q < R) ? __ldcg(p.U + e + q) : 0.0f;
+        u[j] = (c0 + j < kIt && g < ET::kGroups && c4 < bn && i < I && n < R)
+                   ? ldcg4(p.Up + (unsigned int)i * (unsigned int)Rp + (unsigned int)n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int j = 0; j < kChunk; ++j) {
@@ -459,12 +461,13 @@ __device__ void gemm_phase_tc(const LoopParams& p, unsigned char* smem_tiles, tc
         if (c0 + j < kIt && g < ET::kGroups && c4 < bn && i < I && n < R) {
           const float4 h4 = *reinterpret_cast<const float4*>(tile_h + ET::offset(row, c4 >> 2));
           const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+          const float uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
           *reinterpret_cast<float4*>(p.Hls + (unsigned int)i * (unsigned int)Rp + (unsigned int)n) = h4;  // n + 3 < Rp: pad columns hold the zero-filled product
           const unsigned int e = (unsigned int)i * (unsigned int)R + (unsigned int)n;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (n + q < R) {
-              const float d = sub_rn(h[q], u[j][q]);  // V = H_ls - U (:59)
+              const float d = sub_rn(h[q], uu[q]);  // V = H_ls - U (:59)
               p.V[e + q] = d;
               const unsigned int k = float_key(d);
               kmax = max(kmax, k);
@@ -565,9 +568,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   const long long e0 = min(N, (long long)blockIdx.x * cs), e1 = min(N, e0 + cs);
   const Levels L = make_levels(p.bits);
   const float qnan = __int_as_float(0x7fc00000);
-  // (row, column) of this thread's first element; advanced by kThreads elements at a time
-  const int row0 = (int)((e0 + t) / R), col0 = (int)((e0 + t) - (long long)row0 * R);
-  const int drow = kThreads / R, dcol = kThreads - drow * R;
+  // P3 and the copies around the loop walk the working arrays (row pitch Rp) in aligned groups of four floats: groups
+  // [g0, g1) belong to this CTA, thread t takes g0 + t, g0 + t + kThreads, ...  Only the last group of a row can hold
+  // pad columns (Rp - R <= 3 of them).
+  const unsigned int gpr = (unsigned int)Rp >> 2;                       // groups per row
+  unsigned int g0, g1;
+  {
+    const unsigned int gtot = (unsigned int)p.I * gpr;
+    const unsigned int gcs = (gtot + gridDim.x - 1) / gridDim.x;
+    g0 = min(gtot, blockIdx.x * gcs);
+    g1 = min(gtot, g0 + gcs);
+  }
+  // (row, column group) of the thread's first group and the step of kThreads groups are recomputed where they are used
+  // (one integer division per phase) instead of being carried in registers through the tensor-core phase
+#define ADMMQ_GROUP_WALK()                                                                                       \
+  const unsigned int grow0 = (g0 + (unsigned int)t) / gpr, gcol0 = (g0 + (unsigned int)t) - grow0 * gpr;         \
+  const unsigned int gdrow = (unsigned int)kThreads / gpr, gdcol = (unsigned int)kThreads - gdrow * gpr;         \
+  const int last_valid = R - 4 * (int)(gpr - 1) /* valid columns of a row's last group (1 .. 4) */
 
   if constexpr (TCBN > 0 && kLoopPS) {  // tf32 hi / lo parts of Minv for the tensor-core product (same split as the A operand)
     const long long n4 = (long long)R * Rp / 4;
@@ -578,16 +595,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
       reinterpret_cast<float4*>(p.MinvLo)[e] = lo;
     }
   }
-  // RHS = F + rho * (H + U) for the first iteration (:56)
-  if constexpr (TCBN != kDiagP1) {
-    int i = row0, n = col0;
-    for (long long e = e0 + t; e < e1; e += kThreads) {
-      p.RHS[(size_t)i * Rp + n] = add_rn(p.F[e], mul_rn(rho, add_rn(p.H[e], p.U[e])));
-      i += drow;
-      n += dcol;
-      if (n >= R) {
-        n -= R;
-        ++i;
+  // working copies of H, U, F and RHS = F + rho * (H + U) for the first iteration (:56); pad columns are zero
+  {
+    ADMMQ_GROUP_WALK();
+    unsigned int row = grow0, cg = gcol0;
+    for (unsigned int g = g0 + (unsigned int)t; g < g1; g += kThreads) {
+      const int nv = (cg == gpr - 1) ? last_valid : 4;
+      const size_t e = (size_t)row * R + 4 * cg;
+      float h[4], u[4], f[4], rhs[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool ok = q < nv;
+        h[q] = ok ? p.H[e + q] : 0.0f;
+        u[q] = ok ? p.U[e + q] : 0.0f;
+        f[q] = (ok && TCBN != kDiagP1) ? p.F[e + q] : 0.0f;
+        rhs[q] = ok ? add_rn(f[q], mul_rn(rho, add_rn(h[q], u[q]))) : 0.0f;
+      }
+      reinterpret_cast<float4*>(p.Hp)[g] = make_float4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<float4*>(p.Up)[g] = make_float4(u[0], u[1], u[2], u[3]);
+      reinterpret_cast<float4*>(p.Hls)[g] = make_float4(0.f, 0.f, 0.f, 0.f);   // its pad columns are read (and ignored) by P3
+      if constexpr (TCBN != kDiagP1) {
+        reinterpret_cast<float4*>(p.Fp)[g] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4*>(p.RHS)[g] = make_float4(rhs[0], rhs[1], rhs[2], rhs[3]);
+      }
+      row += gdrow;
+      cg += gdcol;
+      if (cg >= gpr) {
+        cg -= gpr;
+        ++row;
       }
     }
   }
@@ -625,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
       degenerate = !(absmax > 0.0f) || isinf(absmax);
       if (!degenerate) {
         unsigned long long* cand = p.cand + (size_t)slot * kMaxCandidates;
-        cta_candidate_sums(p.V, e0, e1, absmax, p.Nc, L, p.bits, (double)N, cand, sm.search, p.neg_zero);
+        cta_candidate_sums(p.V, e0, e1, absmax, p.Nc, L, p.bits, (double)N, cand, sm.search, p.neg_zero, kFormAuto, p.direct_below);
         bar.sync();
         lap(1);
         // ---------------- P3
@@ -642,79 +677,91 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     // division, so the codes stay those of rint(fl(x / scale))
     const bool fast_code = p.scheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC && !degenerate;
     const float rcp_scale = fast_code ? div_rn(1.0f, qp.scale) : 0.0f;
-    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f, f3 = 0.0f;
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     {
-      // batches of 4 elements per thread: all 16 loads of a batch are issued before the first dependent use, so the
-      // phase runs at L2 bandwidth instead of one L2 round trip per element
-      constexpr int kBatch = 4;
-      // 32-bit element offsets (check_loop_args: I * Rp < 2^31): one IMAD.WIDE per address instead of 64-bit shifts and
-      // carries - the phase is issue bound
-      int i = row0, n = col0, cnt = 0;
-      unsigned int e = (unsigned int)e0 + (unsigned int)t;
-      const unsigned int e1u = (unsigned int)e1;
-      while (e < e1u) {
-        unsigned int ee[kBatch], hh[kBatch];
-        float hls[kBatch], u[kBatch], hp[kBatch], fv[kBatch];
+      // batches of kBatch groups (4 elements each) per thread: all 16-byte loads of a batch are issued before the first
+      // dependent use, so the phase runs at L2 bandwidth instead of one L2 round trip per element; every array shares
+      // the group index (working copies with row pitch Rp), one IMAD.WIDE per address
+      constexpr int kBatch = 2;
+      ADMMQ_GROUP_WALK();
+      unsigned int row = grow0, cg = gcol0;
+      unsigned int g = g0 + (unsigned int)t;
+      while (g < g1) {
+        unsigned int gg[kBatch], eb[kBatch];
+        int nvb[kBatch];
+        float4 hls4[kBatch], u4[kBatch], hp4[kBatch], fv4[kBatch];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-          ee[b] = e;
-          hh[b] = (unsigned int)i * (unsigned int)Rp + (unsigned int)n;
-          if (e < e1u) {
-            hls[b] = __ldcg(p.Hls + hh[b]);
-            u[b] = __ldcg(p.U + e);
-            hp[b] = p.H[e];
-            fv[b] = p.F[e];
+          gg[b] = g;
+          nvb[b] = (cg == gpr - 1) ? last_valid : 4;
+          eb[b] = row * (unsigned int)R + 4u * cg;   // dense index of the group's first element (codes)
+          if (g < g1) {
+            hls4[b] = ldcg4(p.Hls + 4u * g);
+            u4[b] = ldcg4(p.Up + 4u * g);
+            hp4[b] = ldcg4(p.Hp + 4u * g);
+            if constexpr (TCBN != kDiagP1) fv4[b] = ldcg4(p.Fp + 4u * g);
           }
-          e += kThreads;
-          i += drow;
-          n += dcol;
-          if (n >= R) {
-            n -= R;
-            ++i;
+          g += kThreads;
+          row += gdrow;
+          cg += gdcol;
+          if (cg >= gpr) {
+            cg -= gpr;
+            ++row;
           }
         }
+        float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f, f3 = 0.0f;   // float32 partial sums over at most 4 * kBatch elements, float64 beyond
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-          if (ee[b] < e1u) {
-            const float v = sub_rn(hls[b], u[b]);
-            float code = 0.0f, hq;                                               // H = Q(H_ls - U)   (:59)
-            if (fast_code) {
-              const float tq = fminf(fmaxf(mul_rn(v, rcp_scale), L.fast_lo), L.fast_hi);
-              code = sub_rn(add_rn(tq, 12582912.0f), 12582912.0f);
-              const bool near_tie = !(fabsf(sub_rn(tq, code)) <= L.fast_thr);
-              code = copysignf(code, tq);  // rint keeps the sign of a quotient in (-0.5, 0); the magic sum returns +0
-              if (near_tie) code = code_exact(v, qp.scale, L);
-              hq = mul_rn(code, qp.scale);
-            } else {
-              hq = degenerate ? qnan : quantize_value(v, qp, L, code);
+          if (gg[b] < g1) {
+            const float hls[4] = {hls4[b].x, hls4[b].y, hls4[b].z, hls4[b].w};
+            const float u[4] = {u4[b].x, u4[b].y, u4[b].z, u4[b].w};
+            const float hp[4] = {hp4[b].x, hp4[b].y, hp4[b].z, hp4[b].w};
+            float hq4[4], un4[4], rhs4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float v = sub_rn(hls[q], u[q]);
+              float code = 0.0f, hq;                                               // H = Q(H_ls - U)   (:59)
+              if (fast_code) {
+                const float tq = fminf(fmaxf(mul_rn(v, rcp_scale), L.fast_lo), L.fast_hi);
+                code = sub_rn(add_rn(tq, 12582912.0f), 12582912.0f);
+                const bool near_tie = !(fabsf(sub_rn(tq, code)) <= L.fast_thr);
+                code = copysignf(code, tq);  // rint keeps the sign of a quotient in (-0.5, 0); the magic sum returns +0
+                if (near_tie) code = code_exact(v, qp.scale, L);
+                hq = mul_rn(code, qp.scale);
+              } else {
+                hq = degenerate ? qnan : quantize_value(v, qp, L, code);
+              }
+              const float d1 = sub_rn(hq, hls[q]);
+              float un = add_rn(u[q], d1);                                         // U += H - H_ls     (:60)
+              const float d2 = sub_rn(hq, hp[q]);
+              if (q < nvb[b]) {
+                f0 = fmaf(d1, d1, f0);  // sum (H - H_ls)^2     (:62)
+                f1 = fmaf(hq, hq, f1);  // sum H^2
+                f2 = fmaf(d2, d2, f2);  // sum (H - H_prev)^2   (:63)
+                f3 = fmaf(un, un, f3);  // sum U^2
+                if (p.codes != nullptr) p.codes[eb[b] + q] = (int8_t)code;
+              } else {                  // pad column: stays zero
+                hq = 0.0f;
+                un = 0.0f;
+              }
+              hq4[q] = hq;
+              un4[q] = un;
             }
-            const float d1 = sub_rn(hq, hls[b]);
-            const float un = add_rn(u[b], d1);                                     // U += H - H_ls     (:60)
-            const float d2 = sub_rn(hq, hp[b]);
-            f0 = fmaf(d1, d1, f0);  // sum (H - H_ls)^2     (:62)
-            f1 = fmaf(hq, hq, f1);  // sum H^2
-            f2 = fmaf(d2, d2, f2);  // sum (H - H_prev)^2   (:63)
-            f3 = fmaf(un, un, f3);  // sum U^2
-            p.H[ee[b]] = hq;
-            p.U[ee[b]] = un;
-            if constexpr (TCBN != kDiagP1) p.RHS[hh[b]] = add_rn(fv[b], mul_rn(rho, add_rn(hq, un)));
-            if (p.codes != nullptr) p.codes[ee[b]] = (int8_t)code;
-            if (++cnt == 16) {  // float32 partial sums over at most 16 elements, float64 beyond
-              sums[0] += (double)f0;
-              sums[1] += (double)f1;
-              sums[2] += (double)f2;
-              sums[3] += (double)f3;
-              f0 = f1 = f2 = f3 = 0.0f;
-              cnt = 0;
+            reinterpret_cast<float4*>(p.Hp)[gg[b]] = make_float4(hq4[0], hq4[1], hq4[2], hq4[3]);
+            reinterpret_cast<float4*>(p.Up)[gg[b]] = make_float4(un4[0], un4[1], un4[2], un4[3]);
+            if constexpr (TCBN != kDiagP1) {
+              const float fv[4] = {fv4[b].x, fv4[b].y, fv4[b].z, fv4[b].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rhs4[q] = (q < nvb[b]) ? add_rn(fv[q], mul_rn(rho, add_rn(hq4[q], un4[q]))) : 0.0f;
+              reinterpret_cast<float4*>(p.RHS)[gg[b]] = make_float4(rhs4[0], rhs4[1], rhs4[2], rhs4[3]);
             }
           }
         }
+        sums[0] += (double)f0;
+        sums[1] += (double)f1;
+        sums[2] += (double)f2;
+        sums[3] += (double)f3;
       }
-      sums[0] += (double)f0;
-      sums[1] += (double)f1;
-      sums[2] += (double)f2;
-      sums[3] += (double)f3;
     }
     if (degenerate) {  // uniform: the reference would carry NaN through every remaining iteration
       rep.status |= ADMMQ_ST_NONFINITE;
@@ -740,6 +787,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
       break;
     }
   }
+  // the caller's dense H and U (every CTA copies the groups it updated itself in P3: no barrier needed)
+  if (p.max_iter > 1) {
+    ADMMQ_GROUP_WALK();
+    unsigned int row = grow0, cg = gcol0;
+    for (unsigned int g = g0 + (unsigned int)t; g < g1; g += kThreads) {
+      const int nv = (cg == gpr - 1) ? last_valid : 4;
+      const size_t e = (size_t)row * R + 4 * cg;
+      const float4 h4 = reinterpret_cast<const float4*>(p.Hp)[g], u4 = reinterpret_cast<const float4*>(p.Up)[g];
+      const float h[4] = {h4.x, h4.y, h4.z, h4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < nv) {
+          p.H[e + q] = h[q];
+          p.U[e + q] = u[q];
+        }
+      }
+      row += gdrow;
+      cg += gdcol;
+      if (cg >= gpr) {
+        cg -= gpr;
+        ++row;
+      }
+    }
+  }
+#undef ADMMQ_GROUP_WALK
   rep.phase_ns[3] = global_ns() - t_begin;
   if (blockIdx.x == 0 && t == 0) *p.report = rep;
   if constexpr (TCBN > 0) tc::pipe_teardown(pipe);
@@ -747,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
 
 // ------------------------------------------------------------------------------------ host side
 struct LoopLayout {  // workspace of admmq_admm_loop
-  size_t header, cand, slots, hls, rhs, v, minv_hi, minv_lo, total;
+  size_t header, cand, slots, hls, rhs, v, hp, up, fp, minv_hi, minv_lo, total;
   int Rp;
 };
 
@@ -766,6 +838,9 @@ static LoopLayout loop_layout(int I, int R, int grid, bool with_minv_parts = tru
   l.rhs = take((size_t)I * l.Rp * sizeof(float));
   l.hls = take((size_t)I * l.Rp * sizeof(float));
   l.v = take((size_t)I * R * sizeof(float));
+  l.hp = take((size_t)I * l.Rp * sizeof(float));
+  l.up = take((size_t)I * l.Rp * sizeof(float));
+  l.fp = take(with_minv_parts ? (size_t)I * l.Rp * sizeof(float) : 0);   // not used by the two-block splitting
   l.minv_hi = take(with_minv_parts ? (size_t)R * l.Rp * sizeof(float) : 0);
   l.minv_lo = take(with_minv_parts ? (size_t)R * l.Rp * sizeof(float) : 0);
   l.total = off;
@@ -797,6 +872,12 @@ static IterationLayout iteration_layout(int I, int R, int grid) {
   l.loop_ws = take(loop_layout(I, R, grid).total);
   l.total = off;
   return l;
+}
+
+// experiment knob / default of LoopParams::direct_below
+static int direct_below_default() {
+  static const int v = getenv("ADMMQ_DIRECT_BELOW") ? atoi(getenv("ADMMQ_DIRECT_BELOW")) : 0;
+  return v;
 }
 
 constexpr int kTileFixed = 16;   // cost of a tensor-core tile that does not depend on its width, in columns of width
@@ -888,9 +969,8 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     count_launches(1);
     return ADMMQ_OK;
   }
-  // header + candidate accumulators + RHS (its pad columns must be zero)
+  // header + candidate accumulators (RHS and the working copies, pad columns included, are written by the kernel's prologue)
   ADMMQ_CUDA_OK(cudaMemsetAsync(ws, 0, l.slots, stream));
-  ADMMQ_CUDA_OK(cudaMemsetAsync(ws + l.rhs, 0, (size_t)I * l.Rp * sizeof(float), stream));
   LoopParams p;
   p.H = H;
   p.U = U;
@@ -904,6 +984,7 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.scheme = qscheme;
   p.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
   p.neg_zero = -0.0f;
+  p.direct_below = direct_below_default();
   p.codes = codes;
   p.report = report;
   p.rho = rho;
@@ -914,6 +995,9 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
   p.Hls = (float*)(ws + l.hls);
   p.V = (float*)(ws + l.v);
   p.RHS = (float*)(ws + l.rhs);
+  p.Hp = (float*)(ws + l.hp);
+  p.Up = (float*)(ws + l.up);
+  p.Fp = (float*)(ws + l.fp);
   p.Minv = Minv;
   p.Minv64 = Minv64;
   p.MinvHi = (float*)(ws + l.minv_hi);
@@ -1104,6 +1188,9 @@ extern "C" int admmq_split_loop(float* H, float* U, const float* W, const float*
   p.slots = (double*)(ws + l.slots);
   p.Hls = (float*)(ws + l.hls);
   p.V = (float*)(ws + l.v);
+  p.Hp = (float*)(ws + l.hp);
+  p.Up = (float*)(ws + l.up);
+  p.Fp = nullptr;
   p.RHS = nullptr;
   p.Minv = nullptr;
   void* args[] = {&p};

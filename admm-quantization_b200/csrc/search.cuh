@@ -519,13 +519,15 @@ constexpr int kFormAuto = 0, kFormDirect = 1, kFormThresholds = 2;
 constexpr int kPairsPerElement = 18;
 __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long e0, long long e1, float absmax, int Nc,
                                           const Levels L, int bits, double n_total, unsigned long long* cand_sums,
-                                          SearchSmem& sm, float opaque_neg_zero, int form = kFormAuto) {
+                                          SearchSmem& sm, float opaque_neg_zero, int form = kFormAuto, int direct_below = 0) {
   // Both forms give the same sums up to the last fixed-point unit, so each CTA may take the cheaper one for its chunk: the threshold form
   // pays per (candidate, threshold) pair and stage on top of O(1) per element, the direct form per (element, candidate);
   // with 8 bits (255 thresholds) the direct form wins below ~4.6 k elements per stage, with 4 bits never in practice.
   const long long elems = e1 - e0;
   const long long stages = (elems + kStageCap - 1) / kStageCap;
-  const bool direct_is_cheaper = (long long)((1 << bits) - 1) * stages * kPairsPerElement > elems;
+  // ... and below `direct_below` elements per CTA the fixed costs of the threshold form (zeroing and scanning 8192 bins,
+  // (2^bits - 1) x candidates thresholds however few elements there are) dominate: small factors spread over many CTAs
+  const bool direct_is_cheaper = (long long)((1 << bits) - 1) * stages * kPairsPerElement > elems || elems <= direct_below;
   const bool want_direct = form == kFormDirect || (form == kFormAuto && direct_is_cheaper);
   if (!want_direct && binned_range_ok(absmax))
     cta_candidate_sums_binned(v, e0, e1, absmax, Nc, L, bits, n_total, cand_sums, sm.binned);

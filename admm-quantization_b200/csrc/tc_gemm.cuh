@@ -506,27 +506,34 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
 // Accumulator read-back for the calling warp: TMEM lanes 32 * (warp % 4) .. +31 (= tile rows), BN / 4 columns
 // starting at (warp / 4) * BN / 4.  v[i] = D[row = 32 * (warp % 4) + lane][col0 + i] = (lo.hi + hi.lo) + hi.hi.
 // (kAccStride does not depend on PS.)
+// tcgen05.ld of N consecutive columns of the calling thread's TMEM lane; the registers are valid after tmem_load_wait()
 template <int N>
 __device__ __forceinline__ void tmem_load(unsigned int taddr, unsigned int r[N]) {
   if constexpr (N == 8) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
   } else if constexpr (N == 4) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(taddr)
                  : "memory");
   } else {
     static_assert(N == 16, "unsupported width");
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\ttcgen05.wait::ld.sync.aligned;"
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr)
                  : "memory");
   }
 }
+__device__ __forceinline__ void tmem_load_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Accumulator read-back for the calling warp: TMEM lanes 32 * (warp % 4) .. +31 (= tile rows), BN / 4 columns
+// starting at (warp / 4) * BN / 4.  v[i] = D[row = 32 * (warp % 4) + lane][col0 + i] = (lo.hi + hi.lo) + hi.hi.
+// Both accumulators of a column block are requested before the single wait (one tensor-memory round trip per block
+// instead of two; with BN / 4 <= 16 the whole read-back is one round trip).
 template <int BN>
 __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int& row, int& col0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -540,6 +547,7 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
     unsigned int hh[kW], cr[kW];
     tmem_load<kW>(taddr + (unsigned int)c0, hh);
     tmem_load<kW>(taddr + (unsigned int)(TileSmem<BN, true>::kAccStride + c0), cr);
+    tmem_load_wait();
 #pragma unroll
     for (int i = 0; i < kW; ++i) v[c0 + i] = __uint_as_float(cr[i]) + __uint_as_float(hh[i]);
   }

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _native
+from .shapes import layer_weight_as_tensor, rank_from_reduction_rate  # noqa: F401  (re-exported)
 
 
 def _bytes(n, device):
@@ -257,18 +258,3 @@ class LayerSolver:
     def solve_flops_per_sweep(self):
         it = max(self.max_iter_admm - 1, 0)
         return sum(it * 2 * f.shape[0] * self.R * self.R for f in self.factors)
-
-
-def rank_from_reduction_rate(weight, reduction_rate):
-    """scripts/factorize.py:157-158."""
-    return int(weight.numel() / sum(list(weight.shape)) / reduction_rate)
-
-
-def layer_weight_as_tensor(weight):
-    """Intended reshape of scripts/factorize.py:138-145 / scripts/calibrate.py:178-184:
-    conv (Cout,Cin,kh,kw) -> (Cout,Cin,kh*kw); 1x1 conv -> (Cout,Cin)."""
-    if weight.ndim == 4:
-        if tuple(weight.shape[2:]) == (1, 1):
-            return weight.reshape(weight.shape[0], weight.shape[1])
-        return weight.reshape(weight.shape[0], weight.shape[1], -1)
-    return weight

@@ -10,7 +10,7 @@ import math
 
 import torch
 
-from .solver import layer_weight_as_tensor, rank_from_reduction_rate
+from .shapes import layer_weight_as_tensor, rank_from_reduction_rate
 
 # (name, Cout, Cin, kh, kw) of the 3x3 convolutions factorized for ResNet-18
 # (`get_layer_list('resnet18', downsample=False, conv1=False)`, source/layer_map.py:10-13)
@@ -30,6 +30,44 @@ def resnet18_conv_layers():
 def llama7b_linear_layers():
     """Config 5 shapes: the (out, in) matrices are used as they are."""
     return [("q_proj", 4096, 4096, 1, 1), ("gate_proj", 11008, 4096, 1, 1)]
+
+
+def resnet50_conv_layers():
+    """`get_layer_list('resnet50')` (source/layer_map.py:24-31): conv1..conv3 of every bottleneck of torchvision's
+    ResNet-50 (1x1 reduce, 3x3, 1x1 expand; the first block of a stage reads the previous stage's width)."""
+    blocks = {1: 3, 2: 4, 3: 6, 4: 3}
+    layers, inplanes = [], 64
+    for i in range(1, 5):
+        planes = 64 * 2 ** (i - 1)
+        for j in range(blocks[i]):
+            layers.append((f"layer{i}.{j}.conv1", planes, inplanes, 1, 1))
+            layers.append((f"layer{i}.{j}.conv2", planes, planes, 3, 3))
+            layers.append((f"layer{i}.{j}.conv3", planes * 4, planes, 1, 1))
+            inplanes = planes * 4
+    return layers
+
+
+def llama7b_block_layers(n_blocks=1):
+    """The seven linear maps of a Llama-7B decoder block, (out, in) as stored (notebooks/LlamaADMMQuant.ipynb)."""
+    layers = []
+    for b in range(n_blocks):
+        for name in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            layers.append((f"layers.{b}.self_attn.{name}", 4096, 4096, 1, 1))
+        layers.append((f"layers.{b}.mlp.gate_proj", 11008, 4096, 1, 1))
+        layers.append((f"layers.{b}.mlp.up_proj", 11008, 4096, 1, 1))
+        layers.append((f"layers.{b}.mlp.down_proj", 4096, 11008, 1, 1))
+    return layers
+
+
+def model_layers(model_name):
+    """Layer specs (name, Cout, Cin, kh, kw) of the models the whole-model driver knows."""
+    if model_name == "resnet18":
+        return resnet18_conv_layers()
+    if model_name == "resnet50":
+        return resnet50_conv_layers()
+    if model_name == "llama7b":
+        return llama7b_block_layers(1)
+    raise ValueError(f"Unknown model {model_name}")
 
 
 def resnet50_layer4_layers():

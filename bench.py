@@ -2,16 +2,23 @@
 """Benchmark of the quantization-aware CP factorization hot path (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own functions on the host CPU
+  python bench.py --full [--init parafac-epc]              # the metric's second half: factorize time to the stop rule
 
-Workload (BASELINE.json configs[1]): every 3x3 conv layer of ResNet-18 (16 layers, synthetic
+Default workload (BASELINE.json configs[1]): every 3x3 conv layer of ResNet-18 (16 layers, synthetic
 Kaiming-normal weights, rank from reduction-rate 2.0), ADMM with 4-bit tensor_mseminmax_symmetric
 projection, max_iter_admm = 1000.  One STEP = one outer sweep over all 16 layers = 16 x 3 factor updates
 x 999 inner ADMM iterations (+ Gram, MTTKRP, ridge inverse, re-projection, two reconstruction errors).
 Metric: inner ADMM iterations per second (the unit of work is one inner iteration of one
-factor).  With N GPUs every rank factorizes the whole layer set for its own seed (the reference's
-`--seed` axis: independent solves, no data-path collective) -> weak scaling; the factors are gathered
-once with NCCL after the timed region.
+factor), counted from the kernels' device reports (the inner loop may leave early exactly where the reference's
+does, tests/golden/early_exit.npz).
+
+With N GPUs ONE job is sharded: the independent units (layers; with --workload sweep256 the 256 units
+layer x reduction-rate {1.5, 2, 3, 4} x bits {3, 4, 6, 8} of configs[2]) are assigned to the ranks by
+longest-processing-time-first (source/distributed.py), every rank runs its units concurrently on its own SM budgets,
+there is no data-path collective, and the packed factors are gathered once with one NCCL all_gather after the timed
+region -> "scaling": "strong".  `--seed-replicas` keeps round 1's weak-scaling mode (every rank the whole layer set for
+its own seed) as a labelled extra.
 
 Prints ONE JSON line on rank 0.
 """
@@ -36,6 +43,8 @@ for p in (REPO, PKG):
 QSCHEME = "tensor_mseminmax_symmetric"
 METRIC = "admm_inner_iter_per_s"
 UNIT = "inner ADMM iterations/s"
+SWEEP_RATES = (1.5, 2.0, 3.0, 4.0)
+SWEEP_BITS = (3, 4, 6, 8)
 
 
 def parse_args():
@@ -44,13 +53,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="resnet18", choices=["resnet18", "layer1", "resnet50-l4", "llama7b"])
+    ap.add_argument("--workload", default="resnet18", choices=["resnet18", "layer1", "resnet50-l4", "llama7b", "sweep256"])
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--reduction-rate", type=float, default=2.0)
     ap.add_argument("--max-iter-admm", type=int, default=1000)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0, help="CPU seconds for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager-reference", action="store_true",
+                    help="skip the informative second bar: the reference's own Python run eagerly on this GPU")
     ap.add_argument("--mttkrp-precision", type=int, default=1,
                     help="0 = float64-accumulating CUDA-core MTTKRP, 1 = 3xTF32 tcgen05 MTTKRP (default)")
     ap.add_argument("--concurrency", default="prop", choices=["off", "prop"],
@@ -62,33 +73,66 @@ def parse_args():
                          "fitted to the reported phase times (source/workloads.py), 'prop' = proportional to time x CTAs")
     ap.add_argument("--budgets", default=None,
                     help="experiment knob: comma-separated SM budgets, one per layer in workload order; fixes the budgets "
-                         "(no re-balancing during warm-up)")
+                         "(no re-balancing during warm-up; single GPU)")
     ap.add_argument("--trace-layer", default=None, help="print the per-kernel-group times of this layer's last sweep")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs kept out of the cooperative-grid budgets so that the ordinary kernels between the loops "
                          "(Gram, MTTKRP, projection, errors) never wait for a persistent kernel to finish")
     ap.add_argument("--solve-precision", type=int, default=1,
-                    help="ridge product inside the ADMM loop: 0 = float32 FFMA, 1 = 3xTF32 on tcgen05 (default)")
+                    help="ridge product inside the ADMM loop: 0 = parity mode (float64 product with the float64 inverse), "
+                         "1 = 3xTF32 on tcgen05 (default), 2 = float32 FFMA")
+    ap.add_argument("--seed-replicas", action="store_true",
+                    help="round 1's weak-scaling mode: every rank factorizes the whole unit set for its own seed")
+    ap.add_argument("--round-size", type=int, default=16, help="sweep256: units that run concurrently on one GPU")
+    ap.add_argument("--full", action="store_true",
+                    help="run every unit to the reference's stop rule (scripts/factorize.py:259-263) and report the "
+                         "factorize time (init + ADMM) instead of the per-sweep throughput")
+    ap.add_argument("--init", default="random", choices=["random", "parafac-epc"], help="--full: factor initialisation")
+    ap.add_argument("--max-iter-als", type=int, default=1000, help="--full: sweep budget per unit")
     return ap.parse_args()
 
 
-def workload_layers(name):
+# ------------------------------------------------------------------------------------------ workloads
+def workload_units(args):
+    """[(key, name, cout, cin, kh, kw, reduction_rate, bits)] and a description.  Pure Python (no native library)."""
     from source import workloads as wl
+    name = args.workload
+    if name == "sweep256":
+        units = [(f"{l[0]}/rr{rr}/b{b}", *l, rr, b) for rr in SWEEP_RATES for b in SWEEP_BITS for l in wl.resnet18_conv_layers()]
+        return units, ("ResNet-18 sweep: 16 3x3 conv layers x reduction-rate {1.5,2,3,4} x bits {3,4,6,8} = 256 independent "
+                       "solves (admmq_factorize_batch)")
     if name == "resnet18":
-        return wl.resnet18_conv_layers(), "ResNet-18 all 16 3x3 conv layers"
-    if name == "layer1":
-        return wl.resnet18_conv_layers()[:1], "ResNet-18 layer1.0.conv1 (64x64x3x3)"
-    if name == "resnet50-l4":
-        return wl.resnet50_layer4_layers(), "ResNet-50-shaped layer4 (512x512x3x3, 2048x512 1x1)"
-    return wl.llama7b_linear_layers(), "Llama-7B-shaped linear (4096x4096, 11008x4096)"
+        layers, desc = wl.resnet18_conv_layers(), "ResNet-18 all 16 3x3 conv layers"
+    elif name == "layer1":
+        layers, desc = wl.resnet18_conv_layers()[:1], "ResNet-18 layer1.0.conv1 (64x64x3x3)"
+    elif name == "resnet50-l4":
+        layers, desc = wl.resnet50_layer4_layers(), "ResNet-50-shaped layer4 (512x512x3x3, 2048x512 1x1)"
+    else:
+        layers, desc = wl.llama7b_linear_layers(), "Llama-7B-shaped linear (4096x4096, 11008x4096)"
+    return [(l[0], *l, args.reduction_rate, args.bits) for l in layers], desc
+
+
+def unit_shape(u):
+    _, _, cout, cin, kh, kw, _, _ = u
+    return (cout, cin, kh * kw) if kh * kw > 1 else (cout, cin)
+
+
+def unit_rank(u):
+    from source.shapes import rank_for_shape
+    return rank_for_shape(unit_shape(u), u[6])
 
 
 def config_dict(args, desc, extra=None):
-    cfg = {"workload": f"{desc}, ADMM {args.bits}-bit {QSCHEME}, reduction-rate {args.reduction_rate}, init=random, "
-                       f"max_iter_admm={args.max_iter_admm}; one step = one outer sweep over every layer",
+    if args.workload == "sweep256":
+        what = f"{desc}, {QSCHEME}"
+    else:
+        what = f"{desc}, ADMM {args.bits}-bit {QSCHEME}, reduction-rate {args.reduction_rate}"
+    cfg = {"workload": f"{what}, init=random, max_iter_admm={args.max_iter_admm}; one step = one outer sweep over every unit",
            "bits": args.bits, "qscheme": QSCHEME, "reduction_rate": args.reduction_rate,
            "max_iter_admm": args.max_iter_admm, "num_attempts": 200,
-           "ridge_product": "3xTF32 tcgen05" if getattr(args, "solve_precision", 0) == 1 else "float32 FFMA"}
+           "solve_precision": args.solve_precision, "mttkrp_precision": args.mttkrp_precision,
+           "ridge_product": {0: "float64 product with the float64 inverse (parity mode)", 1: "3xTF32 tcgen05",
+                             2: "float32 FFMA"}[args.solve_precision]}
     if extra:
         cfg.update(extra)
     return cfg
@@ -134,91 +178,119 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_sample(args, layers, budget_s, threads=None):
-    """Times the reference algorithm's inner loop (oracle/admm_oracle.py::admm_iteration = the op-for-op
-    restatement of source/admm.py:51-67 + source/quantization.py:118-144 in torch-CPU float32) on every
-    distinct factor shape of the workload for a few inner iterations, and converts to the workload's
-    inner-iterations/s.  Returns (value, description, threads, seconds spent)."""
-    import torch
+# ------------------------------------------------------------------------------------------ reference arm
+def load_reference():
+    """(admm_iteration callable with the reference's signature, kind).  kind "reference": the UNMODIFIED reference
+    functions (from /root/reference in the dev container, else the byte-compiled build product oracle/_ref made by
+    oracle/build_ref.py); kind "port": the oracle's restatement when neither exists."""
+    try:
+        from oracle.ref_import import import_reference, reference_available
+        if reference_available():
+            ref = import_reference()
+            return ref.admm_iteration, "reference"
+    except Exception as e:  # noqa: BLE001 - fall back to the pinned restatement, and say so in `kind`
+        sys.stderr.write(f"[bench] reference import failed ({e}); timing the oracle port instead\n")
     from oracle import admm_oracle as orc
-    from source import workloads as wl
+
+    def port(H, U, F, G, max_iter, eps, bits, qscheme):
+        h, u, _ = orc.admm_iteration(H, U, F, G, max_iter, eps, bits, qscheme)
+        return h, u
+    return port, "port"
+
+
+def reference_sample(args, units, budget_s, device="cpu", thread_cache=None):
+    """Times the reference's `admm_iteration` (source/admm.py:51-67 incl. the Cholesky set-up and the 200-candidate
+    projection of source/quantization.py:118-144) on every distinct factor shape of the workload for a few inner
+    iterations and converts to the workload's inner-iterations/s.  On the CPU the thread count is chosen PER SHAPE
+    (best of {1, 4, nproc/2, nproc}: small shapes get slower with threads).  Returns a dict."""
+    import torch
+    admm_iteration, kind = load_reference()
     nproc = os.cpu_count() or 1
     shapes = {}
-    for name, cout, cin, kh, kw in layers:
-        dims = (cout, cin, kh * kw) if kh * kw > 1 else (cout, cin)
-        numel = 1
-        for d in dims:
-            numel *= d
-        rank = int(numel / sum(dims) / args.reduction_rate)
+    for u in units:
+        dims, rank, bits = unit_shape(u), unit_rank(u), u[7]
         for m, d in enumerate(dims):
             others = [x for k, x in enumerate(dims) if k != m]
-            key = (d, rank)
-            shapes.setdefault(key, [0, others])[0] += 1
+            shapes.setdefault((d, rank, bits), [0, others])[0] += 1
     g = torch.Generator().manual_seed(7)
 
-    def one(I, R, others, iters):
-        mats = [torch.randn(o, R, generator=g) for o in others]
-        G = orc.gram_hadamard(mats)
+    def one(I, R, bits, others, iters):
+        mats = [torch.randn(o, R, generator=g).to(device) for o in others]
+        G = mats[0].T @ mats[0]
+        for M in mats[1:]:
+            G = G * (M.T @ M)
         scale = 1.0
         for o in others:
             scale *= o
-        F = torch.randn(I, R, generator=g) * scale ** 0.5
-        H = torch.randn(I, R, generator=g)
-        U = torch.zeros(I, R)
+        F = (torch.randn(I, R, generator=g) * scale ** 0.5).to(device)
+        H = torch.randn(I, R, generator=g).to(device)
+        U = torch.zeros(I, R, device=device)
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        orc.admm_iteration(H, U, F, G, iters + 1, 1e-8, args.bits, QSCHEME)
+        admm_iteration(H, U, F, G, iters + 1, 1e-8, bits, QSCHEME)
+        if device != "cpu":
+            torch.cuda.synchronize()
         return (time.perf_counter() - t0) / iters
 
-    # thread count: the 200-pass projection is a chain of small elementwise ops; pick what is fastest here
-    if threads is None:
-        big = max(shapes, key=lambda k: k[0] * k[1])
-        best = None
-        for t in sorted({1, max(1, nproc // 2), nproc}):
-            torch.set_num_threads(t)
-            one(big[0], big[1], shapes[big][1], 1)
-            dt = one(big[0], big[1], shapes[big][1], 1)
-            if best is None or dt < best[1]:
-                best = (t, dt)
-        threads = best[0]
-    torch.set_num_threads(threads)
+    thread_cache = {} if thread_cache is None else thread_cache
     t_start = time.perf_counter()
-    total_s_per_sweep = 0.0
-    sampled = 0
-    share = budget_s / len(shapes)          # equal CPU time per distinct shape
-    for (I, R), (count, others) in sorted(shapes.items()):
-        probe = one(I, R, others, 2)
+    total_s_per_sweep, sampled = 0.0, 0
+    share = budget_s / len(shapes)          # equal time per distinct shape
+    used_threads = set()
+    for (I, R, bits), (count, others) in sorted(shapes.items()):
+        if device == "cpu":
+            if (I, R, bits) not in thread_cache:
+                best = None
+                for t in sorted({1, min(4, nproc), max(1, nproc // 2), nproc}):
+                    torch.set_num_threads(t)
+                    dt = min(one(I, R, bits, others, 1), one(I, R, bits, others, 1)) if I * R < 200000 else one(I, R, bits, others, 1)
+                    if best is None or dt < best[1]:
+                        best = (t, dt)
+                thread_cache[(I, R, bits)] = best
+            threads, probe = thread_cache[(I, R, bits)]
+            torch.set_num_threads(threads)
+            used_threads.add(threads)
+        else:
+            probe = one(I, R, bits, others, 1)
+            probe = one(I, R, bits, others, 2)
         iters = int(min(60, max(2, round((share - 2 * probe) / probe))))
-        per_iter = one(I, R, others, iters)
-        sampled += iters + 2
+        per_iter = one(I, R, bits, others, iters)
+        sampled += iters
         total_s_per_sweep += count * (args.max_iter_admm - 1) * per_iter
+    if device == "cpu":
+        torch.set_num_threads(1)
     inner_per_sweep = sum(c for c, _ in shapes.values()) * (args.max_iter_admm - 1)
-    spent = time.perf_counter() - t_start
-    desc = (f"oracle admm_iteration (torch-CPU float32, {threads} threads): {sampled} inner iterations spread over the "
-            f"{len(shapes)} distinct factor shapes of the workload (Cholesky set-up included), extrapolated to one sweep "
-            f"= {inner_per_sweep} inner iterations; Gram/MTTKRP/error terms (<1 % of CPU time) not included")
-    return inner_per_sweep / total_s_per_sweep, desc, threads, spent
+    where = (f"torch-CPU float32, threads chosen per shape from {{1, 4, {max(1, nproc // 2)}, {nproc}}}, used {sorted(used_threads)}"
+             if device == "cpu" else "eager PyTorch on the B200 (stock ATen / cuBLAS / cuSOLVER kernels, ~2000 launches and 3 host "
+                                     "syncs per inner iteration)")
+    what = "the reference's own source/admm.py::admm_iteration" if kind == "reference" else "oracle admm_iteration (port)"
+    return {"value": inner_per_sweep / total_s_per_sweep, "kind": kind, "cores": max(used_threads) if used_threads else 0,
+            "sample": (f"{what} ({where}): {sampled} timed inner iterations spread over the {len(shapes)} distinct factor "
+                       f"shapes of the workload (Cholesky set-up included), extrapolated to one sweep = {inner_per_sweep} "
+                       f"inner iterations; Gram/MTTKRP/error terms (<1 % of the time) not included"),
+            "seconds": round(time.perf_counter() - t_start, 1), "threads_per_shape": {f"{k[0]}x{k[1]}@{k[2]}b": v[0] for k, v in thread_cache.items()}}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    layers, desc = workload_layers(args.workload)
-    vals, threads = [], None
+    units, desc = workload_units(args)
+    vals, cache, res = [], {}, None
     t0 = time.perf_counter()
-    sample = ""
+    per_step = 4.0 if args.workload != "sweep256" else 12.0
     for i in range(args.warmup + args.steps):
-        v, sample, threads, _ = cpu_reference_sample(args, layers, 6.0, threads)
+        res = reference_sample(args, units, per_step, "cpu", cache)
         if i >= args.warmup:
-            vals.append(v)
+            vals.append(res["value"])
     value = len(vals) / sum(1.0 / v for v in vals)
-    inner = sum(3 if l[3] * l[4] > 1 else 2 for l in layers) * (args.max_iter_admm - 1)
+    inner = sum(len(unit_shape(u)) for u in units) * (args.max_iter_admm - 1)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": inner / value * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": inner / value * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, desc),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "host_cores": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
+                             "host_cores": os.cpu_count(), "threads_per_shape": res["threads_per_shape"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
             "note": "ms_per_step is the extrapolated CPU time of one full sweep; each timed step ran a bounded sample"}
@@ -243,56 +315,124 @@ def allocate_ctas(costs, sm_count, min_ctas):
 
 
 # ------------------------------------------------------------------------------------------ native arm
+class Rank:
+    """Process-group plumbing of one rank."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            # bring the communicator up before anything is timed (lazy connection set-up cost 0.2 - 1.3 s in round 1)
+            warm = torch.zeros(8, device=self.dev)
+            dist.all_reduce(warm)
+            out = torch.empty(8 * self.world, device=self.dev)
+            dist.all_gather_into_tensor(out, warm)
+            torch.cuda.synchronize()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, value, op):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def gather_factors(self, tensors):
+        """The job's only collective: ONE all_gather of the packed factors (padded to the largest rank's payload),
+        timed on the device.  Returns (ms, bytes of this rank's payload)."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return None, 0
+        flat = torch.cat([t.reshape(-1) for t in tensors]) if tensors else torch.zeros(1, device=self.dev)
+        width = int(self.reduce(flat.numel(), "MAX"))
+        padded = torch.zeros(width, dtype=torch.float32, device=self.dev)
+        padded[:flat.numel()] = flat
+        out = torch.empty(width * self.world, dtype=torch.float32, device=self.dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(out, padded)
+        e1.record()
+        torch.cuda.synchronize()
+        return self.reduce(e0.elapsed_time(e1), "MAX"), flat.numel() * 4
+
+
+def shard(args, units, rk):
+    """Owner rank of every unit: LPT over the cost model (source/distributed.py); seed replicas: everything everywhere."""
+    if args.seed_replicas or rk.world == 1:
+        return [rk.rank] * len(units)
+    from source.distributed import shard_units
+    return shard_units([{"shape": unit_shape(u), "rank": unit_rank(u)} for u in units], rk.world)
+
+
 def run_native(args):
     import torch
-    import torch.distributed as dist
     from source import _native, workloads as wl
     from source.solver import LayerSolver
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the solver has no CPU path (use --impl reference for the CPU arm)")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    layers, desc = workload_layers(args.workload)
-    # weak scaling: every rank factorizes the whole layer set for its own seed (reference: one run per --seed)
-    problems = wl.build_problems(layers, args.reduction_rate, weight_seed=42, init_seed=42 + rank)
-    host = []   # pinned host state for the end-to-end leg
-    solvers = []
+    rk = Rank()
+    rank, world, dev = rk.rank, rk.world, rk.dev
+    units, desc = workload_units(args)
+    owner = shard(args, units, rk)
+    mine = [u for u, o in zip(units, owner) if o == rank]
+    init_seed = 42 + (rank if args.seed_replicas else 0)
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    budgets = allocate_ctas([wl.solve_cost(W.shape, rnk) for _, W, rnk, _ in problems], sm_count - args.reserve_sms,
-                            args.min_ctas) \
-        if args.concurrency == "prop" else [0] * len(problems)
-    if args.budgets and args.concurrency == "prop":
+    if args.workload == "sweep256":
+        return run_sweep256(args, rk, units, owner, mine, desc, sm_count)
+    if args.full:
+        return run_full(args, rk, units, owner, mine, desc, sm_count)
+
+    problems = []
+    for key, name, cout, cin, kh, kw, rr, bits in mine:
+        W = wl.layer_weight_as_tensor(wl.synthetic_weight(cout, cin, kh, kw, 42, name)).contiguous()
+        rnk = wl.rank_from_reduction_rate(W, rr)
+        problems.append((key, W, rnk, wl.random_init(W.shape, rnk, init_seed), bits))
+    host, solvers = [], []   # pinned host state for the end-to-end leg
+    concurrent = args.concurrency == "prop" and len(problems) > 0
+    budgets = allocate_ctas([wl.solve_cost(W.shape, rnk) for _, W, rnk, _, _ in problems], sm_count - args.reserve_sms,
+                            args.min_ctas) if concurrent else [0] * len(problems)
+    if args.budgets and concurrent and world == 1:
         budgets = [int(x) for x in args.budgets.split(",")]
         assert len(budgets) == len(problems) and sum(budgets) <= sm_count, (len(problems), sum(budgets), sm_count)
-    streams = [torch.cuda.Stream(device=dev) for _ in problems] if args.concurrency == "prop" else None
-    for (name, W, rnk, init), g in zip(problems, budgets):
-        solvers.append(LayerSolver(W.to(dev), [f.to(dev) for f in init], args.bits, QSCHEME,
+    streams = [torch.cuda.Stream(device=dev) for _ in problems] if concurrent else None
+    rep_bytes = _native.new_report(dev).numel()
+    for (key, W, rnk, init, bits), g in zip(problems, budgets):
+        solvers.append(LayerSolver(W.to(dev), [f.to(dev) for f in init], bits, QSCHEME,
                                    max_iter_admm=args.max_iter_admm, mttkrp_precision=args.mttkrp_precision,
                                    solve_precision=args.solve_precision, time_loops=True, max_ctas=g))
         host.append({"W": W.pin_memory(), "factors": [f.clone().pin_memory() for f in init],
                      "duals": [torch.zeros_like(f).pin_memory() for f in init],
                      "factors_q": [torch.zeros_like(f).pin_memory() for f in init],
-                     "err": torch.zeros(2, 2, dtype=torch.float64).pin_memory()})
-    for (name, _, _, _), s in zip(problems, solvers):
-        if args.trace_layer and name == args.trace_layer:
+                     "err": torch.zeros(2, 2, dtype=torch.float64).pin_memory(),
+                     "reports": torch.zeros(W.ndim * rep_bytes, dtype=torch.uint8).pin_memory()})
+    for (key, _, _, _, _), s in zip(problems, solvers):
+        if args.trace_layer and key == args.trace_layer:
             s.part_events = []
     inner_per_step = sum(s.inner_iterations_per_sweep() for s in solvers)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     sweep_events = []
 
     def enqueue_all(prepare=None):
-        """One sweep of every layer.  Concurrent mode: every layer on its own stream (fork from / join into the
+        """One sweep of every local unit.  Concurrent mode: every unit on its own stream (fork from / join into the
         current stream with events, so CUDA events recorded on the current stream bracket all of the work)."""
         if streams is None:
             for k, s in enumerate(solvers):
@@ -320,8 +460,8 @@ def run_native(args):
         return [s.collect() for s in solvers]
 
     def step_e2e():
-        """The same sweep through the public solver API starting from HOST buffers: weights, factors and
-        duals go host->device (pinned), results (factors, duals, re-projected factors, error sums) come back."""
+        """The same sweep through the public solver API starting from HOST buffers: weights, factors and duals go
+        host->device (pinned), results (factors, duals, re-projected factors, error sums, loop reports) come back."""
         moved = [0, 0]
 
         def h2d_copy(k):
@@ -329,8 +469,10 @@ def run_native(args):
 
         enqueue_all(prepare=h2d_copy)
         for s, h in zip(solvers, host):   # results come back on the (joined) current stream
-            moved[1] += s.store_to_host(h["factors"], h["duals"], h["factors_q"], h["err"])
+            moved[1] += s.store_to_host(h["factors"], h["duals"], h["factors_q"], h["err"], h["reports"])
         torch.cuda.synchronize()
+        for s, h in zip(solvers, host):   # a non-PD ridge system raises here like the reference's cholesky
+            s.check_host_reports(h["reports"])
         return moved[0], moved[1]
 
     tried = []   # (step ms, budgets) of every warm-up step: the timed steps run with the best MEASURED budgets
@@ -344,8 +486,8 @@ def run_native(args):
         w1.record()
         torch.cuda.synchronize()
         tried.append((w0.elapsed_time(w1), [s.max_ctas for s in solvers]))
-        if streams is not None and w < args.warmup - 1 and not args.budgets:
-            # re-balance the SM budgets from what was just measured: per layer the sweep time and, per factor, the
+        if streams is not None and w < args.warmup - 1 and not args.budgets and len(solvers) > 1:
+            # re-balance the SM budgets from what was just measured: per unit the sweep time and, per factor, the
             # phase times its persistent kernel reported, through the wave model of source/workloads.py
             fitted = []
             for (a, b), s in zip(sweep_events, solvers):
@@ -366,17 +508,18 @@ def run_native(args):
     budgets[:] = [s.max_ctas for s in solvers]
     for s in solvers:
         s.loop_events.clear()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(rk.local)
     if rank == 0:
         sampler.start()
     launches0 = _native.launch_count()
     step_ms = []
-    # inner iterations actually executed in the timed steps, per layer and factor, from the kernels' device reports (the
-    # loop may leave early: r < eps and s < eps, source/admm.py:64-65) - the metric counts these, not the nominal 999
+    # inner iterations actually executed in the timed steps, per unit and factor, from the kernels' device reports (the
+    # loop leaves early where the reference's own exit test fires, source/admm.py:64-65) - the metric counts these
     done = [[0] * s.N for s in solvers]
-    early = nonfinite = 0
-    barrier()
-    for _ in range(args.steps):
+    early, nonfinite = [], 0
+    errs = []
+    rk.barrier()
+    for stp in range(args.steps):
         flush.fill_(1)                      # L2 flush between timed steps (outside the event pair)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -387,30 +530,29 @@ def run_native(args):
         for k, sv in enumerate(solvers):
             for m, r in enumerate(sv.last_reports):
                 done[k][m] += int(r.iterations)
-                early += int(r.iterations) < sv.max_iter_admm - 1
+                if int(r.iterations) < sv.max_iter_admm - 1:
+                    early.append({"unit": problems[k][0], "mode": m, "step": stp, "sweep": len(sv.loss_hist) - 1,
+                                  "iterations": int(r.iterations), "r": float(r.r), "s": float(r.s), "rows": sv.factors[m].shape[0]})
                 nonfinite += bool(int(r.status) & _native.ST_NONFINITE)
-    barrier()
+    rk.barrier()
     done_total = sum(sum(d) for d in done)
     launches = _native.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    done_all = torch.tensor([done_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(done_all, op=dist.ReduceOp.SUM)
-    value = float(done_all.item()) / (total_ms / 1e3)
+    total_ms = rk.reduce(sum(step_ms), "MAX")
+    done_all = rk.reduce(done_total, "SUM")
+    value = done_all / (total_ms / 1e3)
 
     # ---- the dominant kernel (persistent ADMM loop), timed with CUDA events on its own stream.  In concurrent mode a
     # launch holds only its share g of the SMs, so its duration is weighted by g / SMs: the sum is the time the whole
     # GPU would have been busy with these launches (equals the plain sum when every launch uses every SM).
-    loop_ms, loop_gpu_ms, per_layer = 0.0, 0.0, {}
-    for k, ((name, _, _, _), s) in enumerate(zip(problems, solvers)):
+    loop_ms, loop_gpu_ms, per_layer, sweep_ms = 0.0, 0.0, {}, {}
+    for k, ((key, _, _, _, _), s) in enumerate(zip(problems, solvers)):
         ms = sum(a.elapsed_time(b) for _, a, b in s.loop_events)
         loop_ms += ms
         loop_gpu_ms += ms * ((s.max_ctas or sm_count) / sm_count)
-        per_layer[name] = round(sum(done[k]) / (ms / 1e3), 1)
+        per_layer[key] = round(sum(done[k]) / (ms / 1e3), 1) if ms > 0 else None
+    for (key, _, _, _, _), ev in zip(problems, sweep_events):
+        sweep_ms[key] = round(ev[0].elapsed_time(ev[1]), 1)
     n_loop = sum(len(s.loop_events) for s in solvers)
     # algorithmic work of the iterations that ran
     alg_bytes = sum(it * (16 * f.shape[0] * s.R + 4 * s.R * s.R) for s, d in zip(solvers, done) for f, it in zip(s.factors, d))
@@ -428,36 +570,40 @@ def run_native(args):
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_achieved = alg_bytes / (loop_gpu_ms / 1e3) / 1e9
     # The kernel's dominant phase is the ridge product H_ls = RHS . Minv (2 I R^2 flop per inner iteration, float32
     # accuracy through three TF32 tensor-core products per term), so it is reported against the tensor roofline:
     # dense TF32 = bf16 / 2, 3xTF32 = TF32 / 3, from the MEASURED sustained bf16 rate (the kernel runs inside a long step).
     bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62)))
     tensor_peak = bf16 / 2.0 / 3.0
-    achieved = flops / (loop_gpu_ms / 1e3) / 1e12
-    roofline = {"kernel": "k_admm_loop (persistent ADMM inner loop: ridge product on tcgen05 + clip search + dual update)",
-                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32) / 3 (3xTF32 split), fp32-equivalent" if peaks
-                                else "fallback: 0.62 x 2250 bf16 TFLOP/s / 6"),
-                "traffic": (traffic or {}).get("bytes") if isinstance(traffic, dict) else traffic,
-                "traffic_note": (traffic or {}).get("note") if isinstance(traffic, dict) else None, "launches": n_loop, "avg_launch_ms": loop_ms / max(n_loop, 1),
-                "gpu_share_weighted_ms": loop_gpu_ms, "share_of_step": loop_gpu_ms / sum(step_ms),
-                "algorithmic_flops_per_launch": flops / max(n_loop, 1),
-                "algorithmic_bytes_per_launch": alg_bytes / max(n_loop, 1),
-                "note": "achieved = 2 I R^2 flop per inner iteration (fp32-equivalent; the hardware executes 3x that in "
-                        "TF32) / (launch duration x the launch's share of the SMs); the launch also contains the clip "
-                        "search, the dual update and three device-wide barriers per iteration, so frac is a lower bound "
-                        "for the product itself (tools/microbench/tcprof.cu times the product alone)",
-                "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak, "frac": hbm_achieved / hbm_peak,
-                        "note": "state is L2-resident by design (ncu: see traffic), HBM is not the binding resource"},
-                "clip_search": {"candidates_x_elements_per_s": evals / (loop_gpu_ms / 1e3),
-                                "note": "threshold form: O(1) work per element + (2^bits - 1) x candidates thresholds per CTA"}}
+    roofline = None
+    if loop_gpu_ms > 0:
+        achieved = flops / (loop_gpu_ms / 1e3) / 1e12
+        hbm_achieved = alg_bytes / (loop_gpu_ms / 1e3) / 1e9
+        roofline = {"kernel": "k_admm_loop (persistent ADMM inner loop: ridge product on tcgen05 + clip search + dual update)",
+                    "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32) / 3 (3xTF32 split), fp32-equivalent" if peaks
+                                    else "fallback: 0.62 x 2250 bf16 TFLOP/s / 6"),
+                    "traffic": (traffic or {}).get("bytes") if isinstance(traffic, dict) else traffic,
+                    "traffic_note": (traffic or {}).get("note") if isinstance(traffic, dict) else None,
+                    "launches": n_loop, "avg_launch_ms": loop_ms / max(n_loop, 1),
+                    "gpu_share_weighted_ms": loop_gpu_ms, "share_of_step": loop_gpu_ms / sum(step_ms),
+                    "algorithmic_flops_per_launch": flops / max(n_loop, 1),
+                    "algorithmic_bytes_per_launch": alg_bytes / max(n_loop, 1),
+                    "rank": 0,
+                    "note": "rank 0's launches; achieved = 2 I R^2 flop per inner iteration (fp32-equivalent; the hardware "
+                            "executes 3x that in TF32) / (launch duration x the launch's share of the SMs); the launch also "
+                            "contains the clip search, the dual update and three device-wide barriers per iteration, so frac "
+                            "is a lower bound for the product itself (tools/microbench/tcprof.cu times the product alone)",
+                    "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak, "frac": hbm_achieved / hbm_peak,
+                            "note": "state is L2-resident by design (ncu: see traffic), HBM is not the binding resource"},
+                    "clip_search": {"candidates_x_elements_per_s": evals / (loop_gpu_ms / 1e3),
+                                    "note": "threshold form: O(1) work per element + (2^bits - 1) x candidates thresholds per CTA"}}
 
     # ---- end to end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
         step_e2e()
-        barrier()
+        rk.barrier()
         t_e2e = []
         h2d = d2h = 0
         done_e2e = 0
@@ -469,57 +615,281 @@ def run_native(args):
             e1.record()
             torch.cuda.synchronize()
             t_e2e.append(e0.elapsed_time(e1))
-            done_e2e += sum(int(_native.read_report(r).iterations) for sv in solvers for r in sv.reports_dev)
-        barrier()
-        tot = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
-        cnt = torch.tensor([done_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(cnt.item()) / (float(tot.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(tot.item()) / args.steps}
+            done_e2e += sum(int(r.iterations) for sv in solvers for r in sv.last_reports)
+        rk.barrier()
+        tot = rk.reduce(sum(t_e2e), "MAX")
+        cnt = rk.reduce(done_e2e, "SUM")
+        e2e = {"value": cnt / (tot / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(rk.reduce(h2d, "SUM")),
+               "d2h_bytes_per_step": int(rk.reduce(d2h, "SUM")), "ms_per_step": tot / args.steps}
 
-    # ---- final factor gather over NCCL (once per job, outside the timed region)
-    gather_ms = None
-    if world > 1:
-        packed = torch.cat([f.reshape(-1) for s in solvers for f in s.factors])
-        out = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dist.gather(packed, out, dst=0)
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - t0) * 1e3
-
-    cpu = None
+    # ---- the job's only collective: final factor gather over NCCL (once per job, outside the timed region)
+    gather_ms, gather_bytes = rk.gather_factors([f for s in solvers for f in s.factors])
+    per_rank = rk.gather_objects({"rank": rank, "units": [p[0] for p in problems], "ctas": dict(zip([p[0] for p in problems], budgets)),
+                                  "ms_per_step": sum(step_ms) / args.steps, "inner_iterations": done_total / args.steps,
+                                  "sweep_ms": sweep_ms, "per_unit_inner_iter_per_s": per_layer, "early": early,
+                                  "nonfinite": nonfinite, "launches": launches, "gather_bytes": gather_bytes,
+                                  "rec_error": {p[0]: round(e[0], 6) for p, e in zip(problems, errs)}})
+    cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sample, threads, spent = cpu_reference_sample(args, layers, args.cpu_budget_s)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-               "host_cores": os.cpu_count(), "seconds": round(spent, 1)}
+        r = reference_sample(args, units, args.cpu_budget_s, "cpu")
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "host_cores": os.cpu_count(), "seconds": r["seconds"], "threads_per_shape": r["threads_per_shape"]}
+    if rank == 0 and world == 1 and not args.no_eager_reference:
+        try:
+            r = reference_sample(args, units, 6.0, "cuda")
+            eager = {"value": r["value"], "unit": UNIT, "kind": r["kind"], "sample": r["sample"], "seconds": r["seconds"]}
+        except Exception as e:  # noqa: BLE001 - informative bar only
+            eager = {"unavailable": str(e)[:200]}
     if rank == 0 and args.trace_layer:
-        for (name, _, _, _), s in zip(problems, solvers):
+        for (key, _, _, _, _), s in zip(problems, solvers):
             if s.part_events:
-                sys.stderr.write(f"[trace {name}] " + ", ".join(f"{k} {v:.1f}" for k, v in s.part_times_ms()) + "\n")
+                sys.stderr.write(f"[trace {key}] " + ", ".join(f"{k} {v:.1f}" for k, v in s.part_times_ms()) + "\n")
     if rank == 0:
+        all_early = [e for pr in per_rank for e in pr["early"]]
+        n_loops = args.steps * sum(len(unit_shape(u)) for u in units) * (world if args.seed_replicas else 1)
+        par = (f"{world} independent seeds, one per GPU" if args.seed_replicas else
+               f"one job, {len(units)} units sharded over {world} GPU(s) by LPT on the cost model") + "; no data-path collective"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak" if args.seed_replicas else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, desc, {"l2": "flushed between timed steps (256 MiB write)",
                                                    "concurrency": args.concurrency,
-                                                   "ctas_per_layer": dict(zip([p[0] for p in problems], budgets)),
-                                                   "parallelism": f"{world} independent seeds, one per GPU; no data-path collective",
-                                                   "inner_iterations_per_step_per_gpu": done_total / args.steps,
-                                                   "inner_iterations_nominal_per_step": inner_per_step,
-                                                   "loops_left_early": f"{early} of {args.steps * sum(sv.N for sv in solvers)} "
-                                                                       "(exit test r < eps and s < eps, eps = 1e-8)",
-                                                   "loops_nonfinite": nonfinite}),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "per_layer_inner_iter_per_s": per_layer,
-                "per_layer_sweep_ms_last_step": {p[0]: round(a.elapsed_time(b), 1) for p, (a, b) in zip(problems, sweep_events)},
-                "rec_error_last_step": {n[0]: round(e[0], 6) for n, e in zip(problems, errs)},
-                "factor_gather_ms": gather_ms}
+                                                   "units_per_rank": [len(pr["units"]) for pr in per_rank],
+                                                   "ctas_per_unit": {k: v for pr in per_rank for k, v in pr["ctas"].items()},
+                                                   "parallelism": par,
+                                                   "inner_iterations_per_step": done_all / args.steps,
+                                                   "inner_iterations_nominal_per_step": inner_per_step if world == 1 else
+                                                   sum(len(unit_shape(u)) for u in units) * (args.max_iter_admm - 1) * (world if args.seed_replicas else 1),
+                                                   "loops_left_early": f"{len(all_early)} of {n_loops} (exit test r < eps and s < eps, "
+                                                                       "eps = 1e-8: source/admm.py:62-65; the unmodified reference "
+                                                                       "leaves at the same iteration from the same state, "
+                                                                       "tests/golden/early_exit.npz)",
+                                                   "loops_nonfinite": sum(pr["nonfinite"] for pr in per_rank)}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": sum(pr["launches"] for pr in per_rank), "roofline": roofline,
+                "cpu_baseline": cpu, "reference_eager_b200": eager,
+                "per_unit_inner_iter_per_s": {k: v for pr in per_rank for k, v in pr["per_unit_inner_iter_per_s"].items()},
+                "per_unit_sweep_ms_last_step": {k: v for pr in per_rank for k, v in pr["sweep_ms"].items()},
+                "per_rank_ms_per_step": [round(pr["ms_per_step"], 2) for pr in per_rank],
+                "rec_error_last_step": {k: v for pr in per_rank for k, v in pr["rec_error"].items()},
+                "early_exits": all_early[:64],
+                "factor_gather_ms": gather_ms, "factor_gather_bytes_per_rank": [pr["gather_bytes"] for pr in per_rank]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        rk.dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ config 3: 256 units
+def run_sweep256(args, rk, units, owner, mine, desc, sm_count):
+    """BASELINE configs[2]: layer x reduction-rate x bits as independent solves through admmq_factorize_batch.  A rank's
+    units run in ROUNDS of --round-size units of similar cost (LPT order), every unit of a round on its own stream with
+    an SM budget proportional to its cost; one step = one outer sweep of every unit (one batch call per round with
+    max_iter_als = 1: set-up of the unfoldings included, factors and duals carried from step to step)."""
+    import torch
+    from source import _native, workloads as wl
+    rank, world, dev = rk.rank, rk.world, rk.dev
+    jobs = []
+    weights = {}
+    for key, name, cout, cin, kh, kw, rr, bits in mine:
+        if name not in weights:
+            weights[name] = wl.layer_weight_as_tensor(wl.synthetic_weight(cout, cin, kh, kw, 42, name)).contiguous()
+        W = weights[name]
+        rnk = wl.rank_from_reduction_rate(W, rr)
+        init = wl.random_init(W.shape, rnk, 42)
+        jobs.append({"key": key, "Wh": W, "rank": rnk, "bits": bits, "init": init,
+                     "cost": wl.solve_cost(W.shape, rnk) * (1.0 + ((1 << bits) - 1) / 60.0)})
+    jobs.sort(key=lambda j: -j["cost"])
+    rounds = [jobs[i:i + args.round_size] for i in range(0, len(jobs), args.round_size)]
+    wdev = {n: w.to(dev) for n, w in weights.items()}
+    for rd in rounds:
+        ctas = allocate_ctas([j["cost"] for j in rd], sm_count, 1)
+        for j, g in zip(rd, ctas):
+            name = j["key"].split("/")[0]
+            j.update(W=wdev[name], factors=[f.to(dev) for f in j["init"]], qscheme=QSCHEME, max_iter_als=1,
+                     max_iter_admm=args.max_iter_admm, solve_precision=args.solve_precision,
+                     mttkrp_precision=args.mttkrp_precision, max_ctas=g, stream=torch.cuda.Stream(device=dev))
+            j["duals"] = [torch.zeros_like(f) for f in j["factors"]]
+            need = int(_native.lib.admmq_factorize_workspace_bytes(
+                j["W"].ndim, (_native.ctypes.c_int * j["W"].ndim)(*j["W"].shape), j["rank"],
+                _native.ctypes.byref(_native.FactorizeParams(1, args.max_iter_admm, 1e-8, 1e-5, j["bits"], 0, 200,
+                                                             args.solve_precision, args.mttkrp_precision, g, 1))))
+            j["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            j["host"] = {"factors": [f.clone().pin_memory() for f in j["init"]],
+                         "duals": [torch.zeros_like(f).pin_memory() for f in j["init"]],
+                         "factors_q": [torch.zeros_like(f).pin_memory() for f in j["init"]]}
+    n_modes = sum(j["W"].ndim for j in jobs)
+    inner_nominal = n_modes * (args.max_iter_admm - 1)
+
+    def step(e2e=False):
+        moved = [0, 0]
+        errs = {}
+        for rd in rounds:
+            if e2e:
+                for j in rd:
+                    with torch.cuda.stream(j["stream"]):
+                        for dst, src in zip(j["factors"] + j["duals"], j["host"]["factors"] + j["host"]["duals"]):
+                            dst.copy_(src, non_blocking=True)
+                            moved[0] += dst.numel() * 4
+            out = _native.factorize_batch(rd)
+            for j, (hist, histq, n, fq) in zip(rd, out):
+                errs[j["key"]] = hist[-1]
+                if e2e:
+                    for dst, src in zip(j["host"]["factors"] + j["host"]["duals"] + j["host"]["factors_q"],
+                                        j["factors"] + j["duals"] + fq):
+                        dst.copy_(src, non_blocking=True)
+                        moved[1] += src.numel() * 4
+        torch.cuda.synchronize()
+        return errs, moved
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    sampler = ClockSampler(rk.local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.launch_count()
+    step_ms, errs = [], {}
+    rk.barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        errs, _ = step()
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    rk.barrier()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = rk.reduce(sum(step_ms), "MAX")
+    # the batch entry point keeps the loop reports on the device; the nominal budget is counted (tap factors of wide
+    # layers leave early in later sweeps, so this is an upper bound of the executed iterations by a few per cent)
+    inner_all = rk.reduce(inner_nominal * args.steps, "SUM")
+    value = inner_all / (total_ms / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        step(e2e=True)
+        rk.barrier()
+        t, moved = [], [0, 0]
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, moved = step(e2e=True)
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        rk.barrier()
+        tot = rk.reduce(sum(t), "MAX")
+        e2e = {"value": inner_all / (tot / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(rk.reduce(moved[0], "SUM")),
+               "d2h_bytes_per_step": int(rk.reduce(moved[1], "SUM")), "ms_per_step": tot / args.steps}
+    gather_ms, gather_bytes = rk.gather_factors([f for j in jobs for f in j["factors"]])
+    per_rank = rk.gather_objects({"rank": rank, "units": len(jobs), "rounds": len(rounds), "ms_per_step": sum(step_ms) / args.steps,
+                                  "launches": launches, "gather_bytes": gather_bytes,
+                                  "cost": sum(j["cost"] for j in jobs)})
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, desc, {"l2": "flushed between timed steps (256 MiB write)",
+                                                   "parallelism": f"one job, {len(units)} units sharded over {world} GPU(s) by LPT; "
+                                                                  f"rounds of {args.round_size} concurrent units per GPU; no data-path collective",
+                                                   "units_per_rank": [pr["units"] for pr in per_rank],
+                                                   "rounds_per_rank": [pr["rounds"] for pr in per_rank],
+                                                   "inner_iterations_per_step": inner_all / args.steps,
+                                                   "inner_iterations_counted": "nominal budget (max_iter_admm - 1 per factor update)"}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": sum(pr["launches"] for pr in per_rank), "roofline": None,
+                "cpu_baseline": None, "per_rank_ms_per_step": [round(pr["ms_per_step"], 2) for pr in per_rank],
+                "per_rank_cost_share": [round(pr["cost"] / sum(p["cost"] for p in per_rank), 4) for pr in per_rank],
+                "rec_error_sample": dict(list(errs.items())[:8]),
+                "factor_gather_ms": gather_ms, "factor_gather_bytes_per_rank": [pr["gather_bytes"] for pr in per_rank]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        rk.dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ the metric's second half
+def run_full(args, rk, units, owner, mine, desc, sm_count):
+    """"Full factorize time" (reference: the printed "took N minutes", scripts/factorize.py:177, 342-343): every unit
+    from its initialisation (`--init random | parafac-epc`, source/admm.py:21-48) to the reference's stop rule
+    (:259-263), all local units concurrently on their SM budgets.  Reports init seconds, ADMM seconds and sweeps per
+    unit and the job's wall time = max over ranks."""
+    import torch
+    from source import _native, workloads as wl
+    from source.admm import init_factors
+    from source.solver import LayerSolver
+    rank, world, dev = rk.rank, rk.world, rk.dev
+    import numpy as np
+    problems = []
+    for key, name, cout, cin, kh, kw, rr, bits in mine:
+        W = wl.layer_weight_as_tensor(wl.synthetic_weight(cout, cin, kh, kw, 42, name)).contiguous()
+        problems.append((key, W, wl.rank_from_reduction_rate(W, rr), bits))
+    rk.barrier()
+    t_job = time.perf_counter()
+    init_s, solvers = {}, []
+    budgets = allocate_ctas([wl.solve_cost(W.shape, r) for _, W, r, _ in problems], sm_count, args.min_ctas) \
+        if len(problems) > 1 else [0] * len(problems)
+    for (key, W, rnk, bits), g in zip(problems, budgets):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        np.random.seed(42)
+        Wd = W.to(dev)
+        fac = init_factors(Wd, rank=rnk, init=args.init, device=dev if args.init != "random" else None, seed=42)
+        fac = [f.to(dev) for f in fac]
+        torch.cuda.synchronize()
+        init_s[key] = time.perf_counter() - t0
+        solvers.append(LayerSolver(Wd, fac, bits, QSCHEME, max_iter_admm=args.max_iter_admm, init_is_random=(args.init == "random"),
+                                   mttkrp_precision=args.mttkrp_precision, solve_precision=args.solve_precision, max_ctas=g))
+    streams = [torch.cuda.Stream(device=dev) for _ in solvers]
+    torch.cuda.synchronize()
+    t_admm = time.perf_counter()
+    active = list(range(len(solvers)))
+    sweeps = {p[0]: 0 for p in problems}
+    admm_s = {}
+    inner = 0
+    while active:
+        for k in active:
+            streams[k].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[k]):
+                solvers[k].enqueue_sweep()
+        nxt = []
+        for k in active:
+            streams[k].synchronize()
+            solvers[k].collect()
+            inner += sum(int(r.iterations) for r in solvers[k].last_reports)
+            sweeps[problems[k][0]] += 1
+            if solvers[k].should_stop() or sweeps[problems[k][0]] >= args.max_iter_als:
+                admm_s[problems[k][0]] = time.perf_counter() - t_admm
+            else:
+                nxt.append(k)
+        if len(nxt) < len(active) and len(nxt) > 0:   # units that finished hand their SMs to the others
+            for k, g in zip(nxt, allocate_ctas([wl.solve_cost(problems[k][1].shape, problems[k][2]) for k in nxt], sm_count,
+                                               args.min_ctas if len(nxt) > 1 else sm_count)):
+                solvers[k].max_ctas = g if len(nxt) > 1 else 0
+        active = nxt
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_job
+    job_s = rk.reduce(wall, "MAX")
+    inner_all = rk.reduce(inner, "SUM")
+    gather_ms, _ = rk.gather_factors([f for s in solvers for f in s.factors])
+    per_rank = rk.gather_objects({"init_s": {k: round(v, 3) for k, v in init_s.items()},
+                                  "admm_s": {k: round(v, 3) for k, v in admm_s.items()}, "sweeps": sweeps,
+                                  "rec_error": {p[0]: round(s.loss_hist[-1], 6) for p, s in zip(problems, solvers)},
+                                  "quant_rec_error": {p[0]: round(s.loss_quant_hist[-1], 6) for p, s in zip(problems, solvers)},
+                                  "wall_s": wall})
+    if rank == 0:
+        merged = {f: {k: v for pr in per_rank for k, v in pr[f].items()} for f in ("init_s", "admm_s", "sweeps", "rec_error", "quant_rec_error")}
+        line = {"metric": "full_factorize_time_s", "value": job_s, "unit": "s", "n_gpus": world, "steps": 1, "warmup": 0,
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, desc, {"init": args.init, "max_iter_als": args.max_iter_als,
+                                                   "stop_rule": "scripts/factorize.py:259-263 (|d rec_error| < 1e-5 or divergence guard)",
+                                                   "parallelism": f"{len(units)} units sharded over {world} GPU(s) by LPT; no data-path collective"}),
+                "inner_iterations": inner_all, "inner_iter_per_s_incl_init": inner_all / job_s,
+                "per_rank_wall_s": [round(pr["wall_s"], 2) for pr in per_rank], "factor_gather_ms": gather_ms, **merged}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        rk.dist.destroy_process_group()
     return 0
 
 

@@ -196,3 +196,67 @@ def test_early_exit_at_the_references_iteration(capsys, precision):
         assert agree >= 0.999, lines[-1]
     with capsys.disabled():
         print("\n[early-exit] " + "\n[early-exit] ".join(lines))
+
+
+# ------------------------------------------------------------------ whole-model driver on hardware
+def _run_driver(tmp, extra, nproc=1):
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(repo, "admm-quantization_b200", "scripts", "factorize_model.py")
+    common = ["--model-name", "resnet18", "--layers", "layer1.0.conv1", "layer1.0.conv2", "layer2.0.conv1", "--bits", "4", "8",
+              "--reduction-rate", "2", "--max_iter_als", "3", "--max_iter_admm", "30", "--outroot", str(tmp)] + extra
+    if nproc == 1:
+        cmd = [sys.executable, script] + common
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+               "127.0.0.1", "--master-port", "29613", script] + common
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return r.stdout
+
+
+def _factor_files(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".pt"):
+                out[os.path.relpath(os.path.join(d, f), root)] = torch.load(os.path.join(d, f))
+    return out
+
+
+def test_whole_model_driver_on_the_gpu(tmp_path, capsys):
+    """scripts/factorize_model.py on hardware: 3 layers x 2 bit-widths through admmq_factorize_batch on one GPU - the
+    reference's file set per solve (scripts/factorize.py:164-166, 315-318, 345-347), every factor equal to what a
+    stand-alone solve of that unit gives - and, where the box has >= 2 GPUs, the same job under torchrun on 2 ranks
+    (LPT sharding, one NCCL gather): bitwise the same files."""
+    from source import _native, workloads as wl
+    from source.solver import layer_weight_as_tensor, rank_from_reduction_rate
+    out1 = _run_driver(tmp_path / "one", [])
+    files = _factor_files(tmp_path / "one")
+    assert len(files) == 3 * 2 * 5, sorted(files)          # 3 modes + 2 histories per solve
+    for bits in (4, 8):
+        for name, cout, cin, kh, kw in [l for l in wl.resnet18_conv_layers() if l[0] in ("layer1.0.conv1", "layer2.0.conv1")]:
+            W = layer_weight_as_tensor(wl.synthetic_weight(cout, cin, kh, kw, 42, name)).contiguous().cuda()
+            R = rank_from_reduction_rate(W, 2.0)
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(42)
+            fac = [torch.randn(d, R, generator=gen, device="cuda") for d in W.shape]   # init_factors('random', device=cuda)
+            hist, _, n, _ = _native.factorize(W, fac, [torch.zeros_like(f) for f in fac], bits, MSE, 3, 30, solve_precision=1,
+                                              mttkrp_precision=1)
+            pre = f"{bits}bit_{MSE}/factors_admm_seed42/{name}_admm_random_rank_{R}"
+            for m in range(3):
+                got = files[f"{pre}_mode_{m}.pt"]
+                assert got.dtype == torch.float32 and torch.equal(got, fac[m].cpu()), (name, bits, m)
+            assert files[f"{pre}_losshist.pt"] == hist
+    with capsys.disabled():
+        print("\n[driver] 1 GPU:", out1.strip().splitlines()[-1])
+    if torch.cuda.device_count() >= 2:
+        out2 = _run_driver(tmp_path / "two", [], nproc=2)
+        files2 = _factor_files(tmp_path / "two")
+        assert sorted(files2) == sorted(files)
+        for k in files:
+            a, b = files[k], files2[k]
+            assert torch.equal(a, b) if torch.is_tensor(a) else a == b, k
+        with capsys.disabled():
+            print("[driver] 2 GPUs:", out2.strip().splitlines()[-1], "- files bitwise identical to the 1-GPU run")
