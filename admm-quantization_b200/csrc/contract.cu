@@ -18,15 +18,18 @@ constexpr int kBK = 16;   // depth of one shared-memory slab
 
 // ---------------------------------------------------------------------------- Gram-Hadamard
 // G[a,b] = fl32(sum_k U1[k,a] U1[k,b]) * fl32(sum_k U2[k,a] U2[k,b]); 32x32 outputs per CTA.
-__global__ void __launch_bounds__(kCT) k_gram_hadamard(const float* __restrict__ U1, int n1,
-                                                      const float* __restrict__ U2, int n2, int R,
-                                                      float* __restrict__ G) {
+// T = float: the solver's Gram (each Gram rounded to float32 before the float32 Hadamard product, like the reference's
+// float32 matmuls); T = double: the ALS / EPC initialisation (source/parafac_epc.py runs in float64), everything double.
+template <typename T>
+__global__ void __launch_bounds__(kCT) k_gram_hadamard(const T* __restrict__ U1, int n1,
+                                                      const T* __restrict__ U2, int n2, int R,
+                                                      T* __restrict__ G) {
   __shared__ double sa[kBK][33], sb[kBK][33];
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8; each thread: rows ty, ty+8, ty+16, ty+24
-  float prod[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+  T prod[4] = {(T)1, (T)1, (T)1, (T)1};
   for (int m = 0; m < 2; ++m) {
-    const float* U = (m == 0) ? U1 : U2;
+    const T* U = (m == 0) ? U1 : U2;
     const int n = (m == 0) ? n1 : n2;
     if (U == nullptr) continue;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -47,7 +50,10 @@ __global__ void __launch_bounds__(kCT) k_gram_hadamard(const float* __restrict__
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) prod[r] = (m == 0) ? (float)acc[r] : mul_rn(prod[r], (float)acc[r]);
+    for (int r = 0; r < 4; ++r) {
+      if constexpr (sizeof(T) == 4) prod[r] = (m == 0) ? (float)acc[r] : mul_rn((float)prod[r], (float)acc[r]);
+      else prod[r] = (m == 0) ? acc[r] : prod[r] * acc[r];
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -75,11 +81,14 @@ __global__ void __launch_bounds__(kCT) k_unfold3(const float* __restrict__ W, in
 
 // ---------------------------------------------------------------------------- MTTKRP (float64 accumulate)
 // F[m, r] = sum_p Wn[m, p] * X[p / ny, r] * Y[p % ny, r]; tile BM x 64, split over p into gridDim.z slices.
-template <int BM>
-__global__ void __launch_bounds__(kCT) k_mttkrp_f64(const float* __restrict__ Wn, int M, long long P,
-                                                   const float* __restrict__ X, const float* __restrict__ Y,
+// TI / TO = float: the solver's parity-mode MTTKRP (float32 operands, result = correctly rounded float32 of the exact
+// contraction); TI = TO = double: the ALS / EPC initialisation - the Khatri-Rao operand is formed on the fly from the two
+// factors, never materialised (source/parafac_epc.py via tensorly's unfolding_dot_khatri_rao builds (I J) x R in memory).
+template <int BM, typename TI, typename TO>
+__global__ void __launch_bounds__(kCT) k_mttkrp_f64(const TI* __restrict__ Wn, int M, long long P,
+                                                   const TI* __restrict__ X, const TI* __restrict__ Y,
                                                    int ny, int R, long long p_per_split,
-                                                   double* __restrict__ partial, float* __restrict__ F) {
+                                                   double* __restrict__ partial, TO* __restrict__ F) {
   constexpr int BN = 64;
   constexpr int TM = BM / 16;  // rows per thread (16 x 16 thread grid, 4 columns per thread)
   __shared__ double sw[kBK][BM + 1], skr[kBK][BN + 2];
@@ -129,18 +138,19 @@ __global__ void __launch_bounds__(kCT) k_mttkrp_f64(const float* __restrict__ Wn
     for (int b = 0; b < 4; ++b) {
       const int m = m0 + ty * TM + a, r = n0 + tx * 4 + b;
       if (m < M && r < R) {
-        if (gridDim.z == 1) F[(size_t)m * R + r] = (float)acc[a][b];
+        if (gridDim.z == 1) F[(size_t)m * R + r] = (TO)acc[a][b];
         else partial[((size_t)blockIdx.z * M + m) * R + r] = acc[a][b];
       }
     }
 }
 
+template <typename TO>
 __global__ void __launch_bounds__(kCT) k_sum_partials(const double* __restrict__ partial, int splits, long long n,
-                                                     float* __restrict__ F) {
+                                                     TO* __restrict__ F) {
   for (long long i = (long long)blockIdx.x * kCT + threadIdx.x; i < n; i += (long long)gridDim.x * kCT) {
     double s = 0.0;
     for (int z = 0; z < splits; ++z) s += partial[(size_t)z * n + i];  // fixed order
-    F[i] = (float)s;
+    F[i] = (TO)s;
   }
 }
 
@@ -259,6 +269,63 @@ static int mttkrp_splits(int M, long long P, int R, int bm, int sms) {
   return (int)std::min<long long>(want, 64);
 }
 
+template <typename TI, typename TO>
+static int launch_mttkrp_f64(const TI* Wn, int M, const TI* X, int nx, const TI* Y, int ny, int R, TO* F, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream) {
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  const long long P = (long long)nx * ny;
+  const int bm = (M <= 16) ? 16 : 64;
+  int splits = mttkrp_splits(M, P, R, bm, dp.sm_count);
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * R * sizeof(double))) splits = 1;
+  long long per = (P + splits - 1) / splits;
+  per = (per + kBK - 1) / kBK * kBK;
+  splits = (int)((P + per - 1) / per);
+  dim3 grid((R + 63) / 64, (M + bm - 1) / bm, splits);
+  if (bm == 16) k_mttkrp_f64<16, TI, TO><<<grid, kCT, 0, stream>>>(Wn, M, P, X, Y, ny, R, per, (double*)workspace, F);
+  else k_mttkrp_f64<64, TI, TO><<<grid, kCT, 0, stream>>>(Wn, M, P, X, Y, ny, R, per, (double*)workspace, F);
+  if (splits > 1) {
+    const long long n = (long long)M * R;
+    k_sum_partials<TO><<<(int)std::min<long long>((n + kCT - 1) / kCT, 148 * 8), kCT, 0, stream>>>((const double*)workspace,
+                                                                                                splits, n, F);
+  }
+  ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(splits > 1 ? 2 : 1);
+  return ADMMQ_OK;
+}
+
+// Column 2-norms of an n x R float64 factor (one warp-wide column strip of 32 columns per CTA, 8 row groups summed in
+// fixed order); a zero norm is reported as 1 (the column is left alone, like the restated cp_anc does).
+__global__ void __launch_bounds__(kCT) k_column_norms(const double* __restrict__ U, int n, int R, double* __restrict__ norms) {
+  __shared__ double red[kCT / 32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (c < R)
+    for (int k = ty; k < n; k += kCT / 32) {
+      const double v = U[(size_t)k * R + c];
+      s = fma(v, v, s);
+    }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < R) {
+    double t = 0.0;
+    for (int w = 0; w < kCT / 32; ++w) t += red[w][tx];
+    const double nrm = sqrt(t);
+    norms[c] = nrm == 0.0 ? 1.0 : nrm;
+  }
+}
+// U[:, c] /= norms[c]; carry[c] *= norms[c] (the scale the caller moves into another factor), carry may be null
+__global__ void __launch_bounds__(kCT) k_scale_columns(double* __restrict__ U, int n, int R, const double* __restrict__ norms,
+                                                      double* __restrict__ carry) {
+  const long long tot = (long long)n * R;
+  for (long long i = (long long)blockIdx.x * kCT + threadIdx.x; i < tot; i += (long long)gridDim.x * kCT) {
+    const int c = (int)(i % R);
+    U[i] = U[i] / norms[c];
+    if (carry != nullptr && i < R) carry[i] *= norms[i];
+  }
+}
+
 }  // namespace admmq
 
 using namespace admmq;
@@ -267,7 +334,7 @@ extern "C" int admmq_gram_hadamard(const float* U1, int n1, const float* U2, int
   if (U1 == nullptr || G == nullptr || n1 <= 0 || R <= 0 || (U2 != nullptr && n2 <= 0))
     return fail(ADMMQ_E_BADARG, "admmq_gram_hadamard: bad argument");
   dim3 grid((R + 31) / 32, (R + 31) / 32);
-  k_gram_hadamard<<<grid, kCT, 0, (cudaStream_t)stream_>>>(U1, n1, U2, n2, R, G);
+  k_gram_hadamard<float><<<grid, kCT, 0, (cudaStream_t)stream_>>>(U1, n1, U2, n2, R, G);
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return ADMMQ_OK;
@@ -313,25 +380,40 @@ extern "C" int admmq_mttkrp(const float* Wn, int M, const float* X, int nx, cons
                                      "admmq_permute_myx once per layer and admmq_mttkrp_tc");
   }
   if (precision != 0) return fail(ADMMQ_E_BADARG, "admmq_mttkrp: precision must be 0 (f64 accumulate) or 1 (3xTF32)");
-  DeviceProps dp;
-  if (int e = device_props(&dp)) return e;
-  const long long P = (long long)nx * ny;
-  const int bm = (M <= 16) ? 16 : 64;
-  int splits = mttkrp_splits(M, P, R, bm, dp.sm_count);
-  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * R * sizeof(double))) splits = 1;
-  long long per = (P + splits - 1) / splits;
-  per = (per + kBK - 1) / kBK * kBK;
-  splits = (int)((P + per - 1) / per);
-  dim3 grid((R + 63) / 64, (M + bm - 1) / bm, splits);
-  if (bm == 16) k_mttkrp_f64<16><<<grid, kCT, 0, stream>>>(Wn, M, P, X, Y, ny, R, per, (double*)workspace, F);
-  else k_mttkrp_f64<64><<<grid, kCT, 0, stream>>>(Wn, M, P, X, Y, ny, R, per, (double*)workspace, F);
-  if (splits > 1) {
-    const long long n = (long long)M * R;
-    k_sum_partials<<<(int)std::min<long long>((n + kCT - 1) / kCT, 148 * 8), kCT, 0, stream>>>((const double*)workspace,
-                                                                                            splits, n, F);
-  }
+  return launch_mttkrp_f64<float, float>(Wn, M, X, nx, Y, ny, R, F, workspace, workspace_bytes, stream);
+}
+
+// ---- float64 pieces of the ALS / EPC initialisation (source/parafac_epc.py:12-82; tensorly parafac, musco cp_anc)
+extern "C" size_t admmq_mttkrp_f64_workspace_bytes(int M, int nx, int ny, int R) {
+  return admmq_mttkrp_workspace_bytes(M, nx, ny, R, 0);
+}
+
+extern "C" int admmq_mttkrp_f64(const double* Wn, int M, const double* X, int nx, const double* Y, int ny, int R,
+                                double* F, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (Wn == nullptr || X == nullptr || F == nullptr || M <= 0 || nx <= 0 || R <= 0 || (Y != nullptr && ny <= 0))
+    return fail(ADMMQ_E_BADARG, "admmq_mttkrp_f64: bad argument");
+  if (Y == nullptr) ny = 1;
+  return launch_mttkrp_f64<double, double>(Wn, M, X, nx, Y, ny, R, F, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int admmq_gram_hadamard_f64(const double* U1, int n1, const double* U2, int n2, int R, double* G, void* stream_) {
+  if (U1 == nullptr || G == nullptr || n1 <= 0 || R <= 0 || (U2 != nullptr && n2 <= 0))
+    return fail(ADMMQ_E_BADARG, "admmq_gram_hadamard_f64: bad argument");
+  dim3 grid((R + 31) / 32, (R + 31) / 32);
+  k_gram_hadamard<double><<<grid, kCT, 0, (cudaStream_t)stream_>>>(U1, n1, U2, n2, R, G);
   ADMMQ_CUDA_OK(cudaGetLastError());
-  count_launches(splits > 1 ? 2 : 1);
+  count_launches(1);
+  return ADMMQ_OK;
+}
+
+extern "C" int admmq_normalize_columns_f64(double* U, int n, int R, double* norms, double* carry, void* stream_) {
+  if (U == nullptr || norms == nullptr || n <= 0 || R <= 0) return fail(ADMMQ_E_BADARG, "admmq_normalize_columns_f64: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  k_column_norms<<<(R + 31) / 32, kCT, 0, stream>>>(U, n, R, norms);
+  const long long tot = (long long)n * R;
+  k_scale_columns<<<(int)std::min<long long>((tot + kCT - 1) / kCT, 148 * 8), kCT, 0, stream>>>(U, n, R, norms, carry);
+  ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(2);
   return ADMMQ_OK;
 }
 

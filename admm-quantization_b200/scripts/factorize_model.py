@@ -109,7 +109,7 @@ def main(argv=None):
         out = _native.factorize_batch(jobs)
         torch.cuda.synchronize()
         for u, j, (hist, histq, sweeps, fq) in zip(rd, jobs, out):
-            results[u["key"]] = {"factors": [f.clone() for f in j["factors"]], "loss": hist, "loss_quant": histq}
+            results[u["key"]] = {"factors": [f.detach().cpu() for f in j["factors"]], "loss": hist, "loss_quant": histq}
             print(f"[rank {rank}] {u['key']} rank {u['rank']} on {j['max_ctas'] or sm_count} SMs: {sweeps} sweeps, "
                   f"rec_error {hist[-1]:.6f}, quant {histq[-1]:.6f}", flush=True)
     merged = gather_results(results, device=dev if args.backend == "nccl" else torch.device("cpu"))

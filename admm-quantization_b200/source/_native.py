@@ -63,6 +63,10 @@ def _load():
         "admmq_permute_myx": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
         "admmq_mttkrp_tc_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
         "admmq_mttkrp_tc": (c_int, [vp, c_int, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
+        "admmq_mttkrp_f64_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+        "admmq_mttkrp_f64": (c_int, [vp, c_int, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
+        "admmq_gram_hadamard_f64": (c_int, [vp, c_int, vp, c_int, c_int, vp, vp]),
+        "admmq_normalize_columns_f64": (c_int, [vp, c_int, c_int, vp, vp, vp]),
         "admmq_recon_error_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "admmq_recon_error": (c_int, [vp, c_int, vp, vp, c_int, vp, c_int, c_int, vp, vp, c_sz, vp]),
         "admmq_gemm_nt": (c_int, [vp, c_int, c_int, vp, c_int, c_int, c_int, vp, c_int, vp]),
@@ -95,7 +99,8 @@ lib = _load()
 EXPORTS = ("admmq_version admmq_last_error admmq_device_info admmq_launch_count admmq_project_workspace_bytes "
            "admmq_project admmq_clip_search_sums admmq_admm_loop_workspace_bytes admmq_admm_loop admmq_gemm_nt "
            "admmq_gram_hadamard admmq_unfold3 admmq_mttkrp_workspace_bytes admmq_mttkrp admmq_permute_myx "
-           "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc "
+           "admmq_mttkrp_tc_workspace_bytes admmq_mttkrp_tc admmq_mttkrp_f64_workspace_bytes admmq_mttkrp_f64 "
+           "admmq_gram_hadamard_f64 admmq_normalize_columns_f64 "
            "admmq_recon_error_workspace_bytes admmq_recon_error admmq_padded_ld admmq_spd_inverse_workspace_bytes "
            "admmq_spd_inverse admmq_admm_iteration_workspace_bytes admmq_admm_iteration "
            "admmq_factorize_workspace_bytes admmq_factorize_cp3 admmq_factorize_mat admmq_factorize_batch "
@@ -299,6 +304,51 @@ def mttkrp_tc(V, M, X, Y=None, out=None, ws=None):
     ws = _ws(mttkrp_tc_workspace_bytes(M, nx, ny, R), V.device, ws)
     call(V.device, lib.admmq_mttkrp_tc, ptr(V), int(M), ptr(X), nx, ptr(Y), ny, R, ptr(F), ptr(ws), ws.numel(), stream_ptr(V.device))
     return F
+
+
+# ---- float64 pieces of the ALS + EPC initialisation (source/parafac_epc.py)
+def _f64c(t):
+    assert t.dtype == torch.float64 and t.is_contiguous(), "float64 contiguous tensor expected"
+    return t
+
+
+def mttkrp_f64(Wn, X, Y=None, out=None, ws=None):
+    """F = Wn @ khatri_rao(X, Y) in float64 without materialising the Khatri-Rao operand; Wn is the (M, nx*ny) unfolding."""
+    require_cuda(Wn, X, Y, out, ws)
+    Wn, X = _f64c(Wn), _f64c(X)
+    Y = None if Y is None else _f64c(Y)
+    M, R = Wn.shape[0], X.shape[1]
+    nx, ny = X.shape[0], (1 if Y is None else Y.shape[0])
+    assert Wn.shape[1] == nx * ny, (Wn.shape, nx, ny)
+    F = torch.empty(M, R, dtype=torch.float64, device=Wn.device) if out is None else _f64c(out)
+    ws = _ws(int(lib.admmq_mttkrp_f64_workspace_bytes(M, nx, ny, R)), Wn.device, ws)
+    call(Wn.device, lib.admmq_mttkrp_f64, ptr(Wn), M, ptr(X), nx, ptr(Y), ny, R, ptr(F), ptr(ws), ws.numel(),
+         stream_ptr(Wn.device))
+    return F
+
+
+def gram_hadamard_f64(U1, U2=None, out=None):
+    """G = (U1^T U1) * (U2^T U2) in float64."""
+    require_cuda(U1, U2, out)
+    U1 = _f64c(U1)
+    U2 = None if U2 is None else _f64c(U2)
+    R = U1.shape[1]
+    G = torch.empty(R, R, dtype=torch.float64, device=U1.device) if out is None else _f64c(out)
+    call(U1.device, lib.admmq_gram_hadamard_f64, ptr(U1), U1.shape[0], ptr(U2), 0 if U2 is None else U2.shape[0], R, ptr(G),
+         stream_ptr(U1.device))
+    return G
+
+
+def normalize_columns_f64(U, carry=None, norms=None):
+    """In place: U[:, c] /= ||U[:, c]|| (zero columns untouched), carry[c] *= ||U[:, c]||.  Returns the norms."""
+    require_cuda(U, carry, norms)
+    U = _f64c(U)
+    n, R = U.shape
+    norms = torch.empty(R, dtype=torch.float64, device=U.device) if norms is None else _f64c(norms)
+    if carry is not None:
+        _f64c(carry)
+    call(U.device, lib.admmq_normalize_columns_f64, ptr(U), n, R, ptr(norms), ptr(carry), stream_ptr(U.device))
+    return norms
 
 
 def recon_error_workspace_bytes(M, nx, ny):

@@ -205,6 +205,8 @@ def reference_sample(args, units, budget_s, device="cpu", thread_cache=None):
     (best of {1, 4, nproc/2, nproc}: small shapes get slower with threads).  Returns a dict."""
     import torch
     admm_iteration, kind = load_reference()
+    if device != "cpu" and kind != "reference":
+        raise RuntimeError("the eager-on-GPU bar needs the reference's own functions (oracle/_ref is missing)")
     nproc = os.cpu_count() or 1
     shapes = {}
     for u in units:

@@ -121,6 +121,21 @@ ADMMQ_API size_t admmq_recon_error_workspace_bytes(int M, int nx, int ny);
 ADMMQ_API int admmq_recon_error(const float* W0, int M, const float* A, const float* X, int nx, const float* Y, int ny,
                       int R, double* out2, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ float64 pieces of the ALS + EPC initialisation
+ * `parafac_epc` (source/parafac_epc.py:12-82) runs tensorly's ALS (`parafac`, :42-43) and musco's error-preserving
+ * correction (`cp_anc`, :63) in float64; both spend their time in MTTKRP and Gram-Hadamard products (tensorly forms the
+ * MTTKRP as unfolding x materialised Khatri-Rao: (I J) x R doubles, 2.4 GB for mode 2 of a 512 x 512 x 9 layer, every
+ * pass).  Same contracts as admmq_mttkrp / admmq_gram_hadamard with float64 operands and results; the Khatri-Rao
+ * operand is formed on the fly.  The R x R eigen-decomposition / linear solve of a mode update stays with the caller.
+ *   admmq_normalize_columns_f64   norms[c] = ||U[:, c]||_2 (a zero norm is reported as 1), U[:, c] /= norms[c] in
+ *                                 place, carry[c] *= norms[c] (carry may be NULL): the column normalisation that
+ *                                 precedes every mode update of cp_anc, with the scale moved into another factor. */
+ADMMQ_API size_t admmq_mttkrp_f64_workspace_bytes(int M, int nx, int ny, int R);
+ADMMQ_API int admmq_mttkrp_f64(const double* Wn, int M, const double* X, int nx, const double* Y, int ny, int R,
+                     double* F, void* workspace, size_t workspace_bytes, void* stream);
+ADMMQ_API int admmq_gram_hadamard_f64(const double* U1, int n1, const double* U2, int n2, int R, double* G, void* stream);
+ADMMQ_API int admmq_normalize_columns_f64(double* U, int n, int R, double* norms, double* carry, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core building block
  * C (M x N, ldc) = A (M x K, lda) . B (N x K, ldb)^T in 3xTF32 on tcgen05/TMEM: float32 operands are split into
  * tf32 hi + lo on the fly and accumulated as lo.hi + hi.lo + hi.hi in float32 (csrc/tc_gemm.cuh).  This is the tile

@@ -2,8 +2,8 @@
 
 TEST / MEASUREMENT INFRASTRUCTURE - not product code.  /root/reference does not exist on the GPU box, and its sources
 are never copied into this repository.  What travels is a BUILD PRODUCT made from the sources where they lie, like a
-compiled C reference would be: CPython bytecode (`py_compile`, sourceless `.pyc` modules laid out as the package
-`source`) of
+compiled C reference would be: CPython bytecode (`py_compile`; stored as `<module>.pyc.bin` because snapshot tools
+commonly drop `*.pyc`, loaded by oracle/ref_import.py with `marshal`) of
 
     source/admm.py  source/quantization.py  source/utils.py  source/parafac_epc.py
 
@@ -28,17 +28,12 @@ def build(verbose=False):
         return None
     out_pkg = os.path.join(OUT, "source")
     os.makedirs(out_pkg, exist_ok=True)
-    init_src = os.path.join(src_dir, "__init__.py")
     made = []
-    if os.path.exists(init_src):
-        made.append(py_compile.compile(init_src, cfile=os.path.join(out_pkg, "__init__.pyc"), doraise=True, optimize=0))
-    else:   # namespace package in the reference: an empty package marker is enough
-        empty = os.path.join(OUT, "_empty.py")
-        open(empty, "w").close()
-        made.append(py_compile.compile(empty, cfile=os.path.join(out_pkg, "__init__.pyc"), doraise=True, optimize=0))
-        os.remove(empty)
+    for f in os.listdir(out_pkg):   # stale products of an earlier layout
+        if f.endswith(".pyc"):
+            os.remove(os.path.join(out_pkg, f))
     for m in MODULES:
-        made.append(py_compile.compile(os.path.join(src_dir, m + ".py"), cfile=os.path.join(out_pkg, m + ".pyc"),
+        made.append(py_compile.compile(os.path.join(src_dir, m + ".py"), cfile=os.path.join(out_pkg, m + ".pyc.bin"),
                                        doraise=True, optimize=0))
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"py_compile of {src_dir}/{{{','.join(MODULES)}}}.py by oracle/build_ref.py; python {sys.version.split()[0]}\n")

@@ -26,7 +26,7 @@ def reference_root():
     the sourceless bytecode package oracle/_ref (made from those sources by oracle/build_ref.py), else None."""
     if os.path.isfile(os.path.join(REFERENCE_ROOT, "source", "admm.py")):
         return REFERENCE_ROOT
-    if os.path.isfile(os.path.join(COMPILED_ROOT, "source", "admm.pyc")):
+    if os.path.isfile(os.path.join(COMPILED_ROOT, "source", "admm.pyc.bin")):
         return COMPILED_ROOT
     return None
 
@@ -44,6 +44,27 @@ def _stub(name, **attrs):
 
 def _missing(*_a, **_k):
     raise RuntimeError("third-party routine (tensorly/musco) is not available in this container")
+
+
+def _load_compiled():
+    """The reference's `source` package from the bytecode files of oracle/build_ref.py: a package module plus the four
+    hot-path modules executed in dependency order (source.admm imports the other three)."""
+    import marshal
+    pkg = types.ModuleType("source")
+    pkg.__path__ = [os.path.join(COMPILED_ROOT, "source")]
+    sys.modules["source"] = pkg
+    mods = {}
+    for name in ("utils", "quantization", "parafac_epc", "admm"):
+        with open(os.path.join(COMPILED_ROOT, "source", name + ".pyc.bin"), "rb") as f:
+            code = marshal.loads(f.read()[16:])      # 16-byte .pyc header: magic, flags, mtime, size
+        mod = types.ModuleType("source." + name)
+        mod.__package__ = "source"
+        mod.__file__ = code.co_filename
+        sys.modules["source." + name] = mod
+        exec(code, mod.__dict__)
+        setattr(pkg, name, mod)
+        mods[name] = mod
+    return mods["admm"], mods["quantization"], mods["utils"]
 
 
 def import_reference():
@@ -68,10 +89,13 @@ def import_reference():
         sys.modules["tensorly.kruskal_tensor"].KruskalTensor = _missing
         sys.modules["tensorly.kruskal_tensor"].kruskal_to_tensor = _missing
         sys.modules["musco.pytorch.compressor.decompose.cpd.lib_anc"].cp_anc = _missing
-        sys.path.insert(0, root)
-        admm = importlib.import_module("source.admm")
-        quant = importlib.import_module("source.quantization")
-        utils = importlib.import_module("source.utils")
+        if root == COMPILED_ROOT:
+            admm, quant, utils = _load_compiled()
+        else:
+            sys.path.insert(0, root)
+            admm = importlib.import_module("source.admm")
+            quant = importlib.import_module("source.quantization")
+            utils = importlib.import_module("source.utils")
         ns = types.SimpleNamespace(
             admm_iteration=admm.admm_iteration,
             init_factors=admm.init_factors,

@@ -4,6 +4,7 @@ BASELINE configs 4 / 5, early exits.  Everything goes through the C ABI (`libadm
 `tests/golden/long_run.npz` / `solve_divergence.npz` (generator: `oracle/make_golden.py --only long_run,solve_divergence`).
 """
 import json
+import math
 import os
 import zlib
 
@@ -247,7 +248,7 @@ def test_whole_model_driver_on_the_gpu(tmp_path, capsys):
             pre = f"{bits}bit_{MSE}/factors_admm_seed42/{name}_admm_random_rank_{R}"
             for m in range(3):
                 got = files[f"{pre}_mode_{m}.pt"]
-                assert got.dtype == torch.float32 and torch.equal(got, fac[m].cpu()), (name, bits, m)
+                assert got.dtype == torch.float32 and torch.equal(got.cpu(), fac[m].cpu()), (name, bits, m)
             assert files[f"{pre}_losshist.pt"] == hist
     with capsys.disabled():
         print("\n[driver] 1 GPU:", out1.strip().splitlines()[-1])
@@ -257,6 +258,73 @@ def test_whole_model_driver_on_the_gpu(tmp_path, capsys):
         assert sorted(files2) == sorted(files)
         for k in files:
             a, b = files[k], files2[k]
-            assert torch.equal(a, b) if torch.is_tensor(a) else a == b, k
+            assert torch.equal(a.cpu(), b.cpu()) if torch.is_tensor(a) else a == b, k
         with capsys.disabled():
             print("[driver] 2 GPUs:", out2.strip().splitlines()[-1], "- files bitwise identical to the 1-GPU run")
+
+
+# ------------------------------------------------------------------ ALS + EPC initialisation (parity unpinned)
+def test_als_epc_initialisation_on_native_kernels(capsys):
+    """source/parafac_epc.py on the GPU (float64; MTTKRP without a materialised Khatri-Rao, Gram-Hadamard and column
+    normalisation are libadmmq kernels) against the CPU restatement oracle.admm_oracle.parafac_epc_fp64 from the same
+    numpy seed, and the properties the method is defined by: the error bound delta is preserved by every EPC pass, the
+    total intensity sum(lambda^2) never grows, factors come back in the ORIGINAL mode order (source/parafac_epc.py:77-82)."""
+    from oracle import admm_oracle as orc
+    from source import _native
+    from source.parafac_epc import _Tensor, _als, _epc_sweep, _intensities, _reconstruct, parafac_epc
+    g = torch.Generator().manual_seed(3)
+    # ---- kernels against float64 torch
+    for shape, R in (((14, 10, 6), 12), ((33, 20, 9), 40), ((64, 64, 9), 134), ((40, 28), 17)):
+        Y = torch.randn(*shape, generator=g, dtype=torch.float64).cuda()
+        fac = [torch.randn(d, R, generator=g, dtype=torch.float64).cuda() for d in shape]
+        T = _Tensor(Y)
+        for m in range(len(shape)):
+            others = [f for k, f in enumerate(fac) if k != m]
+            kr = others[0]
+            for M in others[1:]:
+                kr = (kr[:, None, :] * M[None, :, :]).reshape(-1, R)
+            ref = T.unf[m] @ kr
+            got = T.mttkrp(fac, m)
+            assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max()), (shape, m)
+            gref = torch.ones(R, R, dtype=torch.float64, device="cuda")
+            for f in others:
+                gref = gref * (f.T @ f)
+            assert float((T.gram(fac, m) - gref).abs().max()) <= 1e-12 * float(gref.abs().max())
+        U = fac[0].clone()
+        carry = torch.full((R,), 2.0, dtype=torch.float64, device="cuda")
+        nrm = _native.normalize_columns_f64(U, carry=carry)
+        assert torch.allclose(nrm, torch.linalg.norm(fac[0], dim=0), rtol=1e-14)
+        assert torch.allclose(U, fac[0] / nrm, rtol=1e-15) and torch.allclose(carry, 2.0 * nrm, rtol=1e-15)
+    # ---- the whole initialisation against the CPU restatement (same numpy stream)
+    W = torch.randn(14, 10, 6, generator=g)
+    np.random.seed(3)
+    lam_o, Us_o = orc.parafac_epc_fp64(W, 12, als_maxiter=15, epc_maxiter=4, epc_rounds=2)
+    np.random.seed(3)
+    info = {}
+    lam, Us = parafac_epc(W.cuda(), 12, als_maxiter=15, epc_maxiter=4, epc_rounds=2, info=info)
+    assert [tuple(u.shape) for u in Us] == [(14, 12), (10, 12), (6, 12)] and Us[0].dtype == torch.float64 and Us[0].is_cuda
+    worst = max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(Us, Us_o))
+    assert worst <= 1e-9 and torch.allclose(lam.cpu(), lam_o, rtol=1e-9), worst
+    # a CPU tensor is a host-buffer call: computed on the GPU, returned on the CPU
+    np.random.seed(3)
+    _, Us_h = parafac_epc(W, 12, als_maxiter=15, epc_maxiter=4, epc_rounds=2)
+    assert not Us_h[0].is_cuda and all(torch.equal(a.cpu(), b) for a, b in zip(Us, Us_h))
+    # ---- properties on the config-1 shape (64 x 64 x 9, R = 134)
+    Y = (torch.randn(64, 64, 9, generator=g) * 0.06).double().cuda()
+    T = _Tensor(Y.permute(2, 0, 1).contiguous())                   # ascending mode sizes (source/parafac_epc.py:38-40)
+    w, fac = _als(T, 134, 50, 1e-5, np.random.RandomState(42), True)
+    delta = float(torch.linalg.norm(T.Y - _reconstruct(w, fac)))
+    fac[-1] = (fac[-1] * w).contiguous()
+    prev = float((_intensities(fac) ** 2).sum())
+    first = prev
+    for _ in range(12):
+        fac = _epc_sweep(T, fac, delta)
+        err = float(torch.linalg.norm(T.Y - torch.einsum("ir,jr,kr->ijk", *fac)))
+        cur = float((_intensities(fac) ** 2).sum())
+        assert err <= delta * (1 + 1e-6) and cur <= prev * (1 + 1e-9), (err, delta, cur, prev)
+        prev = cur
+    with capsys.disabled():
+        print(f"\n[als-epc] CUDA vs CPU restatement after 15 ALS + 8 EPC passes: max rel. factor difference {worst:.1e}; "
+              f"64x64x9 R=134: delta/||Y|| = {delta / math.sqrt(T.norm2):.4f} preserved over 12 EPC passes, "
+              f"sum(lambda^2) {first:.1f} -> {prev:.1f}; small case: ALS {info['als_s'] * 1e3:.0f} ms, EPC {info['epc_s'] * 1e3:.0f} ms "
+              f"({info['epc_passes']} passes)")

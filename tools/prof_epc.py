@@ -1,37 +1,40 @@
-import sys, time
-sys.path[:0]=['/root/repo','/root/repo/admm-quantization_b200']
+"""Dev tool: where does one ALS / EPC pass spend its time?   python tools/prof_epc.py I J K [passes]
+
+Prints the time of an ALS run (50 iterations budget), of `passes` EPC passes and of the pieces of one mode update:
+the native float64 MTTKRP / Gram-Hadamard / column normalisation (csrc/contract.cu) against the materialised
+Khatri-Rao form, and torch's (cuSOLVER's) symmetric eigen-decomposition, which is what remains."""
+import os, sys, time
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [REPO, os.path.join(REPO, "admm-quantization_b200")]
 import numpy as np, torch
-from source import parafac_epc as pe
+from source import _native, parafac_epc as pe
 shp = tuple(int(a) for a in sys.argv[1:4])
+passes = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 g = torch.Generator().manual_seed(42)
 W = (torch.randn(*shp, generator=g) * 0.05).cuda().double()
-order = np.argsort(W.shape); Yp = W.permute(tuple(int(o) for o in order)).contiguous()
+order = np.argsort(W.shape)
+T = pe._Tensor(W.permute(tuple(int(o) for o in order)).contiguous())
 R = int(W.numel() / sum(W.shape) / 2.0)
-np.random.seed(42)
-torch.cuda.synchronize(); t0=time.perf_counter()
-w, fac = pe.parafac_als(Yp, R, n_iter_max=50, tol=1e-5, normalize_factors=True)
-torch.cuda.synchronize(); t1=time.perf_counter()
-print("ALS", t1-t0, "s")
-delta = float(torch.linalg.norm(Yp - pe._reconstruct(w, fac))); fac[-1] = fac[-1]*w
-n2 = float((Yp*Yp).sum())
-for name, cache in (("eigh", None), ("chol", [None]*3)):
-    f = [x.clone() for x in fac]
-    torch.cuda.synchronize(); t0=time.perf_counter()
-    for i in range(10): f = pe.epc_sweep(Yp, f, delta, n2, cache)
-    torch.cuda.synchronize(); t1=time.perf_counter()
-    print(name, "per sweep", (t1-t0)/10*1e3, "ms")
-# parts
-m=0
-gamma = (f[1].T@f[1])*(f[2].T@f[2]); T = pe._mttkrp(Yp, f, 0)
-def tm(fn,n=5):
-    fn(); torch.cuda.synchronize(); t0=time.perf_counter()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+w, fac = pe._als(T, R, 50, 1e-5, np.random.RandomState(42), True)
+torch.cuda.synchronize(); t1 = time.perf_counter()
+print(f"shape {shp} rank {R}: ALS {t1 - t0:.3f} s")
+delta = float(torch.linalg.norm(T.Y - pe._reconstruct(w, fac))); fac[-1] = (fac[-1] * w).contiguous()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for i in range(passes):
+    fac = pe._epc_sweep(T, fac, delta)
+torch.cuda.synchronize(); t1 = time.perf_counter()
+print(f"EPC: {(t1 - t0) / passes * 1e3:.2f} ms per pass -> {2500 * (t1 - t0) / passes:.1f} s for the reference's budget of 50 rounds x 50 passes")
+def tm(fn, n=5):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(n): fn()
-    torch.cuda.synchronize(); return (time.perf_counter()-t0)/n*1e3
-print("eigh ms", tm(lambda: torch.linalg.eigh(gamma)))
-L = torch.linalg.cholesky(gamma + 0.1*torch.eye(R, device='cuda', dtype=torch.float64))
-S = T.T@T
-print("cholesky ms", tm(lambda: torch.linalg.cholesky_ex(gamma + 0.1*torch.eye(R, device='cuda', dtype=torch.float64))))
-print("cholesky_solve RxR ms", tm(lambda: torch.cholesky_solve(S, L)))
-print("mttkrp ms", tm(lambda: pe._mttkrp(Yp, f, 0)))
-print("inverse via solve_triangular ms", tm(lambda: torch.linalg.solve_triangular(L, torch.eye(R, device='cuda', dtype=torch.float64), upper=False)))
-print("matmul RxR ms", tm(lambda: S@S))
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+m = T.N - 1   # the largest mode
+gamma = T.gram(fac, m)
+def kr_form():
+    o = [f for k, f in enumerate(fac) if k != m]
+    kr = (o[0][:, None, :] * o[1][None, :, :]).reshape(-1, R)
+    return T.unf[m] @ kr
+print(f"mode {m}: native MTTKRP {tm(lambda: T.mttkrp(fac, m)):.3f} ms (materialised Khatri-Rao + matmul {tm(kr_form):.3f} ms), "
+      f"native Gram-Hadamard {tm(lambda: T.gram(fac, m)):.3f} ms, column normalisation {tm(lambda: _native.normalize_columns_f64(fac[0].clone())):.3f} ms, "
+      f"eigh {tm(lambda: torch.linalg.eigh(gamma)):.3f} ms, T @ V {tm(lambda: T.mttkrp(fac, m) @ gamma):.3f} ms")
