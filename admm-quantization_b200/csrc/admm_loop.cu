@@ -23,6 +23,7 @@
 #include "spd_inverse.cuh"
 #include "tc_gemm.cuh"
 #include "admm_loop_resident.cuh"
+#include "admm_loop_cluster.cuh"
 
 namespace admmq {
 
@@ -944,8 +945,11 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
                        int8_t* codes, admmq_loop_report* report, char* ws, int grid, cudaStream_t stream) {
   const LoopLayout l = loop_layout(I, R, grid);
   static const bool no_resident = getenv("ADMMQ_NO_RESIDENT") != nullptr;  // diagnostics: force the general kernel
-  if (grid == 1 && precision != 0 && !no_resident && resident_fits(I, R, l.Rp, num_attempts)) {
-    // a small factor on a single CTA: the shared-memory-resident loop (admm_loop_resident.cuh)
+  static const bool no_cluster = getenv("ADMMQ_NO_CLUSTER") != nullptr;    // diagnostics: never take the cluster kernel
+  const int ccl = (precision != 0 && !no_resident && !no_cluster && grid >= 4) ? cluster_ctas_for(I, R, l.Rp, num_attempts, grid) : 0;
+  if ((grid == 1 || ccl >= 4) && precision != 0 && !no_resident && resident_fits(I, R, l.Rp, num_attempts)) {
+    // a small factor: the shared-memory-resident loop on one CTA (admm_loop_resident.cuh) or, with a budget of at
+    // least two CTAs, on a thread-block cluster that splits rows and clip candidates (admm_loop_cluster.cuh)
     ResidentParams rp;
     rp.H = H;
     rp.U = U;
@@ -963,6 +967,25 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     rp.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
     rp.codes = codes;
     rp.report = report;
+    if (ccl >= 4) {
+      ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_admm_loop_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem)));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(ccl);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = sizeof(ClusterSmem);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = ccl;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ADMMQ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_admm_loop_cluster, rp));
+      count_launches(1);
+      return ADMMQ_OK;
+    }
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_admm_loop_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResidentSmem)));
     k_admm_loop_resident<<<1, kThreads, sizeof(ResidentSmem), stream>>>(rp);
     ADMMQ_CUDA_OK(cudaGetLastError());

@@ -18,6 +18,9 @@ int gemm_nt(const float* A, int lda, int M, const float* B, const float* Blo, in
             cudaStream_t stream);  // tc_gemm.cu
 int mttkrp_fold_gemm(const float* V, int ldv, int Mout, int ny, const float* B, const float* Blo, int ldb, int N, int K,
                      const float* Y, float* F, cudaStream_t stream);  // tc_gemm.cu
+size_t mttkrp_foldlong_partial_bytes(int Mout, int ny, int N);
+int mttkrp_foldlong_gemm(const float* V, int ldv, int Mout, int ny, const float* B, const float* Blo, int ldb, int N, int K,
+                         const float* Y, float* F, double* partial, cudaStream_t stream);  // tc_gemm.cu
 
 constexpr int kTT = 256;
 
@@ -66,25 +69,14 @@ __global__ void __launch_bounds__(kTT) k_transpose_split(const float* __restrict
   }
 }
 
-// F[m, r] = sum_y Y[y, r] * T[(m, y), r], float64 accumulation, float32 result
-__global__ void __launch_bounds__(kTT) k_fold_y(const float* __restrict__ T, int M, int ny, int R, int ldt,
-                                               const float* __restrict__ Y, float* __restrict__ F) {
-  const long long n = (long long)M * R;
-  for (long long o = (long long)blockIdx.x * kTT + threadIdx.x; o < n; o += (long long)gridDim.x * kTT) {
-    const int m = (int)(o / R), r = (int)(o - (long long)m * R);
-    double acc = 0.0;
-    for (int y = 0; y < ny; ++y) acc = fma((double)Y[(size_t)y * R + r], (double)T[((size_t)m * ny + y) * ldt + r], acc);
-    F[o] = (float)acc;
-  }
-}
-
 static size_t tc_layout(int M, int nx, int ny, int R, size_t* xt_off, size_t* t_off) {
   const size_t ldx = (size_t)(nx + 3) / 4 * 4;
   size_t off = 0;
   *xt_off = off;
   off += 2 * align_up((size_t)R * ldx * sizeof(float), 256);  // hi and lo parts of X^T
   *t_off = off;
-  if (ny > 1) off += align_up((size_t)M * ny * R * sizeof(float), 256);
+  // ny > 128: float64 partial sums of the long fold (two per row tile and column); the intermediate T itself is never stored
+  if (ny > 128) off += align_up(mttkrp_foldlong_partial_bytes(M, ny, R), 256);
   return off;
 }
 
@@ -104,7 +96,7 @@ int mttkrp_tc(const float* V, int M, const float* X, int nx, const float* Y, int
   const int ldx = (nx + 3) / 4 * 4;
   float* Xt = (float*)((char*)workspace + xt_off);
   float* XtLo = (float*)((char*)workspace + xt_off + align_up((size_t)R * ldx * sizeof(float), 256));
-  float* T = (ny > 1) ? (float*)((char*)workspace + t_off) : F;
+  double* partial = (double*)((char*)workspace + t_off);
   dim3 tg((R + 31) / 32, (ldx + 31) / 32);
   k_transpose_split<<<tg, kTT, 0, stream>>>(X, nx, R, Xt, XtLo, ldx, -0.0f);  // (R x ldx) = X^T, pad columns zero
   ADMMQ_CUDA_OK(cudaGetLastError());
@@ -113,14 +105,8 @@ int mttkrp_tc(const float* V, int M, const float* X, int nx, const float* Y, int
     // the fold over the small index happens in the GEMM's epilogue: T is never materialised
     return mttkrp_fold_gemm(V, ldx, M, ny, Xt, XtLo, ldx, R, nx, Y, F, stream);
   }
-  if (int e = gemm_nt(V, ldx, M * ny, Xt, XtLo, ldx, R, nx, T, R, stream)) return e;
-  if (ny > 1) {
-    const long long n = (long long)M * R;
-    k_fold_y<<<(int)std::min<long long>((n + kTT - 1) / kTT, 148 * 8), kTT, 0, stream>>>(T, M, ny, R, R, Y, F);
-    ADMMQ_CUDA_OK(cudaGetLastError());
-    count_launches(1);
-  }
-  return ADMMQ_OK;
+  if (ny > 128) return mttkrp_foldlong_gemm(V, ldx, M, ny, Xt, XtLo, ldx, R, nx, Y, F, partial, stream);
+  return gemm_nt(V, ldx, M, Xt, XtLo, ldx, R, nx, F, R, stream);   // matrix case: F = W . X
 }
 
 }  // namespace admmq

@@ -1,6 +1,7 @@
 // tc_gemm.cu - C = A . B^T in 3xTF32 on tcgen05 (admmq_gemm_nt), the stand-alone form of the tile product that
 // the persistent ADMM loop uses for its ridge product and that the tensor-core MTTKRP builds on.
 #include <algorithm>
+#include <cstdlib>
 #include "tc_gemm.cuh"
 
 namespace admmq {
@@ -82,24 +83,26 @@ k_gemm_nt_tc(const __grid_constant__ GemmMaps maps, int M, int N, int K, float* 
 // and T never goes to global memory.  float64 accumulation over y like the stand-alone fold kernel.
 template <int BN>
 __global__ void __launch_bounds__(tc::kThreadsTC, 1)
-k_mttkrp_fold_tc(const __grid_constant__ GemmMaps maps, int Mout, int ny, int N, int K, const float* __restrict__ Y,
+k_mttkrp_fold_tc(const __grid_constant__ GemmMaps maps, int Mout, int ny, int N, int K, int bn, const float* __restrict__ Y,
                  float* __restrict__ F, float neg_zero) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ tc::Pipe pipe;
   tc::PipeState st;
   tc::pipe_setup(pipe, st, neg_zero);
   const int mg = tc::kTileM / ny;  // m per tile
-  const int tilesM = (Mout + mg - 1) / mg, tilesN = (N + BN - 1) / BN;
+  // bn <= BN (a multiple of 16) is the tile width actually computed: chosen on the host so that the tiles fill whole
+  // waves of the grid (37 x 12 tiles of width 96 are exactly 3 waves of 148 for 512 x 512 x 9 at R = 1141)
+  const int tilesM = (Mout + mg - 1) / mg, tilesN = (N + bn - 1) / bn;
   for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
-    const int m0 = (tile / tilesN) * mg, n0 = (tile % tilesN) * BN;
+    const int m0 = (tile / tilesN) * mg, n0 = (tile % tilesN) * bn;
     const int next = tile + (int)gridDim.x;
     const bool has_next = next < tilesM * tilesN;
-    tc::tile_3xtf32<BN, true>(&maps.a, m0 * ny, &maps.b, &maps.blo, n0, BN, K, smem_dyn, pipe, st,
-                              has_next ? (next / tilesN) * mg * ny : -1, has_next ? (next % tilesN) * BN : -1);
+    tc::tile_3xtf32<BN, true>(&maps.a, m0 * ny, &maps.b, &maps.blo, n0, bn, K, smem_dyn, pipe, st,
+                              has_next ? (next / tilesN) * mg * ny : -1, has_next ? (next % tilesN) * bn : -1);
     const float* tile_c = tc::acc_to_smem<BN, true>(pipe, smem_dyn);
     using ET = tc::EpiTile<BN>;
-    for (int idx = threadIdx.x; idx < mg * BN; idx += tc::kThreadsTC) {
-      const int ml = idx / BN, c = idx - ml * BN;
+    for (int idx = threadIdx.x; idx < mg * bn; idx += tc::kThreadsTC) {
+      const int ml = idx / bn, c = idx - ml * bn;
       const int m = m0 + ml, n = n0 + c;
       if (m < Mout && n < N) {
         double acc = 0.0;
@@ -111,6 +114,75 @@ k_mttkrp_fold_tc(const __grid_constant__ GemmMaps maps, int Mout, int ny, int N,
     __syncthreads();
   }
   tc::pipe_teardown(pipe);
+}
+
+// The same contraction when the folded index is LONG (ny > 128: the tap factor of a convolution, F (9 x R) folded over the
+// 512 input channels): a 128-row tile of A covers rows (m, y) of at most two consecutive m.  The tile folds its rows
+// with their weights Y[y, n] into two float64 partial sums per column (slot 0: the tile's first m, slot 1: the next
+// one), written to partial[(tile_row * 2 + slot) * N + n]; k_fold_partials adds the partials of every m in tile order.
+// The intermediate T = A . B^T (M * ny x N floats: 21 MB for 9 x 512 x 1141) never exists.
+template <int BN>
+__global__ void __launch_bounds__(tc::kThreadsTC, 1)
+k_mttkrp_foldlong_tc(const __grid_constant__ GemmMaps maps, int rows, int ny, int N, int K, int bn, const float* __restrict__ Y,
+                     double* __restrict__ partial, float neg_zero) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ tc::Pipe pipe;
+  tc::PipeState st;
+  tc::pipe_setup(pipe, st, neg_zero);
+  const int tilesM = (rows + tc::kTileM - 1) / tc::kTileM, tilesN = (N + bn - 1) / bn;
+  for (int tile = blockIdx.x; tile < tilesM * tilesN; tile += gridDim.x) {
+    const int tr = tile / tilesN, r0 = tr * tc::kTileM, n0 = (tile % tilesN) * bn;
+    const int next = tile + (int)gridDim.x;
+    const bool has_next = next < tilesM * tilesN;
+    tc::tile_3xtf32<BN, true>(&maps.a, r0, &maps.b, &maps.blo, n0, bn, K, smem_dyn, pipe, st,
+                              has_next ? (next / tilesN) * tc::kTileM : -1, has_next ? (next % tilesN) * bn : -1);
+    const float* tile_c = tc::acc_to_smem<BN, true>(pipe, smem_dyn);
+    using ET = tc::EpiTile<BN>;
+    const int m_first = r0 / ny;
+    // thread -> (column c, quarter q): the four quarters of a column are neighbouring lanes and take rows q, q + 4, ...
+    // (consecutive rows sit in different swizzle positions of the staging tile: no bank conflicts), summed in fixed
+    // order ((q0 + q1) + (q2 + q3)) with two shuffles - the tile leaves no room for another shared-memory array
+    const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
+    static_assert(BN * 4 == tc::kThreadsTC, "one thread per (column, quarter)");
+    double a0 = 0.0, a1 = 0.0;
+    const bool col_ok = c < bn && n0 + c < N;
+    if (col_ok) {
+      for (int i = 0; i < tc::kTileM / 4; ++i) {
+        const int rr = i * 4 + q, r = r0 + rr;
+        if (r < rows) {
+          const int m = r / ny, y = r - m * ny;
+          const double v = (double)__ldg(Y + (size_t)y * N + n0 + c) * (double)tile_c[ET::offset(rr, c >> 2) + (c & 3)];
+          if (m == m_first) a0 += v;
+          else a1 += v;
+        }
+      }
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    if (col_ok && q == 0) {
+      partial[((size_t)tr * 2 + 0) * N + n0 + c] = a0;
+      partial[((size_t)tr * 2 + 1) * N + n0 + c] = a1;
+    }
+    __syncthreads();
+  }
+  tc::pipe_teardown(pipe);
+}
+
+// F[m, n] = sum over the row tiles that hold rows of m, in tile order (fixed: deterministic)
+__global__ void __launch_bounds__(256) k_fold_partials(const double* __restrict__ partial, int M, int ny, int N, float* __restrict__ F) {
+  const long long tot = (long long)M * N;
+  for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < tot; o += (long long)gridDim.x * 256) {
+    const int m = (int)(o / N), n = (int)(o - (long long)m * N);
+    const int t_first = (int)(((long long)m * ny) / tc::kTileM), t_last = (int)(((long long)(m + 1) * ny - 1) / tc::kTileM);
+    double acc = 0.0;
+    for (int t = t_first; t <= t_last; ++t) {
+      const int slot = m - (int)(((long long)t * tc::kTileM) / ny);   // 0 or 1 (ny > 128: a tile spans at most two m)
+      acc += partial[((size_t)t * 2 + slot) * N + n];
+    }
+    F[o] = (float)acc;
+  }
 }
 
 template <int BN, bool PS>
@@ -180,18 +252,24 @@ int mttkrp_fold_gemm(const float* V, int ldv, int Mout, int ny, const float* B, 
   if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "the tensor-core MTTKRP needs an sm_100 device (tcgen05)");
   const int mg = tc::kTileM / ny;
   const long long tilesM = (Mout + mg - 1) / mg;
+  // tile width: any multiple of 16 up to 128; a tile costs a fixed part (pipeline fill, epilogue, fold) worth ~40
+  // columns at K = 512 plus bn columns of tensor-core work: minimise waves * (kFoldFixed + bn), ties to the wider tile
+  constexpr int kFoldFixed = 40;
   int bn = 64;
   {
     long long best = -1;
-    const int widths[2] = {128, 64};
-    for (int w = 0; w < 2; ++w) {
-      const long long tiles_w = tilesM * ((N + widths[w] - 1) / widths[w]);
-      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (16 + widths[w]);
+    for (int w = 128; w >= 16; w -= 16) {
+      const long long tiles_w = tilesM * ((N + w - 1) / w);
+      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (kFoldFixed + w);
       if (best < 0 || cost < best) {
         best = cost;
-        bn = widths[w];
+        bn = w;
       }
     }
+  }
+  if (const char* force = getenv("ADMMQ_FOLD_BN")) {  // experiment knob
+    const int w = atoi(force);
+    if (w >= 16 && w <= 128 && (w & 15) == 0) bn = w;
   }
   const long long tiles = tilesM * ((N + bn - 1) / bn);
   const int grid = (int)std::min<long long>(tiles, dp.sm_count);
@@ -199,17 +277,61 @@ int mttkrp_fold_gemm(const float* V, int ldv, int Mout, int ny, const float* B, 
   if (int e = tc::make_operand_tmap(&maps.a, V, Mout * ny, K, ldv, tc::kTileM)) return e;
   if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
   if (int e = tc::make_operand_tmap(&maps.blo, Blo, N, K, ldb, bn)) return e;
-  if (bn == 128) {
+  if (bn > 64) {
     const int smem = tc::TileSmem<128, true>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mttkrp_fold_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_mttkrp_fold_tc<128><<<grid, tc::kThreadsTC, smem, stream>>>(maps, Mout, ny, N, K, Y, F, -0.0f);
+    k_mttkrp_fold_tc<128><<<grid, tc::kThreadsTC, smem, stream>>>(maps, Mout, ny, N, K, bn, Y, F, -0.0f);
   } else {
     const int smem = tc::TileSmem<64, true>::kBytes;
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mttkrp_fold_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_mttkrp_fold_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, Mout, ny, N, K, Y, F, -0.0f);
+    k_mttkrp_fold_tc<64><<<grid, tc::kThreadsTC, smem, stream>>>(maps, Mout, ny, N, K, bn, Y, F, -0.0f);
   }
   ADMMQ_CUDA_OK(cudaGetLastError());
   count_launches(1);
+  return ADMMQ_OK;
+}
+
+size_t mttkrp_foldlong_partial_bytes(int Mout, int ny, int N) {
+  const long long rows = (long long)Mout * ny;
+  return (size_t)((rows + tc::kTileM - 1) / tc::kTileM) * 2 * (size_t)N * sizeof(double);
+}
+
+// F (Mout x N) = fold_y( V ((Mout * ny) x K) . B^T , Y ) for ny > 128, see k_mttkrp_foldlong_tc; partial: workspace of
+// mttkrp_foldlong_partial_bytes
+int mttkrp_foldlong_gemm(const float* V, int ldv, int Mout, int ny, const float* B, const float* Blo, int ldb, int N, int K,
+                         const float* Y, float* F, double* partial, cudaStream_t stream) {
+  if (ny <= tc::kTileM) return fail(ADMMQ_E_UNSUPPORTED, "mttkrp_foldlong_gemm: ny must exceed 128");
+  DeviceProps dp;
+  if (int e = device_props(&dp)) return e;
+  if (dp.cc_major != 10) return fail(ADMMQ_E_UNSUPPORTED, "the tensor-core MTTKRP needs an sm_100 device (tcgen05)");
+  const int rows = Mout * ny;
+  const long long tilesM = (rows + tc::kTileM - 1) / tc::kTileM;
+  constexpr int kFoldFixed = 40;
+  int bn = 128;
+  {
+    long long best = -1;
+    for (int w = 128; w >= 80; w -= 16) {   // the fold maps one thread to one column of a 128-wide staging tile
+      const long long tiles_w = tilesM * ((N + w - 1) / w);
+      const long long cost = ((tiles_w + dp.sm_count - 1) / dp.sm_count) * (kFoldFixed + w);
+      if (best < 0 || cost < best) {
+        best = cost;
+        bn = w;
+      }
+    }
+  }
+  const long long tiles = tilesM * ((N + bn - 1) / bn);
+  const int grid = (int)std::min<long long>(tiles, dp.sm_count);
+  GemmMaps maps;
+  if (int e = tc::make_operand_tmap(&maps.a, V, rows, K, ldv, tc::kTileM)) return e;
+  if (int e = tc::make_operand_tmap(&maps.b, B, N, K, ldb, bn)) return e;
+  if (int e = tc::make_operand_tmap(&maps.blo, Blo, N, K, ldb, bn)) return e;
+  const int smem = tc::TileSmem<128, true>::kBytes;
+  ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_mttkrp_foldlong_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_mttkrp_foldlong_tc<128><<<grid, tc::kThreadsTC, smem, stream>>>(maps, rows, ny, N, K, bn, Y, partial, -0.0f);
+  const long long tot = (long long)Mout * N;
+  k_fold_partials<<<(int)std::min<long long>((tot + 255) / 256, 148 * 4), 256, 0, stream>>>(partial, Mout, ny, N, F);
+  ADMMQ_CUDA_OK(cudaGetLastError());
+  count_launches(2);
   return ADMMQ_OK;
 }
 

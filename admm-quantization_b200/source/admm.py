@@ -15,10 +15,11 @@ def squared_relative_diff(X, Y):
     return torch.sqrt(torch.sum((X - Y) ** 2) / torch.sum(X ** 2)).item()
 
 
-def init_factors(tensor, rank, init='random', device=None, seed=None):
+def init_factors(tensor, rank, init='random', device=None, seed=None, rng=None):
     """reference source/admm.py:21-48.  'random' and 'svd' draw from a torch.Generator on `device`
     exactly like the reference; 'parafac' / 'parafac-epc' run the restated ALS / ALS+EPC
-    (source/parafac_epc.py) because tensorly/musco are third-party packages."""
+    (source/parafac_epc.py) because tensorly/musco are third-party packages.  `rng` (optional numpy RandomState, an
+    addition to the reference signature) replaces numpy's global stream for the 'parafac-epc' start."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
 
@@ -39,7 +40,7 @@ def init_factors(tensor, rank, init='random', device=None, seed=None):
                                  normalize_factors=False, dtype=torch.float32)
     elif init == 'parafac-epc':
         from .parafac_epc import parafac_epc
-        _, factors = parafac_epc(tensor, rank=rank, init='random', als_maxiter=50, epc_maxiter=50)
+        _, factors = parafac_epc(tensor, rank=rank, init='random', als_maxiter=50, epc_maxiter=50, rng=rng)
         factors = [f.to(dtype=torch.float) for f in factors]
     else:
         raise NotImplementedError(init)

@@ -184,11 +184,14 @@ def _intensities(factors):
 
 def parafac_epc(tensor, rank, als_maxiter=5000, als_tol=1e-5, num_threads=4, init="random",
                 epc_maxiter=5000, epc_rounds=50, epc_tol=1e-5, stop_tol=1e-4, ratio_tol=1e-3,
-                ratio_max_iters=10, info=None):
+                ratio_max_iters=10, info=None, rng=None):
     """reference source/parafac_epc.py:12-82.  Returns (lmbda, Us) with Us in the ORIGINAL mode order,
     float64, on the device of `tensor`.  `num_threads` is accepted for signature compatibility; the
     reference's `torch.set_num_threads` (:33) is a CPU-side global side effect that has no GPU meaning.
-    `info` (a dict, optional) receives delta, the pass counts and the seconds spent in ALS and EPC."""
+    `info` (a dict, optional) receives delta, the pass counts and the seconds spent in ALS and EPC.  `rng` (optional
+    numpy RandomState) replaces numpy's GLOBAL stream, which tensorly's random ALS start draws from (:42-43 pass no
+    random_state): a driver that initialises several layers concurrently gives every layer RandomState(seed), the stream
+    a fresh process gets from `np.random.seed(seed)` (scripts/factorize.py:21-24)."""
     import time
     if init != "random":
         raise NotImplementedError(init)
@@ -197,7 +200,7 @@ def parafac_epc(tensor, rank, als_maxiter=5000, als_tol=1e-5, num_threads=4, ini
     Y = tensor.detach().to(device=dev, dtype=torch.float64)                 # :36
     order = np.argsort(Y.shape)                                             # :38
     T = _Tensor(Y.permute(tuple(int(o) for o in order)).contiguous())       # :40
-    weights, factors = _als(T, rank, als_maxiter, als_tol, np.random.mtrand._rand, True)   # :42-43
+    weights, factors = _als(T, rank, als_maxiter, als_tol, np.random.mtrand._rand if rng is None else rng, True)   # :42-43
     delta = float(torch.linalg.norm(T.Y - _reconstruct(weights, factors)))  # :51
     lam_prev_norm = float(torch.linalg.norm(weights))                       # :52
     factors[-1] = (factors[-1] * weights).contiguous()                      # :53

@@ -328,3 +328,75 @@ def test_als_epc_initialisation_on_native_kernels(capsys):
               f"64x64x9 R=134: delta/||Y|| = {delta / math.sqrt(T.norm2):.4f} preserved over 12 EPC passes, "
               f"sum(lambda^2) {first:.1f} -> {prev:.1f}; small case: ALS {info['als_s'] * 1e3:.0f} ms, EPC {info['epc_s'] * 1e3:.0f} ms "
               f"({info['epc_passes']} passes)")
+
+
+# ------------------------------------------------------------------ thread-block-cluster loop for small factors
+def test_cluster_loop_for_small_factors(nat, capsys):
+    """csrc/admm_loop_cluster.cuh: a small factor on a cluster of 4 / 8 CTAs (rows and clip candidates split,
+    exchange through distributed shared memory, two cluster barriers per iteration with a deferred exit test): H, U,
+    codes and iteration counts are bit-identical whatever the cluster size; against the shared-memory-resident
+    single-CTA kernel (float32 FMAs instead of the cluster's float64-accumulated product) they agree to rounding over
+    the first iterations; same NaN semantics and exit test; per-iteration time printed."""
+    from oracle import admm_oracle as orc
+    g = torch.Generator().manual_seed(77)
+    lines = []
+
+    def close_frac(a, b):
+        return float(((a - b).abs() <= 1e-4 * float(b.abs().max())).float().mean())
+
+    for (I, R, bits, qs, iters) in [(64, 134, 4, MSE, 60), (9, 134, 4, MSE, 60), (64, 134, 3, MSE, 25), (48, 100, 8, "tensor_minmax", 25),
+                                    (64, 134, 4, "tensor_affine", 25), (33, 77, 4, MSE, 40), (7, 20, 2, MSE, 30)]:
+        Bf, Cf = torch.randn(64, R, generator=g), torch.randn(9, R, generator=g)
+        G = ((Bf.T @ Bf) * (Cf.T @ Cf)).cuda()
+        F = (torch.randn(I, R, generator=g) * 24).cuda()
+        H0 = torch.randn(I, R, generator=g).cuda()
+        U0 = (torch.randn(I, R, generator=g) * 0.1).cuda()
+        for n_it in (3, iters):
+            outs = []
+            for ctas in (1, 4, 8, 0):
+                H, U = H0.clone(), U0.clone()
+                codes = torch.empty(I, R, dtype=torch.int8, device="cuda")
+                rep = nat.read_report(nat.admm_iteration_inplace(H, U, F, G, n_it + 1, 1e-8, bits, qs, codes=codes, precision=2, max_ctas=ctas))
+                assert rep.iterations == n_it
+                outs.append((H, U, codes, rep.scale, rep.best_index))
+            for o in outs[2:]:   # clusters of 4, 8 and "every SM" (= 8): bit-identical
+                assert o[4] == outs[1][4] and o[3] == outs[1][3], (I, R, qs)
+                assert torch.equal(o[0], outs[1][0]) and torch.equal(o[1], outs[1][1]) and torch.equal(o[2], outs[1][2]), (I, R, bits, qs)
+            if n_it == 3:        # single-CTA kernel: the same recipe up to the rounding of the ridge product
+                assert close_frac(outs[1][0], outs[0][0]) >= 0.999, (I, R, bits, qs)
+    # the exit test fires at the same iteration (huge eps: after the first iteration), degenerate input -> NaN + status
+    I, R = 64, 134
+    Bf = torch.randn(64, R, generator=g)
+    G = (Bf.T @ Bf).cuda()
+    F = (torch.randn(I, R, generator=g) * 24).cuda()
+    H0 = torch.randn(I, R, generator=g).cuda()
+    for ctas in (1, 8):
+        H, U = H0.clone(), torch.zeros_like(H0)
+        rep = nat.read_report(nat.admm_iteration_inplace(H, U, F, G, 50, 1e30, 4, MSE, precision=2, max_ctas=ctas))
+        assert rep.iterations == 1 and rep.status & nat.ST_CONVERGED
+        if ctas == 1:
+            ref = (H.clone(), U.clone())
+        else:
+            assert close_frac(H, ref[0]) >= 0.9999 and close_frac(U, ref[1]) >= 0.999
+        Z = torch.zeros(I, R).cuda()
+        Hz, Uz = Z.clone(), Z.clone()
+        rep = nat.read_report(nat.admm_iteration_inplace(Hz, Uz, Z.clone(), G, 5, 1e-8, 4, MSE, precision=2, max_ctas=ctas))
+        assert rep.status & nat.ST_NONFINITE and torch.isnan(Hz).all()
+    # against the CPU oracle, one step from identical state
+    Ho, Uo, _ = orc.admm_iteration(H0.cpu().clone(), torch.zeros(I, R), F.cpu(), G.cpu(), 2, 1e-8, 4, MSE)
+    H, U = H0.clone(), torch.zeros_like(H0)
+    nat.admm_iteration_inplace(H, U, F, G, 2, 1e-8, 4, MSE, precision=2, max_ctas=8)
+    close = float(((H.cpu() - Ho).abs() <= 1e-4 * float(Ho.abs().max())).float().mean())
+    assert close >= 0.9999, close
+    # timing
+    for (I, R) in ((64, 134), (9, 134)):
+        F = (torch.randn(I, R, generator=g) * 24).cuda()
+        H0 = torch.randn(I, R, generator=g).cuda()
+        for ctas in (1, 4, 8):
+            H, U = H0.clone(), torch.zeros_like(H0)
+            rep = nat.read_report(nat.admm_iteration_inplace(H, U, F, G, 301, 1e-8, 4, MSE, precision=2, max_ctas=ctas))
+            lines.append(f"{I} x {R} on {ctas} CTA(s): {rep.phase_ns[3] / 1e3 / rep.iterations:.2f} us per iteration "
+                         f"(P1 {rep.phase_ns[0] / 1e3 / rep.iterations:.2f}, P2 {rep.phase_ns[1] / 1e3 / rep.iterations:.2f}, "
+                         f"P3 {rep.phase_ns[2] / 1e3 / rep.iterations:.2f})")
+    with capsys.disabled():
+        print("\n[cluster] " + "\n[cluster] ".join(lines))
