@@ -147,12 +147,27 @@ k_mttkrp_foldlong_tc(const __grid_constant__ GemmMaps maps, int rows, int ny, in
     double a0 = 0.0, a1 = 0.0;
     const bool col_ok = c < bn && n0 + c < N;
     if (col_ok) {
-      for (int i = 0; i < tc::kTileM / 4; ++i) {
-        const int rr = i * 4 + q, r = r0 + rr;
-        if (r < rows) {
-          const int m = r / ny, y = r - m * ny;
-          const double v = (double)__ldg(Y + (size_t)y * N + n0 + c) * (double)tile_c[ET::offset(rr, c >> 2) + (c & 3)];
-          if (m == m_first) a0 += v;
+      // rows q, q + 4, ... of the tile: (m, y) advance without a division; the weights Y[y, n] of eight rows are
+      // requested before the first use (they come from L2: one round trip per batch instead of one per row)
+      const int y_first = r0 - m_first * ny;          // y of the tile's first row
+      const float* ycol = Y + n0 + c;
+      constexpr int kB = 8;
+      for (int i0 = 0; i0 < tc::kTileM / 4; i0 += kB) {
+        float w[kB];
+        int slot[kB];
+#pragma unroll
+        for (int b = 0; b < kB; ++b) {
+          const int rr = (i0 + b) * 4 + q;
+          int y = y_first + rr;
+          slot[b] = y >= ny ? 1 : 0;
+          if (y >= ny) y -= ny;
+          w[b] = (r0 + rr < rows) ? __ldg(ycol + (size_t)y * N) : 0.0f;
+        }
+#pragma unroll
+        for (int b = 0; b < kB; ++b) {
+          const int rr = (i0 + b) * 4 + q;
+          const double v = (double)w[b] * (double)tile_c[ET::offset(rr, c >> 2) + (c & 3)];
+          if (slot[b] == 0) a0 += v;
           else a1 += v;
         }
       }

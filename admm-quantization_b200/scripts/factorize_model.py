@@ -88,7 +88,7 @@ def main(argv=None):
     t0 = time.time()
     mine = [u for u, o in zip(units, owner) if o == rank]
     for u in mine:
-        u["cost"] = wl.solve_cost(u["shape"], u["rank"]) * (1.0 + ((1 << u["bits"]) - 1) / 60.0)
+        u["cost"] = wl.unit_cost(u["shape"], u["rank"], u["bits"])
     mine.sort(key=lambda u: -u["cost"])
     results = {}
     wdev = {}

@@ -9,7 +9,7 @@ tests).  Because no arithmetic crosses a shard boundary, N-GPU results are bitwi
 import torch
 import torch.distributed as dist
 
-from .workloads import lpt_assign, solve_cost
+from .workloads import lpt_assign, unit_cost
 
 
 def world():
@@ -19,8 +19,8 @@ def world():
 
 
 def shard_units(units, world_size):
-    """units: list of dicts with 'shape' and 'rank' (and optionally 'num_attempts').  Returns the owner rank of each."""
-    costs = [solve_cost(u["shape"], u["rank"], u.get("num_attempts", 200)) for u in units]
+    """units: list of dicts with 'shape' and 'rank' (and optionally 'bits', 'num_attempts').  Returns the owner rank of each."""
+    costs = [unit_cost(u["shape"], u["rank"], u.get("bits", 4), u.get("num_attempts", 200)) for u in units]
     return lpt_assign(costs, world_size)
 
 

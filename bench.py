@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--cpu-budget-s", type=float, default=15.0, help="CPU seconds for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity-leg", action="store_true",
+                    help="skip the one-step measurement of the same workload in the parity mode (precision 0: FP64 pipe, ~10x slower)")
     ap.add_argument("--no-eager-reference", action="store_true",
                     help="skip the informative second bar: the reference's own Python run eagerly on this GPU")
     ap.add_argument("--mttkrp-precision", type=int, default=1,
@@ -382,7 +384,7 @@ def shard(args, units, rk):
     if args.seed_replicas or rk.world == 1:
         return [rk.rank] * len(units)
     from source.distributed import shard_units
-    return shard_units([{"shape": unit_shape(u), "rank": unit_rank(u)} for u in units], rk.world)
+    return shard_units([{"shape": unit_shape(u), "rank": unit_rank(u), "bits": u[7]} for u in units], rk.world)
 
 
 def run_native(args):
@@ -631,6 +633,39 @@ def run_native(args):
                                   "sweep_ms": sweep_ms, "per_unit_inner_iter_per_s": per_layer, "early": early,
                                   "nonfinite": nonfinite, "launches": launches, "gather_bytes": gather_bytes,
                                   "rec_error": {p[0]: round(e[0], 6) for p, e in zip(problems, errs)}})
+    # ---- the same sweep in the PARITY mode (precision 0: float64 ridge product against the float64 inverse, float64-
+    # accumulating MTTKRP) - the mode the bit-level claims are made in; one warm-up + one timed step, same SM budgets
+    parity = None
+    if world == 1 and args.solve_precision != 0 and not args.no_parity_leg and streams is not None:
+        psolvers = [LayerSolver(W.to(dev), [f.to(dev) for f in init], bits, QSCHEME, max_iter_admm=args.max_iter_admm,
+                                mttkrp_precision=0, solve_precision=0, max_ctas=g)
+                    for (key, W, rnk, init, bits), g in zip(problems, budgets)]
+        times = []
+        for _ in range(2):
+            flush.fill_(1)
+            main = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            joins = []
+            for s, st in zip(psolvers, streams):   # fork every stream from e0, join them all afterwards
+                st.wait_event(e0)
+                with torch.cuda.stream(st):
+                    s.enqueue_sweep()
+                    j = torch.cuda.Event()
+                    j.record(st)
+                joins.append(j)
+            for j in joins:
+                main.wait_event(j)
+            e1.record(main)
+            for s in psolvers:
+                s.collect()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        pdone = sum(int(r.iterations) for s in psolvers for r in s.last_reports)
+        parity = {"solve_precision": 0, "mttkrp_precision": 0, "ms_per_step": times[-1], "value": pdone / (times[-1] / 1e3),
+                  "unit": UNIT, "steps": 1, "warmup": 1,
+                  "note": "same workload and SM budgets in the parity mode (second sweep of a fresh run)"}
+        del psolvers
     cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = reference_sample(args, units, args.cpu_budget_s, "cpu")
@@ -668,7 +703,7 @@ def run_native(args):
                                                                        "tests/golden/early_exit.npz)",
                                                    "loops_nonfinite": sum(pr["nonfinite"] for pr in per_rank)}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": sum(pr["launches"] for pr in per_rank), "roofline": roofline,
-                "cpu_baseline": cpu, "reference_eager_b200": eager,
+                "cpu_baseline": cpu, "reference_eager_b200": eager, "parity_mode": parity,
                 "per_unit_inner_iter_per_s": {k: v for pr in per_rank for k, v in pr["per_unit_inner_iter_per_s"].items()},
                 "per_unit_sweep_ms_last_step": {k: v for pr in per_rank for k, v in pr["sweep_ms"].items()},
                 "per_rank_ms_per_step": [round(pr["ms_per_step"], 2) for pr in per_rank],
@@ -699,7 +734,7 @@ def run_sweep256(args, rk, units, owner, mine, desc, sm_count):
         rnk = wl.rank_from_reduction_rate(W, rr)
         init = wl.random_init(W.shape, rnk, 42)
         jobs.append({"key": key, "Wh": W, "rank": rnk, "bits": bits, "init": init,
-                     "cost": wl.solve_cost(W.shape, rnk) * (1.0 + ((1 << bits) - 1) / 60.0)})
+                     "cost": wl.unit_cost(W.shape, rnk, bits)})
     jobs.sort(key=lambda j: -j["cost"])
     rounds = [jobs[i:i + args.round_size] for i in range(0, len(jobs), args.round_size)]
     wdev = {n: w.to(dev) for n, w in weights.items()}
