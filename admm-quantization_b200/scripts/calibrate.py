@@ -1,7 +1,7 @@
 """Factor files -> CP model -> BN calibration -> top-1: the consumer side of scripts/factorize.py
 (reference scripts/calibrate.py:151-189 + source/utils.py:134-155), on SYNTHETIC images because neither ImageNet nor
 pretrained checkpoints exist offline: the model is torchvision's architecture with seeded random weights
-(the same weights scripts/factorize.py falls back to), images are standard normal, labels are the original model's
+(the weights scripts/factorize.py factorizes with `--weights random`), images are standard normal, labels are the original model's
 own predictions.
 
     python admm-quantization_b200/scripts/calibrate.py --model-name resnet18 --method admm --init random \

@@ -57,12 +57,16 @@ def parse_args(argv=None):
     parser.add_argument("--seed", required=True, type=int, help="Random seed.")
     parser.add_argument("--qscheme", required=True, type=str, help="[tensor_mseminmax_symmetric, tensor_minmax]")
     # additions (defaults reproduce the reference's hard-coded values)
-    parser.add_argument("--weights", default="random", choices=["random", "pretrained"])
+    parser.add_argument("--weights", default="pretrained", choices=["pretrained", "random"],
+                        help="pretrained (default, what the reference loads: `resnet18(pretrained=True)`): fails loudly when the "
+                             "checkpoint is neither cached nor downloadable; random: the architecture's own initialisation "
+                             "(must be asked for explicitly - the output directory is then tagged `_randomweights`)")
     parser.add_argument("--weight-file", default=None, help=".pt file holding the layer's weight tensor or a state_dict")
     parser.add_argument("--eps", type=float, default=1e-8)
     parser.add_argument("--tol", type=float, default=1e-5)
     parser.add_argument("--num-attempts", type=int, default=200)
-    parser.add_argument("--solve-precision", type=int, default=0, help="0 float32 FFMA (parity), 1 3xTF32 tcgen05")
+    parser.add_argument("--solve-precision", type=int, default=0,
+                        help="0 parity mode (float64 product with the float64 inverse), 1 3xTF32 tcgen05, 2 float32 FFMA")
     parser.add_argument("--outdir", default=None)
     args = parser.parse_args(argv)
     if args.rank is None and args.reduction_rate is None:
@@ -82,7 +86,16 @@ def load_weight(args):
         raise ValueError(f"unrecognized model name: {args.model_name}")
     import torchvision
     ctor = getattr(torchvision.models, args.model_name)
-    model = ctor(weights="DEFAULT") if args.weights == "pretrained" else ctor(weights=None)
+    if args.weights == "pretrained":
+        try:
+            model = ctor(weights="DEFAULT")
+        except Exception as e:  # noqa: BLE001 - no network / no cached checkpoint: never fall back to random weights silently
+            raise RuntimeError(f"could not load the pretrained {args.model_name} checkpoint ({type(e).__name__}: {e}); pass "
+                               "--weight-file with a local checkpoint, or --weights random to factorize the architecture's "
+                               "random initialisation on purpose") from e
+    else:
+        print("WARNING: --weights random: factorizing RANDOMLY INITIALISED weights (not the reference's pretrained model)")
+        model = ctor(weights=None)
     layer = model
     for attr in args.layer.split("."):
         layer = layer[int(attr)] if attr.isdigit() else getattr(layer, attr)
@@ -107,6 +120,8 @@ def main(argv=None):
     if args.rank is None:
         args.rank = int(weight.numel() / sum(list(weight.shape)) / args.reduction_rate)
     outdir = args.outdir or f"{args.bits}bit_{args.qscheme}/factors_{args.method}_seed{args.seed}"
+    if args.outdir is None and args.weights == "random" and args.weight_file is None:
+        outdir += "_randomweights"   # never under the reference's name: calibrate.py would score meaningless factors
     os.makedirs(outdir, exist_ok=True)
     fileprefix = f"{args.layer}_{args.method}_{args.init}_rank_{args.rank}"
     run = None

@@ -813,7 +813,8 @@ def test_factorize_cli_writes_the_reference_file_set(tmp_path, monkeypatch):
     fz = load("factorize")
     err, errq = fz.main(["--model-name", "resnet18", "--method", "admm", "--init", "random", "--layer", "layer1.0.conv1",
                          "--reduction-rate", "2", "--bits", "4", "--qscheme", MSE, "--seed", "42",
-                         "--max_iter_als", "2", "--max_iter_admm", "20"])
+                         "--max_iter_als", "2", "--max_iter_admm", "20", "--weights", "random",
+                         "--outdir", f"4bit_{MSE}/factors_admm_seed42"])
     d = tmp_path / f"4bit_{MSE}" / "factors_admm_seed42"
     names = sorted(p.name for p in d.iterdir())
     prefix = "layer1.0.conv1_admm_random_rank_134_"
@@ -825,6 +826,20 @@ def test_factorize_cli_writes_the_reference_file_set(tmp_path, monkeypatch):
     assert len(hist) == 2 and 0.5 < hist[-1] < 1.0 and abs(err - hist[-1]) < 1e-3 and abs(errq - err) < 1e-2
     with pytest.raises(SystemExit):
         fz.parse_args(["--model-name", "resnet18"])                       # required flags (:38-102)
+    # the reference loads the PRETRAINED model: that is the default, and without network / cache it fails loudly instead
+    # of factorizing random weights under the reference's file names
+    base = ["--model-name", "resnet18", "--method", "admm", "--layer", "layer1.0.conv1", "--reduction-rate", "2", "--bits", "4",
+            "--qscheme", MSE, "--seed", "42"]
+    assert fz.parse_args(base).weights == "pretrained"
+    try:
+        import torchvision
+        torchvision.models.resnet18(weights="DEFAULT")
+        have_checkpoint = True
+    except Exception:  # noqa: BLE001
+        have_checkpoint = False
+    if not have_checkpoint:
+        with pytest.raises(RuntimeError, match="pretrained"):
+            fz.main(base + ["--max_iter_als", "1", "--max_iter_admm", "5"])
     acc = load("calibrate").main(["--bits", "4", "--qscheme", MSE, "--seed", "42", "--layers", "layer1.0.conv1",
                                   "--eval-batches", "2", "--batch-size", "16", "--calibration-samples", "32"])
     assert 0.0 <= acc <= 100.0
