@@ -1060,21 +1060,28 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     // tensor-core work; minimise waves * (kTileFixed + bn), ties go to the wider tile
     int tcbn = kLoopPS ? 128 : 64;
     {
+      // widths above 128 (one accumulator, shallower raw ring: ~5 % dearer per column) exist for the wave structure:
+      // 4 x 8 tiles of width 144 cover 512 x 1141 in ONE wave on 32 .. 35 CTAs where 4 x 9 of width 128 need two
       long long best = -1;
-      for (int bn = (kLoopPS ? 128 : 64); bn >= 16; bn -= 16) {
+      for (int bn = (kLoopPS ? 160 : 64); bn >= 16; bn -= 16) {
         const long long tiles = (long long)tilesM * ((R + bn - 1) / bn);
-        const long long cost = ((tiles + grid - 1) / grid) * (kTileFixed + bn);
+        const long long cost = ((tiles + grid - 1) / grid) * (kTileFixed + bn) * (bn > 128 ? 105 : 100);
         if (best < 0 || cost < best) {
           best = cost;
           tcbn = bn;
         }
       }
+      static const int force_bn = getenv("ADMMQ_LOOP_BN") ? atoi(getenv("ADMMQ_LOOP_BN")) : 0;   // experiment knob
+      if (force_bn >= 16 && force_bn <= (kLoopPS ? 160 : 64) && (force_bn & 15) == 0) tcbn = force_bn;
     }
     p.tc_bn = tcbn;
     if (int e = tc::make_operand_tmap(&p.tm_rhs, p.RHS, I, R, l.Rp, tc::kTileM)) return e;
     if (int e = tc::make_operand_tmap(&p.tm_minv_hi, kLoopPS ? p.MinvHi : Minv, R, R, l.Rp, tcbn)) return e;
     if (int e = tc::make_operand_tmap(&p.tm_minv_lo, kLoopPS ? p.MinvLo : Minv, R, R, l.Rp, tcbn)) return e;
-    if (tcbn > 64) {
+    if (tcbn > 128) {
+      fn = (const void*)k_admm_loop<16, 32, 1, 2, (kLoopPS ? 160 : 64)>;
+      smem = sizeof(LoopSmem<16, 32, (kLoopPS ? 160 : 64)>);
+    } else if (tcbn > 64) {
       fn = (const void*)k_admm_loop<16, 32, 1, 2, (kLoopPS ? 128 : 64)>;
       smem = sizeof(LoopSmem<16, 32, (kLoopPS ? 128 : 64)>);
     } else if (tcbn > 32) {

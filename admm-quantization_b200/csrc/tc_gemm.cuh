@@ -45,21 +45,32 @@ constexpr int kPrefetchB = 2;     // operand stages whose B hi / lo may be reque
 
 constexpr int kMaxRawDepth = 4;  // K-blocks of raw float32 in flight (TMA): TileSmem::kRawDepth = 4 with PS, 3 without
 constexpr int kStageCols = 2 * kBlockK;  // TMEM columns of one A stage: hi [0, 64), lo [64, 128)
-constexpr int kTmemCols = 512;   // 2 accumulators + stages x 128: 64 + 3 x 128 (BN <= 32), 128 + 3 x 128 (BN = 64), 256 + 2 x 128 (BN = 128)
+constexpr int kTmemCols = 512;   // 2 accumulators + stages x 128: 64 + 3 x 128 (BN <= 32), 128 + 3 x 128 (BN = 64), 256 + 2 x 128 (BN = 128);
+                                 // BN = 160: ONE accumulator of 160 (in 256) + 2 x 128
 
 // PS ("pre-split B"): the B operand is given as two tf32-valued float32 matrices hi / lo made once by the caller (the
 // ridge inverse is constant for all inner iterations of an ADMM call), fetched by TMA straight into the operand stage
 // in the layout the MMA reads, so that the producer warps only convert A.
 template <int BN, bool PS = false>
 struct TileSmem {
-  static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128, "BN must be 16, 32, 64 or 128");
-  static_assert(PS || BN <= 64, "128-wide tiles need the pre-split B operand (shared-memory budget)");
+  static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 160, "BN must be 16, 32, 64, 128 or 160");
+  static_assert(PS || BN <= 64, "128-wide and wider tiles need the pre-split B operand (shared-memory budget)");
+  // Tiles up to 128 columns keep TWO accumulators: hi.hi in one, the small cross terms lo.hi + hi.lo in the other,
+  // added once by the epilogue.  That is not a nicety: the tensor core's accumulate rounds toward zero, so the error of
+  // an accumulator grows with the number of MMAs added into it - measured on the 512 x 512 x 9 MTTKRP: 1.1e-6 of the
+  // largest entry with the cross terms apart (K / 8 additions into the large accumulator), 3.2e-6 with all three
+  // products in one (3 K / 8).  Tiles wider than 128 columns (BN = 160, used with bn = 144 / 160) leave tensor memory
+  // room for ONE accumulator only next to the two operand stages; they take the 3x larger rounding error and exist
+  // for the wave structure: 512 x 1141 is 4 x 9 tiles of width 128 but 4 x 8 of width 144 - ONE wave on 32 .. 35 CTAs
+  // instead of two (ridge product 44 -> 32 us per iteration there).
+  static constexpr bool kSingleAcc = BN > 128;
   // shared-memory / TMEM budgets: BN = 64 without PS: 2 x 32 + 3 x 48 KB; BN = 64 with PS: 3 x 32 + 4 x 32 KB;
-  // BN = 128 (PS): 2 x 64 + 3 x 32 KB and 2 x 128 accumulator + 2 x 128 operand columns of tensor memory
-  static constexpr int kStages = (BN == 128 || (BN == 64 && !PS)) ? 2 : 3;
-  static constexpr int kRawDepth = (BN == 128) ? 3 : (PS ? 4 : 3);
-  static constexpr int kAccStride = (BN == 128) ? 128 : ((BN == 64) ? 64 : 32);  // TMEM columns between the two accumulators
-  static constexpr int kAccCols = 2 * kAccStride;                // hi.hi at +0, hi.lo + lo.hi at +stride
+  // BN = 128 (PS): 2 x 64 + 3 x 32 KB and 2 x 128 accumulator + 2 x 128 operand columns of tensor memory;
+  // BN = 160 (PS): 2 x 80 + 2 x 32 KB and 256 (160 used) + 2 x 128 columns
+  static constexpr int kStages = (BN >= 128 || (BN == 64 && !PS)) ? 2 : 3;
+  static constexpr int kRawDepth = (BN == 160) ? 2 : ((BN == 128) ? 3 : (PS ? 4 : 3));
+  static constexpr int kAccStride = (BN >= 128) ? 128 : ((BN == 64) ? 64 : 32);  // TMEM columns between the two accumulators
+  static constexpr int kAccCols = 2 * kAccStride;   // hi.hi at +0, hi.lo + lo.hi at +stride; one accumulator of up to 256 columns for BN = 160
   static_assert(kAccCols + kStages * kStageCols <= kTmemCols, "tensor memory budget");
   static constexpr int kAAtomBytes = kTileM * 128;               // one 32-deep atom of A as raw float32
   static constexpr int kBAtomBytes = BN * 128;
@@ -354,9 +365,15 @@ __device__ void tile_3xtf32(const CUtensorMap* tmA, int a_row0, const CUtensorMa
             // the small cross terms get their own accumulator (added to hi.hi by the epilogue): this keeps them from
             // being absorbed into the large hi.hi sums and halves the dependent chain on each accumulator
             const unsigned int acc = (a | ks) != 0 ? 1u : first;
-            umma_tf32_ts(tmem + (unsigned int)TS::kAccStride, a_lo, b_hi + adv, idesc, acc);
-            umma_tf32_ts(tmem + (unsigned int)TS::kAccStride, a_hi, b_lo + adv, idesc, 1u);
-            umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
+            if constexpr (TS::kSingleAcc) {   // one accumulator: small terms first within the k-step
+              umma_tf32_ts(tmem, a_lo, b_hi + adv, idesc, acc);
+              umma_tf32_ts(tmem, a_hi, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, 1u);
+            } else {
+              umma_tf32_ts(tmem + (unsigned int)TS::kAccStride, a_lo, b_hi + adv, idesc, acc);
+              umma_tf32_ts(tmem + (unsigned int)TS::kAccStride, a_hi, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(tmem, a_hi, b_hi + adv, idesc, acc);
+            }
           }
         }
         umma_commit(free_bar);
@@ -541,15 +558,23 @@ __device__ __forceinline__ void load_acc(const Pipe& pipe, float v[BN / 4], int&
   row = q * 32 + lane;
   col0 = cgp * (BN / 4);
   const unsigned int taddr = pipe.tmem_base + ((unsigned int)(q * 32) << 16) + (unsigned int)col0;
-  constexpr int kW = (BN / 4 > 16) ? 16 : BN / 4;  // columns per tcgen05.ld (register pressure)
+  constexpr int kCols = BN / 4;
+  constexpr int kW = (kCols % 16 == 0) ? 16 : ((kCols % 8 == 0) ? 8 : 4);  // columns per tcgen05.ld (register pressure)
 #pragma unroll
-  for (int c0 = 0; c0 < BN / 4; c0 += kW) {
-    unsigned int hh[kW], cr[kW];
+  for (int c0 = 0; c0 < kCols; c0 += kW) {
+    unsigned int hh[kW];
     tmem_load<kW>(taddr + (unsigned int)c0, hh);
-    tmem_load<kW>(taddr + (unsigned int)(TileSmem<BN, true>::kAccStride + c0), cr);
-    tmem_load_wait();
+    if constexpr (TileSmem<BN, true>::kSingleAcc) {
+      tmem_load_wait();
 #pragma unroll
-    for (int i = 0; i < kW; ++i) v[c0 + i] = __uint_as_float(cr[i]) + __uint_as_float(hh[i]);
+      for (int i = 0; i < kW; ++i) v[c0 + i] = __uint_as_float(hh[i]);
+    } else {
+      unsigned int cr[kW];
+      tmem_load<kW>(taddr + (unsigned int)(TileSmem<BN, true>::kAccStride + c0), cr);
+      tmem_load_wait();
+#pragma unroll
+      for (int i = 0; i < kW; ++i) v[c0 + i] = __uint_as_float(cr[i]) + __uint_as_float(hh[i]);
+    }
   }
 }
 

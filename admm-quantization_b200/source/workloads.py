@@ -150,9 +150,9 @@ def product_cost(rows, rank, g, solve_precision=1):
         return 1.0 / g                                   # column strips / small FFMA tiles: scales with the grid
     tiles_m = (rows + 127) // 128
     best = None
-    for bn in range(128, 15, -16):
+    for bn in range(160, 15, -16):
         tiles = tiles_m * ((rank + bn - 1) // bn)
-        cost = ((tiles + g - 1) // g) * (_TILE_FIXED + bn)
+        cost = ((tiles + g - 1) // g) * (_TILE_FIXED + bn) * (1.05 if bn > 128 else 1.0)   # mirrors launch_loop
         best = cost if best is None or cost < best else best
     return float(best)
 

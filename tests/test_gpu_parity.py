@@ -473,10 +473,12 @@ def test_tensor_core_tile_product_random_shapes(nat):
 
 
 def test_tensor_core_product_is_independent_of_the_sm_budget(nat):
-    """The 3xTF32 ridge product picks its tile width from the CTA budget (16 .. 128 columns, 1 .. 3 operand stages
-    configurations); every width accumulates over k in the same order, so ten inner iterations at the layer4 size give
-    BIT-IDENTICAL H and U on 148 CTAs (32-wide tiles), 36 (128-wide, one wave), 33 (80-wide), 24 (96-wide) and 7 CTAs -
-    and they agree with the CPU oracle like the full-grid run does."""
+    """The 3xTF32 ridge product picks its tile width from the CTA budget (16 .. 128 columns with two accumulators, 1 .. 3
+    operand stages); every such width accumulates over k in the same order, so ten inner iterations at the layer4 size
+    give BIT-IDENTICAL H and U on 148 CTAs (32-wide tiles), 36 (128-wide, one wave), 24 (96-wide) and 7 CTAs - and they
+    agree with the CPU oracle like the full-grid run does.  On 32 .. 35 CTAs the product takes 144-wide tiles with a
+    single accumulator (one wave instead of two; round-toward-zero accumulation of 3x as many MMAs: ~3x the rounding
+    error of the narrower tiles), whose H agrees to rounding."""
     from oracle import admm_oracle as orc
     torch.set_num_threads(4)
     g = torch.Generator().manual_seed(22)
@@ -487,13 +489,17 @@ def test_tensor_core_product_is_independent_of_the_sm_budget(nat):
     H0 = torch.randn(I, R, generator=g)
     U0 = torch.randn(I, R, generator=g) * 0.1
     outs = []
-    for ctas in (0, 36, 33, 24, 7):
+    for ctas in (0, 36, 24, 7, 33):
         H, U = H0.clone().cuda(), U0.clone().cuda()
-        rep = nat.admm_iteration_inplace(H, U, F, G, 11, 1e-8, 4, MSE, precision=1, max_ctas=ctas)
-        assert nat.read_report(rep).iterations == 10
+        rep = nat.admm_iteration_inplace(H, U, F, G, 11 if ctas != 33 else 2, 1e-8, 4, MSE, precision=1, max_ctas=ctas)
+        assert nat.read_report(rep).iterations == (10 if ctas != 33 else 1)
         outs.append((H.cpu(), U.cpu()))
-    for H, U in outs[1:]:
+    for H, U in outs[1:4]:
         assert torch.equal(H, outs[0][0]) and torch.equal(U, outs[0][1])
+    H1, U1 = H0.clone().cuda(), U0.clone().cuda()
+    nat.admm_iteration_inplace(H1, U1, F, G, 2, 1e-8, 4, MSE, precision=1, max_ctas=36)
+    wide, _ = _agreement(outs[4][0].numpy(), H1.cpu().numpy())
+    assert wide >= 0.9995, wide
     Uo = U0.clone()
     Ho, Uo, _ = orc.admm_iteration(H0.clone(), Uo, F.cpu(), G.cpu(), 3, 1e-8, 4, MSE)
     H, U = H0.clone().cuda(), U0.clone().cuda()
