@@ -711,9 +711,68 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
           }
         }
         float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f, f3 = 0.0f;   // float32 partial sums over at most 4 * kBatch elements, float64 beyond
+        f32x2 a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;     // the same sums of the packed path (even / odd lanes)
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-          if (gg[b] < g1) {
+          if (gg[b] < g1 && fast_code && nvb[b] == 4) {
+            // Full group, clip-search scheme: two elements per instruction (packed f32x2 IEEE operations: the same
+            // roundings as the scalar code below, half the issue slots - the phase is issue bound).  Products that the
+            // reference rounds on their own (code * scale, rho * (H + U)) are formed as fma(a, b, -0.0) with the -0.0
+            // from a kernel parameter, which ptxas cannot contract into the following add (see search.cuh).
+            const f32x2 nz2 = pack2(p.neg_zero, p.neg_zero), sc2 = pack2(qp.scale, qp.scale), rc2 = pack2(rcp_scale, rcp_scale);
+            const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+            const ulonglong2 hl = *reinterpret_cast<const ulonglong2*>(&hls4[b]), uu = *reinterpret_cast<const ulonglong2*>(&u4[b]);
+            const ulonglong2 hpp = *reinterpret_cast<const ulonglong2*>(&hp4[b]);
+            const f32x2 hls2[2] = {hl.x, hl.y}, u2[2] = {uu.x, uu.y}, hp2[2] = {hpp.x, hpp.y};
+            f32x2 hq2[2], un2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const f32x2 v2 = sub2(hls2[h], u2[h]);
+              float t0, t1, v0, v1;
+              unpack2(mul2(v2, rc2), t0, t1);
+              t0 = fminf(fmaxf(t0, L.fast_lo), L.fast_hi);
+              t1 = fminf(fmaxf(t1, L.fast_lo), L.fast_hi);
+              const f32x2 tc2 = pack2(t0, t1);
+              const f32x2 k2 = add2(add2(tc2, magic), nmagic);
+              float c0, c1, r0, r1;
+              unpack2(k2, c0, c1);
+              unpack2(sub2(tc2, k2), r0, r1);
+              c0 = copysignf(c0, t0);   // rint keeps the sign of a quotient in (-0.5, 0); the magic sum returns +0
+              c1 = copysignf(c1, t1);
+              if (!(fmaxf(fabsf(r0), fabsf(r1)) <= L.fast_thr)) {   // rare: too close to a rounding boundary
+                unpack2(v2, v0, v1);
+                if (!(fabsf(r0) <= L.fast_thr)) c0 = code_exact(v0, qp.scale, L);
+                if (!(fabsf(r1) <= L.fast_thr)) c1 = code_exact(v1, qp.scale, L);
+              }
+              if (p.codes != nullptr) {
+                p.codes[eb[b] + 2 * h] = (int8_t)c0;
+                p.codes[eb[b] + 2 * h + 1] = (int8_t)c1;
+              }
+              const f32x2 hq = fma2(pack2(c0, c1), sc2, nz2);            // H = Q(H_ls - U)   (:59)
+              const f32x2 d1 = sub2(hq, hls2[h]);
+              const f32x2 un = add2(u2[h], d1);                         // U += H - H_ls     (:60)
+              const f32x2 d2 = sub2(hq, hp2[h]);
+              a0 = fma2(d1, d1, a0);   // sum (H - H_ls)^2     (:62)
+              a1 = fma2(hq, hq, a1);   // sum H^2
+              a2 = fma2(d2, d2, a2);   // sum (H - H_prev)^2   (:63)
+              a3 = fma2(un, un, a3);   // sum U^2
+              hq2[h] = hq;
+              un2[h] = un;
+            }
+            ulonglong2 ho, uo;
+            ho.x = hq2[0]; ho.y = hq2[1];
+            uo.x = un2[0]; uo.y = un2[1];
+            reinterpret_cast<ulonglong2*>(p.Hp)[gg[b]] = ho;
+            reinterpret_cast<ulonglong2*>(p.Up)[gg[b]] = uo;
+            if constexpr (TCBN != kDiagP1) {
+              const f32x2 rho2 = pack2(rho, rho);
+              const ulonglong2 ff = *reinterpret_cast<const ulonglong2*>(&fv4[b]);
+              ulonglong2 ro;
+              ro.x = add2(ff.x, fma2(rho2, add2(hq2[0], un2[0]), nz2));   // F + rho * (H + U), the product rounded on its own
+              ro.y = add2(ff.y, fma2(rho2, add2(hq2[1], un2[1]), nz2));
+              reinterpret_cast<ulonglong2*>(p.RHS)[gg[b]] = ro;
+            }
+          } else if (gg[b] < g1) {
             const float hls[4] = {hls4[b].x, hls4[b].y, hls4[b].z, hls4[b].w};
             const float u[4] = {u4[b].x, u4[b].y, u4[b].z, u4[b].w};
             const float hp[4] = {hp4[b].x, hp4[b].y, hp4[b].z, hp4[b].w};
@@ -757,6 +816,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
               reinterpret_cast<float4*>(p.RHS)[gg[b]] = make_float4(rhs4[0], rhs4[1], rhs4[2], rhs4[3]);
             }
           }
+        }
+        {
+          float e, o;
+          unpack2(a0, e, o); f0 = add_rn(f0, add_rn(e, o));
+          unpack2(a1, e, o); f1 = add_rn(f1, add_rn(e, o));
+          unpack2(a2, e, o); f2 = add_rn(f2, add_rn(e, o));
+          unpack2(a3, e, o); f3 = add_rn(f3, add_rn(e, o));
         }
         sums[0] += (double)f0;
         sums[1] += (double)f1;
