@@ -24,6 +24,7 @@
 #include "tc_gemm.cuh"
 #include "admm_loop_resident.cuh"
 #include "admm_loop_cluster.cuh"
+#include "admm_loop_tap.cuh"
 
 namespace admmq {
 
@@ -1055,6 +1056,44 @@ static int launch_loop(float* H, float* U, const float* F, const float* Minv, co
     ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_admm_loop_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResidentSmem)));
     k_admm_loop_resident<<<1, kThreads, sizeof(ResidentSmem), stream>>>(rp);
     ADMMQ_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return ADMMQ_OK;
+  }
+  static const bool no_tap = getenv("ADMMQ_NO_TAP") != nullptr;   // diagnostics: never take the tap-factor cluster kernel
+  if (precision != 0 && !no_tap && !no_cluster && tap_cluster_fits(I, R, l.Rp, num_attempts, grid)) {
+    // the tap factor of a wide convolution (9 x R): one cluster of 8 CTAs, columns and clip candidates split (admm_loop_tap.cuh)
+    ResidentParams rp;
+    rp.H = H;
+    rp.U = U;
+    rp.F = F;
+    rp.Minv = Minv;
+    rp.rho = rho;
+    rp.inv_status = inv_status;
+    rp.I = I;
+    rp.R = R;
+    rp.Rp = l.Rp;
+    rp.max_iter = max_iter;
+    rp.eps = eps;
+    rp.bits = bits;
+    rp.scheme = qscheme;
+    rp.Nc = (qscheme == ADMMQ_Q_MSEMINMAX_SYMMETRIC) ? num_attempts : 0;
+    rp.codes = codes;
+    rp.report = report;
+    ADMMQ_CUDA_OK(cudaFuncSetAttribute(k_admm_loop_tap<kTapMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TapSmem)));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kTapCtas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = sizeof(TapSmem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kTapCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ADMMQ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_admm_loop_tap<kTapMaxRows>, rp));
     count_launches(1);
     return ADMMQ_OK;
   }

@@ -85,7 +85,8 @@ __device__ __forceinline__ void cl_store(unsigned int addr, double v) {
 }
 
 // sum over the CTA of four per-thread doubles (fixed order), result valid in every thread
-__device__ __forceinline__ void cl_sum4(double v[4], ClusterSmem& sm) {
+template <class Smem>
+__device__ __forceinline__ void cl_sum4(double v[4], Smem& sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
@@ -106,7 +107,8 @@ __device__ __forceinline__ void cl_sum4(double v[4], ClusterSmem& sm) {
 
 // Fixed-point sums of squared errors of the n elements of sm.Vall for candidates [c0, c1) into sm.acc (threshold form,
 // the same recipe - element order, fixed-point units, float64 terms - as res_candidate_sums of the resident kernel).
-__device__ inline void cl_candidate_sums(ClusterSmem& sm, int n, float absmax, int Nc, int c0, int c1, const Levels L, int bits) {
+template <class Smem>
+__device__ inline void cl_candidate_sums(Smem& sm, int n, float absmax, int Nc, int c0, int c1, const Levels L, int bits) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ClipGrid g = make_clip_grid(absmax, Nc);
   const double unit_inv = fixed_point_unit_inv((double)n, absmax);

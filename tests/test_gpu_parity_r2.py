@@ -406,3 +406,64 @@ def test_cluster_loop_for_small_factors(nat, capsys):
                          f"P3 {rep.phase_ns[2] / 1e3 / rep.iterations:.2f})")
     with capsys.disabled():
         print("\n[cluster] " + "\n[cluster] ".join(lines))
+
+
+def test_tap_factor_cluster_loop(nat, capsys):
+    """csrc/admm_loop_tap.cuh: the 9 x R tap factor of a wide convolution on one cluster of 8 CTAs (columns and clip
+    candidates split, the right-hand side replicated through distributed shared memory) against the general cooperative
+    kernel (budget of 7 CTAs: below one cluster) and the CPU oracle; exit test, NaN semantics, per-iteration time."""
+    from oracle import admm_oracle as orc
+    g = torch.Generator().manual_seed(78)
+    lines = []
+
+    def close_frac(a, b):
+        return float(((a - b).abs() <= 1e-4 * float(b.abs().max())).float().mean())
+
+    for (I, R, bits, qs) in [(9, 278, 4, MSE), (9, 566, 4, MSE), (9, 637, 4, MSE), (9, 566, 8, MSE), (5, 300, 3, MSE), (9, 375, 4, "tensor_minmax")]:
+        Bf, Cf = torch.randn(128, R, generator=g), torch.randn(64, R, generator=g)
+        G = ((Bf.T @ Bf) * (Cf.T @ Cf)).cuda()
+        F = (torch.randn(I, R, generator=g) * 90).cuda()
+        H0 = torch.randn(I, R, generator=g).cuda()
+        U0 = (torch.randn(I, R, generator=g) * 0.1).cuda()
+        outs = []
+        for ctas in (0, 8, 7):
+            H, U = H0.clone(), U0.clone()
+            codes = torch.empty(I, R, dtype=torch.int8, device="cuda")
+            rep = nat.read_report(nat.admm_iteration_inplace(H, U, F, G, 4, 1e-8, bits, qs, codes=codes, precision=1, max_ctas=ctas))
+            assert rep.iterations == 3
+            outs.append((H, U, codes, rep))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+        assert close_frac(outs[0][0], outs[2][0]) >= 0.999 and close_frac(outs[0][1], outs[2][1]) >= 0.995, (I, R, bits, qs)
+        if qs == MSE:
+            assert torch.equal(outs[0][2].float() * outs[0][3].scale, outs[0][0])     # codes * scale == H
+        # one step against the CPU oracle
+        Uo = U0.cpu().clone()
+        Ho, Uo, _ = orc.admm_iteration(H0.cpu().clone(), Uo, F.cpu(), G.cpu(), 2, 1e-8, bits, qs)
+        H, U = H0.clone(), U0.clone()
+        nat.admm_iteration_inplace(H, U, F, G, 2, 1e-8, bits, qs, precision=1, max_ctas=0)
+        assert close_frac(H.cpu(), Ho) >= 0.999 and close_frac(U.cpu(), Uo) >= 0.999, (I, R, bits, qs)
+    I, R = 9, 566
+    Bf = torch.randn(256, R, generator=g)
+    G = (Bf.T @ Bf).cuda()
+    F = (torch.randn(I, R, generator=g) * 50).cuda()
+    H0 = torch.randn(I, R, generator=g).cuda()
+    H, U = H0.clone(), torch.zeros_like(H0)
+    rep = nat.read_report(nat.admm_iteration_inplace(H, U, F, G, 50, 1e30, 4, MSE, precision=1, max_ctas=0))
+    assert rep.iterations == 1 and rep.status & nat.ST_CONVERGED
+    Z = torch.zeros(I, R).cuda()
+    Hz, Uz = Z.clone(), Z.clone()
+    rep = nat.read_report(nat.admm_iteration_inplace(Hz, Uz, Z.clone(), G, 5, 1e-8, 4, MSE, precision=1, max_ctas=0))
+    assert rep.status & nat.ST_NONFINITE and torch.isnan(Hz).all()
+    for R in (278, 566):
+        Bf = torch.randn(256, R, generator=g)
+        G = (Bf.T @ Bf).cuda()
+        F = (torch.randn(9, R, generator=g) * 50).cuda()
+        H0 = torch.randn(9, R, generator=g).cuda()
+        for ctas in (8, 7, 33):
+            H, U = H0.clone(), torch.zeros_like(H0)
+            rep = nat.read_report(nat.admm_iteration_inplace(H, U, F, G, 301, 1e-8, 4, MSE, precision=1, max_ctas=ctas))
+            lines.append(f"9 x {R} with a budget of {ctas} CTAs ({'cluster of 8' if ctas >= 8 else 'general kernel'}): "
+                         f"{rep.phase_ns[3] / 1e3 / rep.iterations:.2f} us per iteration (P1 {rep.phase_ns[0] / 1e3 / rep.iterations:.2f}, "
+                         f"P2 {rep.phase_ns[1] / 1e3 / rep.iterations:.2f}, P3 {rep.phase_ns[2] / 1e3 / rep.iterations:.2f})")
+    with capsys.disabled():
+        print("\n[tap] " + "\n[tap] ".join(lines))
