@@ -12,7 +12,8 @@
 //   P2  per-candidate squared-error sums of the clip search over V (search.cuh)         (q.py:136-139)
 //   --- device-wide barrier
 //   P3  argmin -> scale; H = Q(V); U += H - H_ls; residual sums; next RHS              (:59-63, q.py:141-144)
-//   --- device-wide barrier, then the exit test r < eps && s < eps                       (:64-65)
+//   --- device-wide barrier; the exit test r < eps && s < eps (:64-65) of iteration j is evaluated after the first
+//       barrier of iteration j + 1 (P1 touches no result, so the speculative product is dropped when the test fires)
 // State (H, U, F, H_ls, RHS, Minv) stays L2 resident for the whole call: per iteration the
 // algorithmic traffic is 16 B per element of H plus one pass over Minv, all served from L2.
 // A small factor on a budget of one CTA takes the shared-memory-resident kernel of admm_loop_resident.cuh instead.
@@ -526,6 +527,23 @@ __device__ __forceinline__ void cta_sum4(double v[4], ResidualSmem& rs) {
   }
 }
 
+// Totals of the per-CTA residual slots, formed redundantly by every warp: lane c takes the CTAs c, c + 32, ... in
+// order, then a xor butterfly (the same association in every lane, warp and CTA, so every thread of the grid holds
+// bit-identical totals) - no shared memory and no CTA barrier on the path of the exit test.
+__device__ __forceinline__ void slot_totals(const double* slots, int ctas, double tot[4]) {
+  tot[0] = tot[1] = tot[2] = tot[3] = 0.0;
+  for (int c = threadIdx.x & 31; c < ctas; c += 32) {
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(slots + (size_t)c * 4));
+    const double2 b = __ldcg(reinterpret_cast<const double2*>(slots + (size_t)c * 4 + 2));
+    tot[0] += a.x;
+    tot[1] += a.y;
+    tot[2] += b.x;
+    tot[3] += b.y;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tot[q] = warp_sum(tot[q]);
+}
+
 // TCBN = 0: P1 as float32 FFMA tiles (BM x BN, TM x TN per thread); TCBN = 16 / 32 / 64: P1 on the tensor cores;
 // TCBN = -MI: P1 for factors with at most MI rows (gemm_phase_skinny); TCBN = kDiagP1: elementwise P1 of the
 // two-block splitting (elementwise_phase); TCBN = kF64P1: float64-accumulating tiles against the float64 inverse
@@ -630,6 +648,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   }
   bar.sync();
 
+  bool pending = false;   // the residual slots of the last finished iteration have not been tested yet
+  auto residuals_below_eps = [&]() {
+    double tot[4];
+    slot_totals(p.slots, (int)gridDim.x, tot);
+    rep.r = div_rn((float)tot[0], (float)tot[1]);
+    rep.s = div_rn((float)tot[2], (float)tot[3]);
+    return rep.r < p.eps && rep.s < p.eps;
+  };
   for (int j = 1; j < p.max_iter; ++j) {  // range(1, max_iter), :55
     const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
     // ---------------- P1
@@ -644,6 +670,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     }
     bar.sync();
     lap(0);
+    // ---------------- exit test of iteration j - 1 (:62-65), evaluated identically by every thread of the grid.  It is
+    // deferred past this iteration's P1: the residual slots are complete after the barrier that ended iteration j - 1,
+    // P1 touches neither H, U, the codes nor the report, so a speculative P1 is simply dropped when the test fires, and
+    // the slots' L2 round trip overlaps the one of the min / max keys below instead of standing alone after a barrier.
+    if (pending && residuals_below_eps()) {
+      rep.status |= ADMMQ_ST_CONVERGED;
+      pending = false;
+      break;
+    }
+    pending = false;
     // ---------------- P2
     const float tmax = key_float(__ldcg(&hdr->keys[slot][0]));
     const float tmin = key_float(~__ldcg(&hdr->keys[slot][1]));
@@ -840,21 +876,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
     cta_sum4(sums, sm.res);
     if (t < 4) p.slots[(size_t)blockIdx.x * 4 + t] = sums[t];
     bar.sync();
-    // ---------------- exit test (:62-65), evaluated identically by every CTA
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = t; c < (int)gridDim.x; c += kThreads) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tot[q] += __ldcg(p.slots + (size_t)c * 4 + q);
-    }
-    cta_sum4(tot, sm.res);
-    rep.r = div_rn((float)tot[0], (float)tot[1]);
-    rep.s = div_rn((float)tot[2], (float)tot[3]);
     lap(2);
-    if (rep.r < p.eps && rep.s < p.eps) {
-      rep.status |= ADMMQ_ST_CONVERGED;
-      break;
-    }
+    pending = true;   // r, s of this iteration: tested after the next P1, or below when this was the last iteration
   }
+  if (pending && residuals_below_eps()) rep.status |= ADMMQ_ST_CONVERGED;
   // the caller's dense H and U (every CTA copies the groups it updated itself in P3: no barrier needed)
   if (p.max_iter > 1) {
     ADMMQ_GROUP_WALK();

@@ -249,18 +249,34 @@ ADMMQ_HD float ordered_float(unsigned int k) { return bits_f32((k & 0x80000000u)
 //   mid * scale is exact in float64 (25 x 24 significant bits), so theta is the first float above that product
 //   (or the product itself when it is a float and the tie goes to y*).
 // tests/hostcheck pins theta and its predecessor against the exact division for every level of random scales.
-ADMMQ_HD float code_threshold(float scale, float level) {
+// The level-only part (mid, parity of y*) and the scale-dependent part are separate so that the clip search forms the
+// former once per level instead of once per (candidate, level) pair.
+struct ThresholdMid {
+  double mid;   // midpoint of pred(y*) and y* (25 significant bits, never zero)
+  bool odd;     // mantissa of y* is odd: a product that lands exactly on mid rounds away from y*
+};
+ADMMQ_HD ThresholdMid threshold_mid(float level) {
   const float target = level + 1.0f;
   const float b = target - 0.5f;
   const bool t_even = (((int)target) & 1) == 0;
   const float ystar = t_even ? b : ordered_float(ordered_key(b) + 1u);
   const float pred = ordered_float(ordered_key(ystar) - 1u);
-  const double P = (0.5 * ((double)pred + (double)ystar)) * (double)scale;
+  ThresholdMid m;
+  m.mid = 0.5 * ((double)pred + (double)ystar);
+  m.odd = (f32_bits(ystar) & 1u) != 0u;
+  return m;
+}
+ADMMQ_HD float code_threshold_from_mid(float scale, double mid, bool odd) {
+  const double P = mid * (double)scale;                 // exact; scale > 0, so P != 0 and has the sign of mid
   float x = (float)P;                                   // round to nearest
-  if ((double)x < P) x = ordered_float(ordered_key(x) + 1u);
-  const bool ystar_even = (f32_bits(ystar) & 1u) == 0u;
-  if ((double)x == P && !ystar_even) x = ordered_float(ordered_key(x) + 1u);
+  const double xd = (double)x;
+  // first float above P, or P itself when it is a float and the tie goes to y*: one step towards +inf
+  if (xd < P || (xd == P && odd)) x = bits_f32(f32_bits(x) + (x > 0.0f ? 1u : 0xffffffffu));
   return x;
+}
+ADMMQ_HD float code_threshold(float scale, float level) {
+  const ThresholdMid m = threshold_mid(level);
+  return code_threshold_from_mid(scale, m.mid, m.odd);
 }
 
 // the same threshold by stepping through neighbouring floats with the exact division (reference implementation of the

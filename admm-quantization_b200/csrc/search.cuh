@@ -42,7 +42,7 @@ constexpr int kBins = 8192;        // linear bins over [-absmax, absmax]
 constexpr int kBinSlots = kBins + kBins / 8;  // see bin_slot()
 // elements sorted by bin in shared memory at a time: as many as fit next to the bin arrays in the 227 KB of a CTA (every
 // further stage repeats the fixed costs of the scan and the threshold pass: a 20.7 k chunk took 27 us as two stages)
-constexpr int kStageCap = 24064;
+constexpr int kStageCap = 23296;
 constexpr int kLoadBatch = 5;      // float4 loads in flight per thread
 struct BinnedSmem {
   __align__(16) float sorted[kStageCap];   // the stage's elements grouped by bin
@@ -53,6 +53,8 @@ struct BinnedSmem {
   unsigned long long acc[kMaxCandidates];  // per-candidate fixed-point totals of this CTA (folded once per stage)
   unsigned int part[3][kMaxCandidates];    // the current stage's terms in three 21-bit slices (plain 32-bit adds, no return)
   float scale[kMaxCandidates];
+  double mid[256];                         // per level: the midpoint of code_threshold() (depends on the level only)
+  unsigned int odd[256];                   // ... and the parity of y*'s mantissa
   unsigned long long wsum[kWarps];
   unsigned int wcnt[kWarps];
   double red[kWarps];
@@ -319,6 +321,11 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
     sm.acc[c] = 0ull;
     sm.part[0][c] = sm.part[1][c] = sm.part[2][c] = 0u;
   }
+  for (int j = tid; j < nthr; j += kThreads) {
+    const ThresholdMid tm = threshold_mid(L.lo + (float)j);
+    sm.mid[j] = tm.mid;
+    sm.odd[j] = tm.odd ? 1u : 0u;
+  }
   double x2 = 0.0;
   for (long long base = e0; base < e1; base += kStageCap) {
     const int cnt = (int)min((long long)kStageCap, e1 - base);
@@ -463,11 +470,17 @@ __device__ inline void cta_candidate_sums_binned(const float* __restrict__ v, lo
         stl += in ? (int)__float_as_uint(lb) - 0x4B400000 : 0;
         below += in ? 1 : 0;
       };
-      for (int p = tid; p < npairs; p += kThreads) {
-        const int j = p / Nc, c = p - j * Nc;
+      // (level, candidate) of the thread's pairs without a division per pair
+      int j = tid / Nc, c = tid - j * Nc;
+      const int dj = kThreads / Nc, dc = kThreads - dj * Nc;
+      for (int p = tid; p < npairs; p += kThreads, j += dj, c += dc) {
+        if (c >= Nc) {
+          c -= Nc;
+          ++j;
+        }
         const float s = sm.scale[c];
         const float level = L.lo + (float)j;
-        const float theta = code_threshold(s, level);
+        const float theta = code_threshold_from_mid(s, sm.mid[j], sm.odd[j] != 0u);
         const int bin = bin_of(theta, bmul), b = bin_slot(bin);
         const unsigned int beg = bin ? sm.cnt[bin_slot(bin - 1)] : 0u, end = sm.cnt[b];
         long long ps = (long long)(((unsigned long long)sm.shi[b] << 32) | sm.slo[b]);

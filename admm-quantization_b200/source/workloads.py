@@ -133,7 +133,7 @@ _TILE_FIXED = 16           # csrc/admm_loop.cu kTileFixed: tile cost that does n
 _PHASE_FLOOR_US = 14.0     # P2 + P3 of a factor that is too small to matter: barriers and L2 round trips
 
 
-_STAGE_CAP = 24064         # csrc/search.cuh kStageCap
+_STAGE_CAP = 23296         # csrc/search.cuh kStageCap
 _STAGE_FIXED_US = 7.0      # scan + threshold pass of one more stage (measured: 20.7 k elements as two stages 27 us, as one 20 us)
 
 
