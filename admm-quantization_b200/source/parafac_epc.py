@@ -12,9 +12,12 @@ device and the results come back on the tensor's device, like a host-buffer call
 that dominate a pass are libadmmq kernels (csrc/contract.cu): the MTTKRP forms the Khatri-Rao operand on
 the fly (tensorly materialises it: (I J) x R doubles, 2.4 GB for mode 2 of a 512 x 512 x 9 layer, every
 pass), the Gram-Hadamard product and the column normalisation are one kernel each.  The R x R dense
-factorizations of a mode update - `solve` in ALS, the symmetric eigen-decomposition in EPC - stay with
-torch (cuSOLVER), see SURVEY K9 / K10.  The wrapper logic (float64 copy, ascending mode permutation,
-rounds, stop rules, original mode order) follows source/parafac_epc.py line by line.
+factorizations of a mode update stay with torch (cuSOLVER / cuBLAS), see SURVEY K9 / K10: `solve` in ALS; in EPC
+the symmetric eigen-decomposition only for the first update of a run - every later update expands the residual
+and the factor in power series around a warm-started multiplier from ONE Cholesky factorization
+(`_ridge_factor_chol`: 2 ms against 15 ms at R = 1141, same multiplier and factor to 1e-12).  The wrapper logic
+(float64 copy, ascending mode permutation, rounds, stop rules, original mode order) follows
+source/parafac_epc.py line by line.
 """
 import math
 
@@ -144,9 +147,132 @@ def _multiplier(sig_c, s_c, norm_y2, target):
     return max(mu, floor)
 
 
-def _epc_sweep(T, factors, delta):
+_EYE = {}
+
+
+def _eye(n, like):
+    key = (n, like.device)
+    if key not in _EYE:
+        _EYE[key] = torch.eye(n, dtype=like.dtype, device=like.device)
+    return _EYE[key]
+
+
+def _ridge_eval(gamma, Tm, mu, terms):
+    """Everything the multiplier search needs around one value of mu from ONE Cholesky factorization of
+    M = Gamma + mu I: the explicit inverse M^-1 = L^-T L^-1 (potrf, one triangular solve against the identity, one
+    GEMM: half the time of cuSOLVER's potri-style `cholesky_inverse`), the sequence F_k = Tm M^-k, k = 1..terms (one
+    float64 GEMM each, written into one buffer) and the moments a_k = tr(Tm M^-k Tm^T), k = 1..2 terms, read off the
+    Gram matrix of the flattened [Tm, F_1 .. F_terms] (ONE GEMM): a_1 = <F_1, Tm>, a_{i+j} = <F_i, F_j>.
+    Returns (F buffer of shape terms x I x R, stats) with stats = [a_1 .. a_{2 terms}, ||F_1 M - Tm|| / ||Tm||, info]
+    still on the device."""
+    R = gamma.shape[0]
+    M = gamma.clone()
+    M.diagonal().add_(mu)
+    L, info = torch.linalg.cholesky_ex(M)
+    Li = torch.linalg.solve_triangular(L, _eye(R, L), upper=False)
+    Minv = Li.T @ Li
+    buf = torch.empty((terms + 1,) + tuple(Tm.shape), dtype=Tm.dtype, device=Tm.device)
+    buf[0].copy_(Tm)
+    for k in range(terms):
+        torch.matmul(buf[k], Minv, out=buf[k + 1])
+    flat = buf.reshape(terms + 1, -1)
+    G = flat @ flat.T                                        # G[i, j] = <F_i, F_j>, F_0 = Tm
+    idx_i = [0] + [k // 2 for k in range(2, 2 * terms + 1)]
+    idx_j = [1] + [k - k // 2 for k in range(2, 2 * terms + 1)]
+    mom = G[idx_i, idx_j]
+    chk = torch.linalg.norm(buf[1] @ M - Tm) / torch.sqrt(G[0, 0])
+    return buf[1:], torch.cat([mom, torch.stack([chk, info.to(Tm.dtype)])])
+
+
+def _series_residual(a, mu, d, norm_y2):
+    """residual(mu + d) from the moments a[k - 1] = a_k at mu (|d| < mu + sigma_min):
+    a_1(mu + d) = sum_j (-d)^j a_{1+j},  a_2(mu + d) = sum_j (j + 1) (-d)^j a_{2+j},  residual = ||Y||^2 - a_1 - (mu + d) a_2."""
+    n = len(a)
+    s1 = s2 = 0.0
+    p = 1.0
+    for j in range(n):
+        s1 += p * a[j]
+        if j + 1 < n:
+            s2 += (j + 1) * p * a[j + 1]
+        p *= -d
+    return norm_y2 - s1 - (mu + d) * s2
+
+
+def _ridge_factor_chol(gamma, Tm, norm_y2, target, mu0, floor, max_evals=5, counters=None, terms=12):
+    """The EPC mode update without an eigen-decomposition: the same mu and F = Tm (Gamma + mu I)^-1 as `_multiplier`
+    gives.  residual(mu) = ||Y||^2 - a_1 - mu a_2 with a_k = tr(Tm M^-k Tm^T), M = Gamma + mu I, is analytic in mu:
+    around a warm start mu0 (the multiplier of the previous mode update - it moves by a few per cent per update) both
+    the residual and F(mu0 + d) = sum_j (-d)^j Tm M0^-(j+1) are power series in d that converge for |d| < mu0.  ONE
+    Cholesky factorization + explicit inverse at mu0 and `terms` float64 GEMMs give the moments and the series terms
+    (`_ridge_eval`); the root d of residual(mu0 + d) = target is then found on the host from the moments (bisection on
+    scalars), and F is summed from the terms - against cuSOLVER's symmetric eigen-decomposition of the eigen form
+    (syevd: 15 ms at R = 1141, the whole cost of an update).  |d| / mu0 <= 10^(-12 / terms) keeps the truncation of the F
+    series at 1e-12 (the caller picks 8, 12 or 16 terms from the size of the previous step); a larger step moves mu0
+    to the series' root and factorizes again (rare once the passes settle).
+    residual is increasing in mu, which gives the direction when the root lies outside the series' trust interval.
+    Returns (mu, F, |mu - mu0| / mu0) or None when the factorization fails (Gamma + mu I numerically singular), the explicit
+    inverse is not accurate enough (||F_1 M - Tm|| > 1e-9 ||Tm||) or the budget is spent - the caller then takes the
+    eigen form, which copes with a singular Gamma."""
+    mu = mu_start = max(float(mu0), floor)
+    for _ in range(max_evals):
+        Fs, stats = _ridge_eval(gamma, Tm, mu, terms)
+        st = stats.tolist()                                  # one device -> host copy per factorization
+        a, chk, info = st[:-2], st[-2], st[-1]
+        if counters is not None:
+            counters["chol_evals"] = counters.get("chol_evals", 0) + 1
+        if info != 0 or not all(math.isfinite(v) for v in st) or chk > 1e-9:
+            return None
+        accept = 10.0 ** (-12.0 / terms)
+        g = lambda d: _series_residual(a, mu, d, norm_y2) - target
+        dlo, dhi = max(-0.5 * mu, floor - mu), 0.5 * mu
+        glo, ghi = g(dlo), g(dhi)
+        slope = 2.0 * mu * a[2]                              # d residual / d mu at mu
+        if ghi < 0.0:                                        # the root is above the trust interval
+            step = -g(0.0) / slope if slope > 0.0 else 3.0 * mu
+            mu += min(max(step, 0.5 * mu), 3.0 * mu)
+            terms = max(terms, 12)
+            continue
+        if glo > 0.0:                                        # ... or below it
+            if mu + dlo <= floor:                            # even the least-squares fit leaves more than the target
+                if mu <= floor:
+                    return floor, Fs[0], 0.0
+                mu = floor
+                continue
+            step = -g(0.0) / slope if slope > 0.0 else -0.75 * mu
+            mu = max(mu + min(max(step, -0.75 * mu), -0.5 * mu), floor)
+            terms = max(terms, 12)
+            continue
+        for _b in range(200):                                # bisection on the series (scalars on the host)
+            d = 0.5 * (dlo + dhi)
+            if g(d) < 0.0:
+                dlo = d
+            else:
+                dhi = d
+            if dhi - dlo <= 1e-16 * mu:
+                break
+        d = 0.5 * (dlo + dhi)
+        r = abs(d) / mu
+        if r <= accept:
+            F = Fs[0]
+            if d != 0.0:
+                F = F.clone()
+                p = 1.0
+                for k in range(1, terms):
+                    p *= -d
+                    if abs(p) * a[2 * k + 1] ** 0.5 <= 1e-17 * a[1] ** 0.5:   # ||F_{k+1}|| = sqrt(a_{2k+2}): negligible from here on
+                        break
+                    F.add_(Fs[k], alpha=p)
+            return mu + d, F, abs(mu + d - mu_start) / mu_start
+        mu += d                                              # the series' root is good to ~r^(2 terms): next time |d| is tiny
+        terms = 8 if r <= 0.25 else 12                       # the remaining step is ~r^(2 terms) of mu
+    return None
+
+
+def _epc_sweep(T, factors, delta, state=None):
     """One error-preserving-correction pass over all modes (the body of musco's `cp_anc`); `factors` are float64 CUDA
-    tensors owned by the caller and updated in place / replaced."""
+    tensors owned by the caller and updated in place / replaced.  `state` (a dict the caller keeps across passes)
+    carries the last multiplier: with it a mode update is the Cholesky form (`_ridge_factor_chol`), without it - the
+    first update of a run, a stand-alone pass, or whenever the Cholesky form gives up - the eigen form."""
     rank = factors[0].shape[1]
     target = delta * delta
     for m in range(T.N):
@@ -157,13 +283,33 @@ def _epc_sweep(T, factors, delta):
                 _native.normalize_columns_f64(factors[k])
         gamma = T.gram(factors, m)
         Tm = T.mttkrp(factors, m)
-        sig, V = torch.linalg.eigh(gamma)
-        sig = torch.clamp(sig, min=0.0)
-        Tt = Tm @ V
-        s = (Tt * Tt).sum(dim=0)
-        both = torch.stack([sig, s]).cpu().numpy()  # one device -> host copy per mode update
-        mu = _multiplier(both[0], both[1], T.norm2, target)
-        factors[m] = ((Tt / (sig + mu)) @ V.T).contiguous()
+        got = None
+        if state is not None and state.get("mu") is not None:
+            # warm start: the last multiplier times the ratio the same two consecutive updates had one pass ago (the
+            # multipliers of the modes differ systematically; the prediction is good to ~1e-3 once the passes settle);
+            # series length from the size of the last step: 10^(-12 / terms) stays above it with a margin
+            h = state["hist"]
+            mu0 = h[-1] * (h[-T.N] / h[-T.N - 1]) if len(h) > T.N else h[-1]
+            r_last = state.get("r", 1.0)
+            terms = 4 if r_last <= 4e-4 else 6 if r_last <= 4e-3 else 8 if r_last <= 0.015 else 12 if r_last <= 0.05 else 16
+            got = _ridge_factor_chol(gamma, Tm, T.norm2, target, mu0, state["sig_max"] * 1e-14, counters=state, terms=terms)
+        if got is None:
+            sig, V = torch.linalg.eigh(gamma)
+            sig = torch.clamp(sig, min=0.0)
+            Tt = Tm @ V
+            s = (Tt * Tt).sum(dim=0)
+            both = torch.stack([sig, s]).cpu().numpy()  # one device -> host copy per mode update
+            mu = _multiplier(both[0], both[1], T.norm2, target)
+            factors[m] = ((Tt / (sig + mu)) @ V.T).contiguous()
+            if state is not None:
+                state["sig_max"] = float(both[0].max())
+                state["eigh_updates"] = state.get("eigh_updates", 0) + 1
+        else:
+            mu, F, state["r"] = got
+            factors[m] = F.contiguous()
+        if state is not None:
+            state["mu"] = mu
+            state.setdefault("hist", []).append(mu)
     return factors
 
 
@@ -208,12 +354,13 @@ def parafac_epc(tensor, rank, als_maxiter=5000, als_tol=1e-5, num_threads=4, ini
     torch.cuda.synchronize(dev)
     t1 = time.perf_counter()
     stopflag, passes, rounds = 0, 0, 0
+    state = {}                                                              # last multiplier (warm start of the next update)
     lam = _intensities(factors)
     for _ in range(epc_rounds):                                             # :61
         prev = None
         rounds += 1
         for _it in range(epc_maxiter):                                      # cp_anc(maxiter, tol)  :63
-            factors = _epc_sweep(T, factors, delta)
+            factors = _epc_sweep(T, factors, delta, state)
             passes += 1
             cur = float((_intensities(factors) ** 2).sum())
             if prev is not None and abs(prev - cur) < epc_tol * prev:
@@ -231,6 +378,7 @@ def parafac_epc(tensor, rank, als_maxiter=5000, als_tol=1e-5, num_threads=4, ini
     torch.cuda.synchronize(dev)
     if info is not None:
         info.update(delta=delta, norm=math.sqrt(T.norm2), als_s=t1 - t0, epc_s=time.perf_counter() - t1,
-                    epc_passes=passes, epc_rounds=rounds)
+                    epc_passes=passes, epc_rounds=rounds, epc_chol_evals=state.get("chol_evals", 0),
+                    epc_eigh_updates=state.get("eigh_updates", 0))
     inv = np.argsort(order)
     return lam.to(tensor.device), [factors[int(i)].to(tensor.device) for i in inv]   # :77-82

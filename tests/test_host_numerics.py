@@ -239,3 +239,54 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text or "admm_oracle" in text:
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_epc_cholesky_form_equals_the_eigen_form():
+    """source/parafac_epc.py::_ridge_factor_chol (power series of the residual and of the factor around a warm-started
+    multiplier, one Cholesky factorization + explicit inverse per expansion point) against the eigen form of the same mode update (`_multiplier`, the restatement the oracle
+    pins): same multiplier and same factor to rounding, from good and from poor starts, when the constraint is
+    inactive (mu = floor), and a clean give-up (None) on a singular Gram matrix.  The dense algebra is torch.linalg, so
+    this host check runs the product's own function on CPU tensors (no libadmmq call is involved)."""
+    import math
+    import sys
+    sys.path.insert(0, PKG)
+    from source.parafac_epc import _multiplier, _ridge_factor_chol
+    g = torch.Generator().manual_seed(11)
+    worst_mu, worst_f, evals = 0.0, 0.0, []
+    for (I, R, spread) in ((40, 24, 1.0), (9, 60, 3.0), (128, 96, 2.0), (64, 134, 4.0)):
+        A = torch.randn(3 * R, R, generator=g, dtype=torch.float64) * torch.logspace(0, -spread, R, dtype=torch.float64)
+        gamma = A.T @ A
+        gamma = gamma / gamma.diagonal().max()
+        Tm = torch.randn(I, R, generator=g, dtype=torch.float64)
+        sig, V = torch.linalg.eigh(gamma)
+        sig = sig.clamp(min=0.0)
+        Tt = Tm @ V
+        s = (Tt * Tt).sum(0)
+        ls = float((s / sig).sum())                       # what the unconstrained least-squares fit explains
+        norm_y2 = ls * 1.5
+        for frac in (0.9, 0.5, 0.1):
+            target = norm_y2 - frac * ls                  # residual the multiplier has to reach (> the LS residual)
+            mu_e = _multiplier(sig.numpy(), s.numpy(), norm_y2, target)
+            F_e = (Tt / (sig + mu_e)) @ V.T
+            floor = float(sig.max()) * 1e-14
+            for start in (1.02, 0.7, 30.0):
+                cnt = {}
+                got = _ridge_factor_chol(gamma, Tm, norm_y2, target, mu_e * start, floor, max_evals=12, counters=cnt)
+                assert got is not None, (I, R, frac, start)
+                mu, F = got[0], got[1]
+                worst_mu = max(worst_mu, abs(mu - mu_e) / mu_e)
+                worst_f = max(worst_f, float((F - F_e).abs().max() / F_e.abs().max()))
+                if start == 1.02:
+                    evals.append(cnt["chol_evals"])
+        # inactive constraint: even the least-squares fit leaves more than the target -> mu = floor, F = the LS solution
+        target = (norm_y2 - ls) * 0.8
+        mu_e = _multiplier(sig.numpy(), s.numpy(), norm_y2, target)
+        got = _ridge_factor_chol(gamma, Tm, norm_y2, target, 0.05, float(sig.max()) * 1e-14, max_evals=40)
+        if got is not None:                               # (None = Cholesky of Gamma + 1e-14 I failed: eigen form takes over)
+            assert got[0] == mu_e == float(sig.max()) * 1e-14
+    assert worst_mu <= 1e-9 and worst_f <= 1e-9, (worst_mu, worst_f)
+    assert max(evals) == 1, evals                         # a 2 % warm start: ONE factorization
+    # singular Gram matrix: no exception, the caller falls back to the eigen form
+    B = torch.randn(10, 4, generator=g, dtype=torch.float64)
+    sing = (B @ B.T)
+    assert _ridge_factor_chol(sing, torch.randn(5, 10, generator=g, dtype=torch.float64), 10.0, 1.0, 0.0, 0.0) is None
