@@ -157,31 +157,42 @@ def _eye(n, like):
     return _EYE[key]
 
 
+def _moment_index(terms, device):
+    """Flat positions in the (terms + 1) x (terms + 1) Gram matrix of [Tm, F_1 .. F_terms] that hold a_1 .. a_{2 terms}:
+    a_1 = <Tm, F_1>, a_k = <F_{k // 2}, F_{k - k // 2}>.  Cached per (terms, device): no index upload per call."""
+    key = ("mom", terms, device)
+    if key not in _EYE:
+        ii = [0] + [k // 2 for k in range(2, 2 * terms + 1)]
+        jj = [1] + [k - k // 2 for k in range(2, 2 * terms + 1)]
+        _EYE[key] = torch.tensor([i * (terms + 1) + j for i, j in zip(ii, jj)], dtype=torch.long, device=device)
+    return _EYE[key]
+
+
 def _ridge_eval(gamma, Tm, mu, terms):
     """Everything the multiplier search needs around one value of mu from ONE Cholesky factorization of
     M = Gamma + mu I: the explicit inverse M^-1 = L^-T L^-1 (potrf, one triangular solve against the identity, one
     GEMM: half the time of cuSOLVER's potri-style `cholesky_inverse`), the sequence F_k = Tm M^-k, k = 1..terms (one
     float64 GEMM each, written into one buffer) and the moments a_k = tr(Tm M^-k Tm^T), k = 1..2 terms, read off the
     Gram matrix of the flattened [Tm, F_1 .. F_terms] (ONE GEMM): a_1 = <F_1, Tm>, a_{i+j} = <F_i, F_j>.
-    Returns (F buffer of shape terms x I x R, stats) with stats = [a_1 .. a_{2 terms}, ||F_1 M - Tm|| / ||Tm||, info]
-    still on the device."""
+    Returns (buffer [Tm, F_1 .. F_terms] of shape (terms + 1) x I x R, stats) with
+    stats = [a_1 .. a_{2 terms}, ||F_1 M - Tm|| / ||Tm||, info] still on the device."""
     R = gamma.shape[0]
-    M = gamma.clone()
-    M.diagonal().add_(mu)
+    eye = _eye(R, gamma)
+    M = torch.add(gamma, eye, alpha=mu)
     L, info = torch.linalg.cholesky_ex(M)
-    Li = torch.linalg.solve_triangular(L, _eye(R, L), upper=False)
+    Li = torch.linalg.solve_triangular(L, eye, upper=False)
     Minv = Li.T @ Li
     buf = torch.empty((terms + 1,) + tuple(Tm.shape), dtype=Tm.dtype, device=Tm.device)
     buf[0].copy_(Tm)
     for k in range(terms):
         torch.matmul(buf[k], Minv, out=buf[k + 1])
-    flat = buf.reshape(terms + 1, -1)
+    flat = buf.view(terms + 1, -1)
     G = flat @ flat.T                                        # G[i, j] = <F_i, F_j>, F_0 = Tm
-    idx_i = [0] + [k // 2 for k in range(2, 2 * terms + 1)]
-    idx_j = [1] + [k - k // 2 for k in range(2, 2 * terms + 1)]
-    mom = G[idx_i, idx_j]
-    chk = torch.linalg.norm(buf[1] @ M - Tm) / torch.sqrt(G[0, 0])
-    return buf[1:], torch.cat([mom, torch.stack([chk, info.to(Tm.dtype)])])
+    stats = torch.empty(2 * terms + 2, dtype=Tm.dtype, device=Tm.device)
+    torch.index_select(G.view(-1), 0, _moment_index(terms, G.device), out=stats[:2 * terms])
+    stats[2 * terms] = torch.linalg.norm(torch.addmm(Tm, buf[1], M, beta=-1.0)) / torch.sqrt(G[0, 0])
+    stats[2 * terms + 1] = info
+    return buf, stats
 
 
 def _series_residual(a, mu, d, norm_y2):
@@ -235,7 +246,7 @@ def _ridge_factor_chol(gamma, Tm, norm_y2, target, mu0, floor, max_evals=5, coun
         if glo > 0.0:                                        # ... or below it
             if mu + dlo <= floor:                            # even the least-squares fit leaves more than the target
                 if mu <= floor:
-                    return floor, Fs[0], 0.0
+                    return floor, Fs[1], 0.0
                 mu = floor
                 continue
             step = -g(0.0) / slope if slope > 0.0 else -0.75 * mu
@@ -253,15 +264,10 @@ def _ridge_factor_chol(gamma, Tm, norm_y2, target, mu0, floor, max_evals=5, coun
         d = 0.5 * (dlo + dhi)
         r = abs(d) / mu
         if r <= accept:
-            F = Fs[0]
-            if d != 0.0:
-                F = F.clone()
-                p = 1.0
-                for k in range(1, terms):
-                    p *= -d
-                    if abs(p) * a[2 * k + 1] ** 0.5 <= 1e-17 * a[1] ** 0.5:   # ||F_{k+1}|| = sqrt(a_{2k+2}): negligible from here on
-                        break
-                    F.add_(Fs[k], alpha=p)
+            if d == 0.0:
+                return mu, Fs[1], abs(mu - mu_start) / mu_start
+            coef = [0.0] + [(-d) ** k for k in range(terms)]                   # F(mu + d) = sum_k (-d)^k F_{k+1}: one GEMV
+            F = torch.mv(Fs.view(terms + 1, -1).T, torch.tensor(coef, dtype=Fs.dtype, device=Fs.device)).view(Fs.shape[1:])
             return mu + d, F, abs(mu + d - mu_start) / mu_start
         mu += d                                              # the series' root is good to ~r^(2 terms): next time |d| is tiny
         terms = 8 if r <= 0.25 else 12                       # the remaining step is ~r^(2 terms) of mu

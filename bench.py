@@ -302,6 +302,59 @@ def run_reference(args):
     return 0
 
 
+def mttkrp_roofline(problems, dev, peaks):
+    """GPU time of the tensor-core MTTKRP (scripts/factorize.py:217,227,237) on the workload's largest 3-D unit, per mode:
+    20 calls captured into one CUDA graph (no host launch gaps, transpose / split kernel included), replayed three times
+    and timed with CUDA events on the capturing stream; against the 3xTF32 roof from MEASURED_PEAKS.json."""
+    import torch
+    from source import _native as nat
+    cands = [p for p in problems if p[1].ndim == 3]
+    if not cands:
+        return None
+    name, W, rank, init = max(cands, key=lambda p: p[1].numel())[:4]
+    W = W.to(dev)
+    I, J, K = W.shape
+    fac = [f.to(dev) for f in init]
+    unf = [W.reshape(I, J * K), nat.unfold3(W, 1), nat.unfold3(W, 2)]
+    dims = [I, J, K]
+    flop = 2.0 * I * J * K * rank
+    us = []
+    for mode in range(3):
+        o = [k for k in range(3) if k != mode]
+        X, Y = fac[o[0]], fac[o[1]]
+        V = nat.permute_myx(unf[mode], X.shape[0], Y.shape[0])
+        ws = torch.empty(nat.mttkrp_tc_workspace_bytes(dims[mode], X.shape[0], Y.shape[0], rank), dtype=torch.uint8, device=dev)
+        F = torch.empty(dims[mode], rank, device=dev)
+        fn = lambda: nat.mttkrp_tc(V, dims[mode], X, Y, out=F, ws=ws)
+        fn()
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            fn()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=st):
+                for _ in range(20):
+                    fn()
+            graph.replay()
+            st.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(3):
+                graph.replay()
+            e1.record(st)
+            st.synchronize()
+        us.append(e0.elapsed_time(e1) / 60.0 * 1e3)
+    sustained = float(peaks.get("bf16_tflops_sustained", 2250.0 * 0.62)) / 6.0
+    burst = float(peaks.get("bf16_tflops", 2250.0 * 0.74)) / 6.0
+    tf = [flop / (u * 1e-6) / 1e12 for u in us]
+    return {"kernel": "k_mttkrp_fold_tc / k_mttkrp_foldlong_tc (+ transpose / split)", "unit_name": name, "shape": [I, J, K], "rank": rank,
+            "bound": "tensor", "us_per_mode": [round(u, 2) for u in us], "achieved": [round(t, 1) for t in tf], "unit": "TFLOP/s",
+            "peak": sustained, "frac": [round(t / sustained, 3) for t in tf], "peak_burst": burst,
+            "frac_of_burst": [round(t / burst, 3) for t in tf],
+            "how": "fp32-equivalent flop 2 I J K R per mode (the hardware executes 3x that in TF32) / GPU time per call in a CUDA "
+                   "graph of 20 calls (timed alone, after the sweeps); peak = MEASURED_PEAKS.json bf16 / 2 / 3"}
+
+
 def allocate_ctas(costs, sm_count, min_ctas):
     """Share of the SMs for every independent solve, proportional to its estimated cost (largest-remainder rounding,
     at least `min_ctas` each, sum == sm_count when there are enough SMs)."""
@@ -602,6 +655,12 @@ def run_native(args):
                             "note": "state is L2-resident by design (ncu: see traffic), HBM is not the binding resource"},
                     "clip_search": {"candidates_x_elements_per_s": evals / (loop_gpu_ms / 1e3),
                                     "note": "threshold form: O(1) work per element + (2^bits - 1) x candidates thresholds per CTA"}}
+
+    if roofline is not None and world == 1 and args.mttkrp_precision == 1:
+        try:
+            roofline["mttkrp"] = mttkrp_roofline(problems, dev, peaks)
+        except Exception as e:  # noqa: BLE001 - a side measurement must not take the bench line down
+            roofline["mttkrp"] = {"error": str(e)[:200]}
 
     # ---- end to end through the public API with host buffers
     e2e = None

@@ -731,7 +731,7 @@ def test_model_top1_with_our_factors_vs_reference_factors(capsys, precision):
     from source.models import get_submodule, replace_with_cp
     from source.solver import LayerSolver, layer_weight_as_tensor, rank_from_reduction_rate
     from source.utils import bncalibrate_model, top1_accuracy
-    torch.set_num_threads(8)
+    torch.set_num_threads(4)   # (8 threads crawled on a contended GPU box: OpenMP oversubscription)
     torch.manual_seed(42)
     torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False   # reproducible training run
     base = torchvision.models.resnet18(weights=None, num_classes=10).cuda()

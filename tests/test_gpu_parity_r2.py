@@ -311,6 +311,10 @@ def test_als_epc_initialisation_on_native_kernels(capsys):
     assert [tuple(u.shape) for u in Us] == [(14, 12), (10, 12), (6, 12)] and Us[0].dtype == torch.float64 and Us[0].is_cuda
     worst = max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(Us, Us_o))
     assert worst <= 1e-9 and torch.allclose(lam.cpu(), lam_o, rtol=1e-9), worst
+    # every mode update but the first took the Cholesky / series form (one factorization each, a few more while the
+    # multiplier still moves fast); the CPU restatement it is compared with above is the eigen form throughout
+    n_updates = 3 * info["epc_passes"]
+    assert info["epc_eigh_updates"] == 1 and n_updates - 1 <= info["epc_chol_evals"] <= 2 * n_updates, info
     # a CPU tensor is a host-buffer call: computed on the GPU, returned on the CPU
     np.random.seed(3)
     _, Us_h = parafac_epc(W, 12, als_maxiter=15, epc_maxiter=4, epc_rounds=2)
