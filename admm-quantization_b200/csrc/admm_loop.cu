@@ -43,7 +43,9 @@ struct LoopHeader {  // start of the workspace; zeroed by cudaMemsetAsync before
   unsigned int barrier_loop;
   unsigned int pad[3];
   unsigned int keys[kKeySlots][4];  // rotating {max key, ~min key, -, -} of V
+  unsigned int smid_mask[8];        // diagnostics: bit s is set when a CTA of the last launch ran on SM s (%smid)
 };
+static_assert(sizeof(LoopHeader) <= 256, "the header page is 256 bytes");
 
 struct IterationHeader {  // admmq_admm_iteration only: scalars handed from the inverse to the loop
   unsigned int barrier_inv;
@@ -581,6 +583,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   };
   GridBarrier bar;
   bar.init(&hdr->barrier_loop);
+  if (t == 0) {   // where the grid runs (tools / bench.py --placement read the mask from the workspace header)
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicOr(&hdr->smid_mask[(smid >> 5) & 7], 1u << (smid & 31));
+  }
   const float rho = rep.rho;
   const int R = p.R, Rp = p.Rp;
   const long long N = (long long)p.I * R;

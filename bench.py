@@ -77,6 +77,8 @@ def parse_args():
                     help="experiment knob: comma-separated SM budgets, one per layer in workload order; fixes the budgets "
                          "(no re-balancing during warm-up; single GPU)")
     ap.add_argument("--trace-layer", default=None, help="print the per-kernel-group times of this layer's last sweep")
+    ap.add_argument("--placement", action="store_true",
+                    help="report the SMs (%%smid) the last loop launch of every unit ran on (diagnostics of die / GPC locality)")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs kept out of the cooperative-grid budgets so that the ordinary kernels between the loops "
                          "(Gram, MTTKRP, projection, errors) never wait for a persistent kernel to finish")
@@ -684,6 +686,15 @@ def run_native(args):
         cnt = rk.reduce(done_e2e, "SUM")
         e2e = {"value": cnt / (tot / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(rk.reduce(h2d, "SUM")),
                "d2h_bytes_per_step": int(rk.reduce(d2h, "SUM")), "ms_per_step": tot / args.steps}
+
+    if args.placement:
+        torch.cuda.synchronize()
+        import numpy as np
+        for (key, *_), sv in zip(problems, solvers):
+            ms = sweep_ms.get(key, float("nan"))
+            words = sv.ws_loop[64:96].cpu().numpy().view(np.uint32)
+            smids = [32 * w + b for w in range(8) for b in range(32) if (int(words[w]) >> b) & 1]
+            print(f"[placement] {key:16s} {ms:7.1f} ms  {len(smids):3d} SMs: {smids}", file=sys.stderr, flush=True)
 
     # ---- the job's only collective: final factor gather over NCCL (once per job, outside the timed region)
     gather_ms, gather_bytes = rk.gather_factors([f for s in solvers for f in s.factors])
