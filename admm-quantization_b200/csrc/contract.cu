@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(kCT) k_mttkrp_f64(const TI* __restrict__ Wn, i
                                                    int ny, int R, long long p_per_split,
                                                    double* __restrict__ partial, TO* __restrict__ F) {
   constexpr int BN = 64;
-  constexpr int TM = BM / 16;  // rows per thread (16 x 16 thread grid, 4 columns per thread)
+  constexpr int TM = BM / 16;  // rows per thread (16 x 16 thread grid); thread tx owns the columns tx, tx + 16, tx + 32, tx + 48:
+                               // a half warp reads 16 consecutive doubles of the Khatri-Rao slab (tx * 4 + b was a 4-way bank
+                               // conflict: 0.556 -> 0.435 ms on the 512 x 4608 x 1141 float64 MTTKRP; same sums, same order)
   __shared__ double sw[kBK][BM + 1], skr[kBK][BN + 2];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(kCT) k_mttkrp_f64(const TI* __restrict__ Wn, i
     for (int kk = 0; kk < kBK; ++kk) {
       double bv[4];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = skr[kk][tx * 4 + b];
+      for (int b = 0; b < 4; ++b) bv[b] = skr[kk][tx + 16 * b];
 #pragma unroll
       for (int a = 0; a < TM; ++a) {
         const double av = sw[kk][ty * TM + a];
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kCT) k_mttkrp_f64(const TI* __restrict__ Wn, i
   for (int a = 0; a < TM; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int m = m0 + ty * TM + a, r = n0 + tx * 4 + b;
+      const int m = m0 + ty * TM + a, r = n0 + tx + 16 * b;
       if (m < M && r < R) {
         if (gridDim.z == 1) F[(size_t)m * R + r] = (TO)acc[a][b];
         else partial[((size_t)blockIdx.z * M + m) * R + r] = acc[a][b];

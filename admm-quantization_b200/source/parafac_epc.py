@@ -151,9 +151,15 @@ _EYE = {}
 
 
 def _eye(n, like):
+    """Identity cached per (n, device).  The cache is shared by the host threads that initialise several layers
+    concurrently, each on its own stream: the creating stream is synchronised once so that no other stream can read
+    the constant before it is written."""
     key = (n, like.device)
     if key not in _EYE:
-        _EYE[key] = torch.eye(n, dtype=like.dtype, device=like.device)
+        e = torch.eye(n, dtype=like.dtype, device=like.device)
+        if e.is_cuda:
+            torch.cuda.current_stream(e.device).synchronize()
+        _EYE[key] = e
     return _EYE[key]
 
 
@@ -164,7 +170,10 @@ def _moment_index(terms, device):
     if key not in _EYE:
         ii = [0] + [k // 2 for k in range(2, 2 * terms + 1)]
         jj = [1] + [k - k // 2 for k in range(2, 2 * terms + 1)]
-        _EYE[key] = torch.tensor([i * (terms + 1) + j for i, j in zip(ii, jj)], dtype=torch.long, device=device)
+        idx = torch.tensor([i * (terms + 1) + j for i, j in zip(ii, jj)], dtype=torch.long, device=device)
+        if idx.is_cuda:
+            torch.cuda.current_stream(idx.device).synchronize()   # shared across streams, see _eye
+        _EYE[key] = idx
     return _EYE[key]
 
 
