@@ -555,8 +555,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LoopSmem<BM, BN, TCBN>& sm = *reinterpret_cast<LoopSmem<BM, BN, TCBN>*>(smem_raw);
   __shared__ tc::Pipe pipe;
+  __shared__ unsigned int cta_keys[2];   // this CTA's {max key, ~min key} of V, merged here before they go to the header
   tc::PipeState pst;
   const int t = threadIdx.x;
+  if (t < 2) cta_keys[t] = 0u;           // (visible to all warps after the barrier that ends the prologue)
   LoopHeader* hdr = p.hdr;
   admmq_loop_report rep;
   rep.iterations = 0;
@@ -666,11 +668,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_admm_loop(const __grid_constant
   for (int j = 1; j < p.max_iter; ++j) {  // range(1, max_iter), :55
     const int slot = j % kKeySlots, next_slot = (j + 1) % kKeySlots;
     // ---------------- P1
-    if constexpr (TCBN > 0) gemm_phase_tc<TCBN>(p, sm.tc_tiles, pipe, pst, hdr->keys[slot]);
-    else if constexpr (TCBN == kDiagP1) elementwise_phase(p, rho, e0, e1, hdr->keys[slot]);
-    else if constexpr (TCBN == kF64P1) gemm_phase_f64<BM, BN, TM, TN>(p, sm.gemm64, hdr->keys[slot]);
-    else if constexpr (TCBN < 0) gemm_phase_skinny<-TCBN>(p, sm.skinny, hdr->keys[slot]);
-    else gemm_phase<BM, BN, TM, TN>(p, sm.gemm, hdr->keys[slot]);
+    // the warps' min / max keys are merged in shared memory first: two global atomics per CTA instead of two per warp
+    // (a grid of 148 CTAs otherwise sends 4.7 k atomics to the same two L2 words every iteration)
+    if constexpr (TCBN > 0) gemm_phase_tc<TCBN>(p, sm.tc_tiles, pipe, pst, cta_keys);
+    else if constexpr (TCBN == kDiagP1) elementwise_phase(p, rho, e0, e1, cta_keys);
+    else if constexpr (TCBN == kF64P1) gemm_phase_f64<BM, BN, TM, TN>(p, sm.gemm64, cta_keys);
+    else if constexpr (TCBN < 0) gemm_phase_skinny<-TCBN>(p, sm.skinny, cta_keys);
+    else gemm_phase<BM, BN, TM, TN>(p, sm.gemm, cta_keys);
+    __syncthreads();
+    if (t == 0) {
+      if ((cta_keys[0] | cta_keys[1]) != 0u) {
+        atomicMax(&hdr->keys[slot][0], cta_keys[0]);
+        atomicMax(&hdr->keys[slot][1], cta_keys[1]);
+      }
+      cta_keys[0] = cta_keys[1] = 0u;
+    }
     if (blockIdx.x == 0) {  // recycle the accumulators of iteration j+1 (last read in iteration j-2)
       if (t < 4) hdr->keys[next_slot][t] = 0u;
       for (int c = t; c < p.Nc; c += kThreads) p.cand[(size_t)next_slot * kMaxCandidates + c] = 0ull;

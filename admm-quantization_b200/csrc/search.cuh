@@ -540,7 +540,9 @@ __device__ inline void cta_candidate_sums(const float* __restrict__ v, long long
   const long long stages = (elems + kStageCap - 1) / kStageCap;
   // ... and below `direct_below` elements per CTA the fixed costs of the threshold form (zeroing and scanning 8192 bins,
   // (2^bits - 1) x candidates thresholds however few elements there are) dominate: small factors spread over many CTAs
-  const bool direct_is_cheaper = (long long)((1 << bits) - 1) * stages * kPairsPerElement > elems || elems <= direct_below;
+  // (up to 4 bits = 15 thresholds the threshold form is never the slower one: measured inside the loop 10.8 against 13.4 us
+  // per iteration at 214 elements per CTA, and equal in the stand-alone search at 285, profiles/r1g_search_crossover.txt)
+  const bool direct_is_cheaper = (bits > 4 && (long long)((1 << bits) - 1) * stages * kPairsPerElement > elems) || elems <= direct_below;
   const bool want_direct = form == kFormDirect || (form == kFormAuto && direct_is_cheaper);
   if (!want_direct && binned_range_ok(absmax))
     cta_candidate_sums_binned(v, e0, e1, absmax, Nc, L, bits, n_total, cand_sums, sm.binned);
