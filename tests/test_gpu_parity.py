@@ -527,7 +527,16 @@ def test_outer_loop_against_reference_history(golden_outer, capsys, precision):
         print(f"\n[outer] precision {precision} rel. diff of rec_error per sweep:", np.array2string(rel, precision=2),
               "quant:", np.array2string(relq, precision=2))
     assert rel[0] <= 1e-3 and relq[0] <= 1e-3 and rel[1] <= 1e-3
-    assert rel.max() <= 2e-2  # beyond sweep 1 the reference diverges from itself at this level
+    # From sweep 2 on the yardstick is the UNMODIFIED reference against itself on this very configuration when the output
+    # of its own ridge solve is jittered by +-3e-7 / +-6e-8 per inner iteration (tests/golden/short_divergence.npz, made by
+    # oracle/make_golden.py --only short_divergence: spread 2.9e-4, 7.9e-4, 3.6e-3, 3.1e-3 in sweeps 2 .. 5): every sweep
+    # within north_star's 1e-3 or twice that spread, whichever is larger - no blanket bound.
+    sd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "short_divergence.npz"))
+    trials = [k for k in sd.files if k.endswith("/loss")]
+    spread = np.max([np.abs(sd[k] - ref) / ref for k in trials], axis=0)
+    spreadq = np.max([np.abs(sd[k + "q"] - refq) / refq for k in trials], axis=0)
+    assert len(trials) == 8 and np.all(rel <= np.maximum(1e-3, 2 * spread)), (rel, spread)
+    assert np.all(relq <= np.maximum(1e-3, 2 * spreadq)), (relq, spreadq)
     # 2-D branch
     mm = go.case("mat")
     s2 = LayerSolver(dev(go["mat/W"]), [dev(go["mat/init0"]), dev(go["mat/init1"])], mm["bits"], mm["qscheme"],
