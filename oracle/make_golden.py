@@ -430,6 +430,27 @@ def short_divergence_cases(ref):
             out[f"trial{trial}/loss"], out[f"trial{trial}/lossq"] = np.array(loss), np.array(lossq)
             meta.append(dict(name=f"trial{trial}", noise_seed=noise_seed, eps=eps, sweeps=6, max_iter_admm=60))
             print("short-budget self-divergence trial", trial, eps, loss, flush=True)
+        # ... and for the 2-D branch (scripts/factorize.py:269-310): the `mat` case of outer_loop.npz, same jitter
+        g = torch.Generator().manual_seed(9)
+        Wm = torch.randn(128, 48, generator=g) * 0.02
+        for trial, (eps, noise_seed) in enumerate(trials):
+            gn = torch.Generator().manual_seed(noise_seed + 100)
+
+            def jittered2(b, L, upper=False):
+                x = real_solve(b, L, upper=upper)
+                sign = torch.randint(0, 2, x.shape, generator=gn).float() * 2 - 1
+                return x * (1 + eps * sign)
+
+            torch.cholesky_solve = jittered2
+            A, B = ref.init_factors(Wm, 17, init="random", device=None, seed=3)
+            U_A, U_B = torch.zeros_like(A), torch.zeros_like(B)
+            loss = []
+            for _ in range(5):
+                A, U_A = ref.admm_iteration(A, U_A, Wm @ B, B.T @ B, max_iter=80, eps=1e-8, bits=4, qscheme=MSE)
+                B, U_B = ref.admm_iteration(B, U_B, Wm.T @ A, A.T @ A, max_iter=80, eps=1e-8, bits=4, qscheme=MSE)
+                loss.append(ref.squared_relative_diff(Wm, A @ B.T))
+            out[f"mat_trial{trial}/loss"] = np.array(loss)
+            print("2-D self-divergence trial", trial, eps, loss, flush=True)
     finally:
         torch.cholesky_solve = real_solve
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

@@ -532,7 +532,7 @@ def test_outer_loop_against_reference_history(golden_outer, capsys, precision):
     # oracle/make_golden.py --only short_divergence: spread 2.9e-4, 7.9e-4, 3.6e-3, 3.1e-3 in sweeps 2 .. 5): every sweep
     # within north_star's 1e-3 or twice that spread, whichever is larger - no blanket bound.
     sd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "short_divergence.npz"))
-    trials = [k for k in sd.files if k.endswith("/loss")]
+    trials = [k for k in sd.files if k.startswith("trial") and k.endswith("/loss")]
     spread = np.max([np.abs(sd[k] - ref) / ref for k in trials], axis=0)
     spreadq = np.max([np.abs(sd[k + "q"] - refq) / refq for k in trials], axis=0)
     assert len(trials) == 8 and np.all(rel <= np.maximum(1e-3, 2 * spread)), (rel, spread)
@@ -544,7 +544,12 @@ def test_outer_loop_against_reference_history(golden_outer, capsys, precision):
     for _ in range(mm["sweeps"]):
         s2.sweep()
     rel2 = np.abs(np.array(s2.loss_hist) - go["mat/loss"]) / go["mat/loss"]
-    assert rel2[0] <= 1e-3 and rel2.max() <= 2e-2
+    with capsys.disabled():
+        print(f"[outer] precision {precision} 2-D case, rel. diff of rec_error per sweep:", np.array2string(rel2, precision=2))
+    # the reference does not move on this case under the same jitter (mat_trial* of short_divergence.npz: <= 9e-8 in all
+    # five sweeps), so every sweep is held to north_star's 1e-3
+    spread2 = np.max([np.abs(sd[k] - go["mat/loss"]) / go["mat/loss"] for k in sd.files if k.startswith("mat_trial")], axis=0)
+    assert spread2.max() <= 1e-6 and rel2.max() <= 1e-3, (rel2, spread2)
 
 
 def test_outer_loop_with_tensor_core_mttkrp(golden_outer):
