@@ -552,8 +552,9 @@ def test_outer_loop_against_reference_history(golden_outer, capsys, precision):
     assert spread2.max() <= 1e-6 and rel2.max() <= 1e-3, (rel2, spread2)
 
 
-def test_outer_loop_with_tensor_core_mttkrp(golden_outer):
-    """Throughput configuration (3xTF32 MTTKRP + 3xTF32 ridge product): first sweeps track the reference history."""
+def test_outer_loop_with_tensor_core_mttkrp(golden_outer, capsys):
+    """Throughput configuration (3xTF32 MTTKRP + 3xTF32 ridge product): the first three sweeps track the reference
+    history within north_star's 1e-3 (the reference's own spread there is <= 2.9e-4, short_divergence.npz)."""
     from source.solver import LayerSolver
     go = golden_outer
     m = go.case("config1_short")
@@ -563,7 +564,9 @@ def test_outer_loop_with_tensor_core_mttkrp(golden_outer):
     for _ in range(3):
         s.sweep()
     rel = np.abs(np.array(s.loss_hist) - go["config1_short/loss"][:3]) / go["config1_short/loss"][:3]
-    assert rel[0] <= 1e-3 and rel.max() <= 2e-2, rel
+    with capsys.disabled():
+        print("\n[outer] throughput mode (tensor-core MTTKRP + ridge product), rel. diff of rec_error per sweep:", np.array2string(rel, precision=2))
+    assert rel.max() <= 1e-3, rel
 
 
 @pytest.mark.parametrize("precision", [0, 1])
