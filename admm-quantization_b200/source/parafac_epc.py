@@ -148,6 +148,7 @@ def _multiplier(sig_c, s_c, norm_y2, target):
 
 
 _EYE = {}
+_EYE_LOCK = __import__("threading").Lock()     # layers are initialised concurrently on host threads (bench.py --full)
 
 
 def _eye(n, like):
@@ -155,12 +156,16 @@ def _eye(n, like):
     concurrently, each on its own stream: the creating stream is synchronised once so that no other stream can read
     the constant before it is written."""
     key = (n, like.device)
-    if key not in _EYE:
+    e = _EYE.get(key)
+    if e is None:
         e = torch.eye(n, dtype=like.dtype, device=like.device)
         if e.is_cuda:
             torch.cuda.current_stream(e.device).synchronize()
-        _EYE[key] = e
-    return _EYE[key]
+        with _EYE_LOCK:
+            while sum(1 for k in _EYE if k[0] != "mom") >= 16:  # a sweep over many ranks must not pin one n x n matrix each
+                _EYE.pop(next(k for k in _EYE if k[0] != "mom"), None)
+            _EYE[key] = e
+    return e
 
 
 def _moment_index(terms, device):
@@ -173,7 +178,8 @@ def _moment_index(terms, device):
         idx = torch.tensor([i * (terms + 1) + j for i, j in zip(ii, jj)], dtype=torch.long, device=device)
         if idx.is_cuda:
             torch.cuda.current_stream(idx.device).synchronize()   # shared across streams, see _eye
-        _EYE[key] = idx
+        with _EYE_LOCK:
+            _EYE[key] = idx
     return _EYE[key]
 
 
